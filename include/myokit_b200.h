@@ -1,0 +1,191 @@
+/*
+ * myokit_b200.h — C ABI of libmyokit_b200.so: the B200 (sm_100a) back-end for
+ * the multi-cell time-stepping path of myokit.SimulationOpenCL.
+ *
+ * The reference's native boundary for this path is a generated CPython
+ * extension exporting exactly sim_init / sim_step / sim_clean
+ * (myokit/_sim/openclsim.c:1216-1221). The entry points below are what a
+ * binding for that path would call instead; they take plain pointers and
+ * sizes, no Python and no torch types:
+ *
+ *   reference (file:line)                            this library
+ *   -----------------------------------------------  ---------------------------
+ *   clBuildProgram of the rendered kernel            mkb_jit_compile
+ *     (openclsim.c:815-836)
+ *   sim_init, 21 arguments (openclsim.c:309-1031,    mkb_sim_init(mkb_sim_config)
+ *     format string :385-407)
+ *   sim_step (openclsim.c:1036-1211)                 mkb_sim_step
+ *   log lists appended per sample (:1122-1131)       mkb_sim_log_view
+ *   state_out filled in place (:1185-1190)           mkb_sim_get_state
+ *   sim_clean (openclsim.c:216-304)                  mkb_sim_clean
+ *   ESys_* pacing (pacing.h:240-600)                 events passed as doubles in
+ *                                                    mkb_sim_config; mkb_pacing_probe
+ *   mcl_select_device / mcl_info (mcl.h:265,823)     mkb_device_count / mkb_device_info
+ *
+ * All functions return 0 on success and a negative code on failure unless
+ * stated otherwise; mkb_last_error() returns a message for the calling thread.
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with MKB_ERR_CUDA.
+ */
+#ifndef MYOKIT_B200_H
+#define MYOKIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKB_ABI_VERSION 1
+
+/* Error codes */
+#define MKB_OK               0
+#define MKB_ERR_INVALID     -1   /* bad argument */
+#define MKB_ERR_CUDA        -2   /* CUDA runtime / driver error (no device, OOM, launch) */
+#define MKB_ERR_JIT         -3   /* NVRTC compilation failed (see log) */
+#define MKB_ERR_PACING      -4   /* pacing error other than simultaneous events */
+#define MKB_ERR_SIMULTANEOUS -5  /* myokit.SimultaneousProtocolEventError (pacing.h:112) */
+#define MKB_ERR_STATE       -6   /* call out of order (not initialised / finished) */
+
+/* Precision constants: same values as myokit.SINGLE_PRECISION / DOUBLE_PRECISION */
+#define MKB_SINGLE 32
+#define MKB_DOUBLE 64
+
+/* Diffusion modes */
+#define MKB_DIFF_NONE        0   /* diffusion=False: every cell paced (openclsim.cl:329) */
+#define MKB_DIFF_HOMOGENEOUS 1   /* set_conductance      (openclsim.cl:384-435) */
+#define MKB_DIFF_FIELD       2   /* set_conductance_field (openclsim.cl:452-487) */
+#define MKB_DIFF_CONNECTIONS 3   /* set_connections      (openclsim.cl:537-573) */
+
+/* Log column kinds; `index` uses the REFERENCE's array-of-structs numbering
+ * (openclsim.c:936-1001) so a binding can reuse the reference's key table. */
+#define MKB_LOG_TIME  0          /* global, (Real)engine_time */
+#define MKB_LOG_PACE  1          /* global, (Real)engine_pace */
+#define MKB_LOG_IDIFF 2          /* index = cid */
+#define MKB_LOG_STATE 3          /* index = cid * n_state + k */
+#define MKB_LOG_INTER 4          /* index = cid * n_inter + k */
+
+typedef struct mkb_sim mkb_sim;
+
+typedef struct mkb_device_info_t {
+    char name[256];
+    int cc_major, cc_minor;
+    int sm_count;
+    int clock_khz;
+    size_t total_mem;
+    size_t l2_bytes;
+    size_t smem_per_block_optin;
+} mkb_device_info_t;
+
+typedef struct mkb_sim_config {
+    int abi_version;            /* MKB_ABI_VERSION */
+    int device;                 /* CUDA device ordinal */
+    int precision;              /* MKB_SINGLE | MKB_DOUBLE: arithmetic type Real */
+    int host_precision;         /* dtype of state_in/field_data/gx_field/gy_field/conn_g
+                                   and of mkb_sim_get_state: MKB_DOUBLE (the reference's
+                                   Python floats) or equal to `precision` */
+
+    /* Compiled model kernel (from mkb_jit_compile) */
+    const void* cubin;
+    size_t cubin_size;
+    const char* kernel_name;    /* "mkb_cell_step" */
+    int block_x, block_y;       /* thread-block tile the kernel was generated for */
+
+    /* Model shape */
+    int n_state;
+    int i_vm;                   /* index of membrane potential in the state (diffusion on) */
+    int n_inter;                /* logged intermediary variables */
+    int n_field;                /* set_field variables */
+
+    /* Geometry: cid = ix + iy * nx (openclsim.cl:316) */
+    uint64_t nx, ny;
+    int diffusion_mode;         /* MKB_DIFF_* */
+    double gx, gy;
+    const void* gx_field;       /* [ny][nx-1] */
+    const void* gy_field;       /* [ny-1][nx], may be null when ny == 1 */
+    uint64_t n_connections;     /* edges (i < j, g), openclsim.py:1405-1449 */
+    const uint64_t* conn_i;
+    const uint64_t* conn_j;
+    const void* conn_g;
+
+    /* Pacing */
+    int pace_rect;              /* 1: rectangle below; 0: explicit list */
+    int64_t pace_nx, pace_ny, pace_x, pace_y;   /* openclsim.py:1569-1593 */
+    uint64_t n_paced;           /* explicit list (openclsim.py:1612-1629) */
+    const uint64_t* paced_cells;
+    int n_events;               /* protocol events, 5 doubles each: */
+    const double* events;       /* level, start, duration, period, multiplier */
+
+    /* Time */
+    double tmin, tmax;
+    double dt;                  /* default step size */
+    double log_interval;
+
+    /* Initial data, reference layouts */
+    const void* state_in;       /* [n_cells * n_state], state_in[cid * n_state + k] */
+    const void* field_data;     /* [n_cells * n_field], field_data[cid * n_field + k] */
+
+    /* Logging */
+    uint64_t n_log;
+    const int32_t* log_kind;    /* MKB_LOG_* */
+    const uint64_t* log_index;
+
+    /* Row-slab sharding (multi-GPU); single GPU: iy_offset = 0, ny_global = ny */
+    uint64_t iy_offset;
+    uint64_t ny_global;
+
+    /* Tuning (0 = default) */
+    uint64_t steps_per_call;    /* steps before mkb_sim_step returns (openclsim.c:1046-1047) */
+    int use_graphs;             /* 1: replay batches of steps as CUDA graphs */
+} mkb_sim_config;
+
+/* ---- library ---- */
+int mkb_abi_version(void);
+const char* mkb_last_error(void);
+void mkb_free(void* p);
+
+/* ---- devices (replaces mcl.h device selection / info) ---- */
+int mkb_device_count(void);                                 /* < 0 on error */
+int mkb_device_info(int device, mkb_device_info_t* out);
+
+/* ---- JIT ---- */
+/* Text of the device ABI header generated kernels #include as "mkb_device_abi.h". */
+const char* mkb_device_abi_header(void);
+/* Compiles CUDA C++ `source` to an sm_100a cubin with NVRTC. `options` is a
+ * NUL-separated, double-NUL-terminated list of extra NVRTC options or NULL.
+ * On return *cubin (malloc'ed, free with mkb_free) holds the image and *log
+ * (malloc'ed, may be empty) the compiler log, also on failure. */
+int mkb_jit_compile(const char* source, const char* options,
+                    void** cubin, size_t* cubin_size, char** log);
+
+/* ---- simulation (replaces sim_init / sim_step / sim_clean) ---- */
+int mkb_sim_init(const mkb_sim_config* cfg, mkb_sim** out);
+/* Runs up to steps_per_call time steps. Returns 1 while t < tmax, 0 when the
+ * run has finished (final state available), < 0 on error. *engine_time gets
+ * the current time. *halted (may be null) is set when a NaN was found in the
+ * first state of cell 0 at a logged step (openclsim.c:1087). */
+int mkb_sim_step(mkb_sim* sim, double* engine_time, int* halted);
+/* Logged rows so far: pinned host matrix of Real; element (r, c) of the log is
+ * data[r * row_stride + c] for c < cols (= n_log). Valid until mkb_sim_clean
+ * or the next mkb_sim_step. */
+int mkb_sim_log_view(mkb_sim* sim, const void** data, uint64_t* rows, uint64_t* cols,
+                     uint64_t* row_stride);
+/* Copies the state, reference layout [cid * n_state + k], host_precision. */
+int mkb_sim_get_state(mkb_sim* sim, void* state_out);
+/* Counters: kernels launched by this library for this simulation, steps taken. */
+int mkb_sim_counters(mkb_sim* sim, uint64_t* kernel_launches, uint64_t* steps);
+/* Device time (ms) spent between the first and last step kernel of the calls
+ * made so far, measured with CUDA events on the launching stream. */
+int mkb_sim_device_ms(mkb_sim* sim, double* ms);
+void mkb_sim_clean(mkb_sim* sim);
+
+/* ---- pacing alone (unit tests; mirrors tests/ansic_event_based_pacing.c) ---- */
+int mkb_pacing_probe(double t0, int n_events, const double* events,
+                     int n_times, const double* times,
+                     double* levels, double* next_times);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,63 @@
+/*
+ * mkb_device_abi.h — structs shared by the host runtime (mkb_runtime.cu) and
+ * the generated model kernels (myokit_b200/kernelgen.py). The runtime embeds
+ * this text and hands it to NVRTC as the virtual header "mkb_device_abi.h", so
+ * there is exactly one definition.
+ *
+ * Layout in HBM (one GPU / one row slab):
+ *   state   n_state planes of `stride` Reals, structure-of-arrays:
+ *           state[k * stride + cid], cid = ix + iy * nx (x fastest, as the
+ *           reference's cell ids, myokit/_sim/openclsim.cl:316). `stride` is
+ *           the cell count rounded up to 32 elements so every plane starts
+ *           128-byte aligned.
+ *   V       the membrane-potential plane is double-buffered (v_in = V(t),
+ *           v_out = V(t+dt)); the fused kernel reads neighbours' V(t) while
+ *           writing V(t+dt). The reference needs two kernels and an idiff
+ *           round trip for the same effect (openclsim.c:1066-1096).
+ *   idiff   one plane, written only on logged steps (flag bit 0)
+ *   inter   n_inter planes of logged intermediary variables (same flag)
+ *   field   n_field planes of per-cell constants (set_field)
+ *   gx, gy  conductance fields in the reference's layout:
+ *           gx[(ny, nx-1)], gy[(ny-1, nx)] row-major (openclsim.py:1380-1384)
+ */
+#ifndef MKB_DEVICE_ABI_H
+#define MKB_DEVICE_ABI_H
+
+#define MKB_FLAG_STORE_AUX 1u   /* write idiff + logged intermediaries */
+
+/* One entry per time step in the device schedule ring. Host doubles; the
+ * kernel casts to Real exactly like openclsim.c:1063,1148,1155. */
+struct MkbStepParams {
+    double time;
+    double dt;
+    double pace;
+    unsigned int flags;
+    unsigned int reserved;
+};
+
+struct MkbGridArgs {
+    void* state;                    /* Real[n_state][stride] */
+    void* idiff;                    /* Real[stride] */
+    void* inter;                    /* Real[n_inter][stride] */
+    const void* field;              /* Real[n_field][stride] */
+    const void* gx_field;           /* Real[ny][nx-1] or null */
+    const void* gy_field;           /* Real[ny-1][nx] or null */
+    const unsigned char* paced_mask;/* [n] or null (rectangle in use) */
+    /* connections as CSR over cells (deterministic gather) */
+    const unsigned long long* csr_row;  /* [n+1] */
+    const unsigned int* csr_col;        /* [nnz] */
+    const void* csr_g;                  /* Real[nnz], signed per CSR entry */
+    /* V rows owned by neighbouring slabs (multi-GPU), else null */
+    const void* halo_lo;            /* Real[nx]: global row iy_offset-1 */
+    const void* halo_hi;            /* Real[nx]: global row iy_offset+ny */
+    unsigned long long nx;          /* cells in x */
+    unsigned long long ny;          /* rows in this slab */
+    unsigned long long stride;      /* plane stride in elements */
+    unsigned long long iy_offset;   /* first global row of this slab */
+    unsigned long long ny_global;   /* rows in the whole grid */
+    double gx, gy;                  /* homogeneous conductances */
+    long long pace_x0, pace_x1;     /* paced rectangle [x0,x1) x [y0,y1) */
+    long long pace_y0, pace_y1;
+};
+
+#endif

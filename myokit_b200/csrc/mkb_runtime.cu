@@ -1,0 +1,1068 @@
+// mkb_runtime.cu — host runtime + fixed helper kernels of libmyokit_b200.so.
+//
+// Replaces the reference's generated host driver for SimulationOpenCL
+// (myokit/_sim/openclsim.c): device setup and buffers (sim_init, :309-1031),
+// the time loop (sim_step, :1036-1211) and teardown (sim_clean, :216-304),
+// re-designed for one B200:
+//   * the model kernel arrives as an sm_100a cubin (NVRTC, mkb_jit_compile)
+//     and is ONE fused launch per time step (stencil + cell update) instead of
+//     the reference's diffusion kernel + cell kernel + 3 clSetKernelArg;
+//   * per-step scalars (time, dt, pace, flags) are written ahead into a device
+//     ring, so launches carry no per-step host state and batches of steps can
+//     be replayed as CUDA graphs;
+//   * state is structure-of-arrays with a double-buffered V plane;
+//   * logging is a strided device gather into a device row ring that a side
+//     stream drains into pinned host memory — never a full-state copy per log
+//     point (the reference does one, openclsim.c:1083);
+//   * the host never synchronises inside a batch; NaN detection
+//     (openclsim.c:1087) rides along as a hidden log column.
+//
+// No CPU fallback exists: every compute entry point fails with MKB_ERR_CUDA
+// when there is no device.
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/myokit_b200.h"
+#include "mkb_device_abi.h"
+#include "mkb_pacing.hpp"
+
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------------------
+// Errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                        \
+    do {                                                                      \
+        cudaError_t e_ = (expr);                                              \
+        if (e_ != cudaSuccess) {                                              \
+            return fail(MKB_ERR_CUDA, "CUDA error %d (%s) at %s:%d: %s",      \
+                        (int)e_, cudaGetErrorName(e_), __FILE__, __LINE__,    \
+                        cudaGetErrorString(e_));                              \
+        }                                                                     \
+    } while (0)
+
+static const char* const kDeviceAbiText =
+#include "mkb_device_abi_text.inc"
+    ;
+
+// ---------------------------------------------------------------------------
+// Fixed helper kernels (data movement only; the model kernel is generated)
+// ---------------------------------------------------------------------------
+
+// Reference layout aos[(c0 + c) * nvar + k]  ->  planes[k * stride + c0 + c].
+// One thread per (cell, k), k fastest: coalesced reads of the staging chunk.
+template <typename TH, typename TR>
+__global__ void k_aos_to_soa(const TH* __restrict__ aos, TR* __restrict__ planes,
+                             u64 c0, u64 ncells, int nvar, u64 stride) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    u64 total = ncells * (u64)nvar;
+    for (; i < total; i += (u64)gridDim.x * blockDim.x) {
+        u64 c = i / nvar;
+        int k = (int)(i - c * nvar);
+        planes[(u64)k * stride + c0 + c] = (TR)aos[i];
+    }
+}
+
+// planes -> aos chunk; plane `i_vm` is read from `v_cur` (ping-pong buffer).
+template <typename TR, typename TH>
+__global__ void k_soa_to_aos(const TR* __restrict__ planes, const TR* __restrict__ v_cur,
+                             int i_vm, TH* __restrict__ aos, u64 c0, u64 ncells,
+                             int nvar, u64 stride) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    u64 total = ncells * (u64)nvar;
+    for (; i < total; i += (u64)gridDim.x * blockDim.x) {
+        u64 c = i / nvar;
+        int k = (int)(i - c * nvar);
+        TR val = (k == i_vm) ? v_cur[c0 + c] : planes[(u64)k * stride + c0 + c];
+        aos[i] = (TH)val;
+    }
+}
+
+template <typename TH, typename TR>
+__global__ void k_convert(const TH* __restrict__ in, TR* __restrict__ out, u64 n) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    for (; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (TR)in[i];
+}
+
+// Strided log gather: row[col[j]] = src[off[j]]. Offsets are element offsets
+// from `base` (all planes live in one allocation); bit 63 marks an entry of
+// the ping-pong V plane, resolved against `v_cur`.
+struct GatherEntry {
+    u64 off;
+    unsigned int col;
+    unsigned int pad;
+};
+#define MKB_GATHER_V (1ull << 63)
+
+template <typename TR>
+__global__ void k_log_gather(const TR* __restrict__ base, const TR* __restrict__ v_cur,
+                             const GatherEntry* __restrict__ tab, u64 n,
+                             TR* __restrict__ row) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    for (; i < n; i += (u64)gridDim.x * blockDim.x) {
+        GatherEntry e = tab[i];
+        TR val = (e.off & MKB_GATHER_V) ? v_cur[e.off & ~MKB_GATHER_V] : base[e.off];
+        row[e.col] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Library-level API
+// ---------------------------------------------------------------------------
+extern "C" int mkb_abi_version(void) { return MKB_ABI_VERSION; }
+extern "C" const char* mkb_last_error(void) { return g_error.c_str(); }
+extern "C" void mkb_free(void* p) { free(p); }
+extern "C" const char* mkb_device_abi_header(void) { return kDeviceAbiText; }
+
+extern "C" int mkb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        return fail(MKB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+extern "C" int mkb_device_info(int device, mkb_device_info_t* out) {
+    if (!out) return fail(MKB_ERR_INVALID, "out is null");
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    memset(out, 0, sizeof(*out));
+    snprintf(out->name, sizeof(out->name), "%s", p.name);
+    out->cc_major = p.major;
+    out->cc_minor = p.minor;
+    out->sm_count = p.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    out->clock_khz = khz;
+    out->total_mem = p.totalGlobalMem;
+    out->l2_bytes = (size_t)p.l2CacheSize;
+    out->smem_per_block_optin = p.sharedMemPerBlockOptin;
+    return MKB_OK;
+}
+
+extern "C" int mkb_jit_compile(const char* source, const char* options,
+                               void** cubin, size_t* cubin_size, char** log) {
+    if (!source || !cubin || !cubin_size) return fail(MKB_ERR_INVALID, "null argument");
+    *cubin = nullptr;
+    *cubin_size = 0;
+    if (log) *log = nullptr;
+    nvrtcProgram prog;
+    const char* hdr_src[] = {kDeviceAbiText};
+    const char* hdr_name[] = {"mkb_device_abi.h"};
+    nvrtcResult r = nvrtcCreateProgram(&prog, source, "mkb_model.cu", 1, hdr_src, hdr_name);
+    if (r != NVRTC_SUCCESS) return fail(MKB_ERR_JIT, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    std::vector<const char*> opts;
+    opts.push_back("--gpu-architecture=sm_100a");
+    opts.push_back("--std=c++17");
+    opts.push_back("-lineinfo");
+    opts.push_back("-default-device");
+    if (options) {
+        for (const char* o = options; *o; o += strlen(o) + 1) opts.push_back(o);
+    }
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    std::string logtext(log_size ? log_size : 1, '\0');
+    if (log_size) nvrtcGetProgramLog(prog, &logtext[0]);
+    if (log) {
+        *log = (char*)malloc(logtext.size() + 1);
+        memcpy(*log, logtext.c_str(), strlen(logtext.c_str()) + 1);
+    }
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return fail(MKB_ERR_JIT, "NVRTC compilation failed (%s):\n%s", nvrtcGetErrorString(r),
+                    logtext.c_str());
+    }
+    size_t n = 0;
+    r = nvrtcGetCUBINSize(prog, &n);
+    if (r != NVRTC_SUCCESS || n == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(MKB_ERR_JIT, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+    }
+    void* img = malloc(n);
+    r = nvrtcGetCUBIN(prog, (char*)img);
+    nvrtcDestroyProgram(&prog);
+    if (r != NVRTC_SUCCESS) {
+        free(img);
+        return fail(MKB_ERR_JIT, "nvrtcGetCUBIN: %s", nvrtcGetErrorString(r));
+    }
+    *cubin = img;
+    *cubin_size = n;
+    return MKB_OK;
+}
+
+extern "C" int mkb_pacing_probe(double t0, int n_events, const double* events, int n_times,
+                                const double* times, double* levels, double* next_times) {
+    mkb::EventPacing p;
+    int rc = p.init(t0, n_events, events);
+    for (int i = 0; rc == 0 && i < n_times; i++) {
+        rc = p.advance(times[i]);
+        if (rc) break;
+        levels[i] = p.level();
+        next_times[i] = p.next_time();
+    }
+    if (rc == mkb::PACING_SIMULTANEOUS_EVENT) {
+        return fail(MKB_ERR_SIMULTANEOUS,
+                    "E-Pacing error: Event scheduled or re-occuring at the same time as another event.");
+    }
+    if (rc) return fail(MKB_ERR_PACING, "E-Pacing error %d", rc);
+    return MKB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Simulation object
+// ---------------------------------------------------------------------------
+static const int kRingHalf = 1024;      // schedule entries per ring half
+
+struct StepRec {
+    MkbStepParams p;
+    bool logging;
+    double log_time, log_pace;          // already rounded to Real
+};
+
+struct mkb_sim {
+    // configuration
+    int device = 0, precision = 64, host_precision = 64;
+    size_t rs = 8, hs = 8;              // sizeof(Real), sizeof(host element)
+    int n_state = 0, i_vm = 0, n_inter = 0, n_field = 0, diff_mode = 0;
+    u64 nx = 0, ny = 0, n = 0, stride = 0;
+    int block_x = 32, block_y = 1;
+    u64 steps_per_call = 1000;
+
+    // CUDA objects
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev_ring[2] = {nullptr, nullptr};
+    cudaEvent_t ev_rows = nullptr, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    bool copied_pending[2] = {false, false};
+
+    // device memory
+    char* d_planes = nullptr;           // all Real planes, one allocation
+    u64 plane_alt_v = 0, plane_idiff = 0, plane_inter = 0, plane_field = 0, n_planes = 0;
+    char* d_gx = nullptr;
+    char* d_gy = nullptr;
+    unsigned char* d_mask = nullptr;
+    u64* d_csr_row = nullptr;
+    unsigned int* d_csr_col = nullptr;
+    char* d_csr_g = nullptr;
+    MkbStepParams* d_ring = nullptr;
+    MkbStepParams* h_ring = nullptr;    // pinned
+    u64 ring_chunk = 0;                 // chunks issued so far
+    int parity = 0;                     // 0: V(t) in plane i_vm, 1: in plane alt_v
+    MkbGridArgs grid{};
+    dim3 launch_grid, launch_block;
+
+    // schedule (openclsim.c globals :84-211)
+    double tmin = 0, tmax = 0, default_dt = 0, log_interval = 1;
+    double engine_time = 0, engine_pace = 0, tnext_pace = 0, tnext_log = 0;
+    u64 istep = 1, inext_log = 0;
+    mkb::EventPacing pacing;
+    bool finished = false, halted = false;
+
+    // logging
+    u64 n_log = 0, row_stride = 0;      // row_stride = n_log + 1 (hidden NaN probe)
+    std::vector<int> time_cols, pace_cols;
+    GatherEntry* d_tab_pre = nullptr;   // states at t (before the step kernel)
+    GatherEntry* d_tab_post = nullptr;  // idiff / intermediaries at t (after it)
+    u64 n_pre = 0, n_post = 0;
+    bool logging_states = false, store_aux = false;
+    char* d_log = nullptr;              // device row ring
+    u64 log_cap = 0, log_half = 0;      // rows in ring / per half
+    u64 rows_written = 0, rows_flushed = 0, rows_final = 0;
+    char* h_log = nullptr;              // pinned host matrix
+    u64 h_log_cap = 0;                  // rows
+    std::vector<double> row_time, row_pace;     // for rows >= rows_final
+
+    // counters
+    u64 launches = 0, steps = 0;
+    double device_ms = 0;
+
+    std::vector<StepRec> recs;
+};
+
+template <typename T>
+static T* plane_ptr(mkb_sim* s, u64 plane) {
+    return (T*)(s->d_planes + plane * s->stride * s->rs);
+}
+
+static void sim_destroy(mkb_sim* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->side) cudaStreamSynchronize(s->side);
+    cudaFree(s->d_planes);
+    cudaFree(s->d_gx);
+    cudaFree(s->d_gy);
+    cudaFree(s->d_mask);
+    cudaFree(s->d_csr_row);
+    cudaFree(s->d_csr_col);
+    cudaFree(s->d_csr_g);
+    cudaFree(s->d_ring);
+    cudaFree(s->d_tab_pre);
+    cudaFree(s->d_tab_post);
+    cudaFree(s->d_log);
+    if (s->h_ring) cudaFreeHost(s->h_ring);
+    if (s->h_log) cudaFreeHost(s->h_log);
+    for (int i = 0; i < 2; i++) {
+        if (s->ev_ring[i]) cudaEventDestroy(s->ev_ring[i]);
+        if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+    }
+    if (s->ev_rows) cudaEventDestroy(s->ev_rows);
+    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
+    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->lib) cudaLibraryUnload(s->lib);
+    delete s;
+}
+
+static int grid_for(u64 n) {
+    u64 b = (n + 255) / 256;
+    return (int)std::min<u64>(std::max<u64>(b, 1), 148 * 16);
+}
+
+// Uploads a host array in the reference's cell-major layout into SoA planes.
+template <typename TH, typename TR>
+static int upload_aos(mkb_sim* s, const void* host, TR* planes, int nvar) {
+    if (nvar == 0) return MKB_OK;
+    const u64 chunk_cells = std::max<u64>(1, (64ull << 20) / ((u64)nvar * sizeof(TH)));
+    TH* d_stage = nullptr;
+    u64 cap = std::min<u64>(chunk_cells, s->n);
+    CUDA_TRY(cudaMalloc(&d_stage, cap * nvar * sizeof(TH)));
+    for (u64 c0 = 0; c0 < s->n; c0 += cap) {
+        u64 nc = std::min<u64>(cap, s->n - c0);
+        cudaError_t e = cudaMemcpyAsync(d_stage, (const TH*)host + c0 * nvar,
+                                        nc * nvar * sizeof(TH), cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) {
+            k_aos_to_soa<TH, TR><<<grid_for(nc * nvar), 256, 0, s->stream>>>(
+                d_stage, planes, c0, nc, nvar, s->stride);
+            s->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) {
+            cudaFree(d_stage);
+            return fail(MKB_ERR_CUDA, "state upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFree(d_stage);
+    return MKB_OK;
+}
+
+template <typename TR, typename TH>
+static int download_aos(mkb_sim* s, void* host) {
+    const int nvar = s->n_state;
+    const u64 chunk_cells = std::max<u64>(1, (64ull << 20) / ((u64)nvar * sizeof(TH)));
+    TH* d_stage = nullptr;
+    u64 cap = std::min<u64>(chunk_cells, s->n);
+    CUDA_TRY(cudaMalloc(&d_stage, cap * nvar * sizeof(TH)));
+    const TR* planes = plane_ptr<TR>(s, 0);
+    const TR* v_cur = plane_ptr<TR>(s, s->parity ? s->plane_alt_v : (u64)std::max(s->i_vm, 0));
+    for (u64 c0 = 0; c0 < s->n; c0 += cap) {
+        u64 nc = std::min<u64>(cap, s->n - c0);
+        k_soa_to_aos<TR, TH><<<grid_for(nc * nvar), 256, 0, s->stream>>>(
+            planes, v_cur, s->i_vm, d_stage, c0, nc, nvar, s->stride);
+        s->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) {
+            e = cudaMemcpyAsync((TH*)host + c0 * nvar, d_stage, nc * nvar * sizeof(TH),
+                                cudaMemcpyDeviceToHost, s->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) {
+            cudaFree(d_stage);
+            return fail(MKB_ERR_CUDA, "state download failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFree(d_stage);
+    return MKB_OK;
+}
+
+// Host array (host precision) -> existing device array of Real.
+template <typename TH, typename TR>
+static int upload_convert(mkb_sim* s, const void* host, u64 count, TR* d) {
+    if (count == 0) return MKB_OK;
+    if (sizeof(TH) == sizeof(TR)) {
+        CUDA_TRY(cudaMemcpy(d, host, count * sizeof(TR), cudaMemcpyHostToDevice));
+        return MKB_OK;
+    }
+    TH* stage = nullptr;
+    CUDA_TRY(cudaMalloc(&stage, count * sizeof(TH)));
+    cudaError_t e = cudaMemcpy(stage, host, count * sizeof(TH), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_convert<TH, TR><<<grid_for(count), 256, 0, s->stream>>>(stage, d, count);
+        s->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return fail(MKB_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    return MKB_OK;
+}
+
+template <typename TR>
+static int sim_init_typed(mkb_sim* s, const mkb_sim_config* c) {
+    const bool host_double = (c->host_precision == MKB_DOUBLE);
+    int rc;
+
+    // --- planes ---
+    s->plane_alt_v = (u64)s->n_state;
+    s->plane_idiff = s->plane_alt_v + 1;
+    s->plane_inter = s->plane_idiff + 1;
+    s->plane_field = s->plane_inter + (u64)s->n_inter;
+    s->n_planes = s->plane_field + (u64)s->n_field;
+    CUDA_TRY(cudaMalloc(&s->d_planes, s->n_planes * s->stride * s->rs));
+    CUDA_TRY(cudaMemsetAsync(s->d_planes, 0, s->n_planes * s->stride * s->rs, s->stream));
+
+    // --- state + fields ---
+    if (!c->state_in) return fail(MKB_ERR_INVALID, "state_in is null");
+    rc = host_double ? upload_aos<double, TR>(s, c->state_in, plane_ptr<TR>(s, 0), s->n_state)
+                     : upload_aos<TR, TR>(s, c->state_in, plane_ptr<TR>(s, 0), s->n_state);
+    if (rc) return rc;
+    if (s->n_field > 0) {
+        if (!c->field_data) return fail(MKB_ERR_INVALID, "field_data is null");
+        rc = host_double
+                 ? upload_aos<double, TR>(s, c->field_data, plane_ptr<TR>(s, s->plane_field), s->n_field)
+                 : upload_aos<TR, TR>(s, c->field_data, plane_ptr<TR>(s, s->plane_field), s->n_field);
+        if (rc) return rc;
+    }
+
+    // --- conductance fields (config arrays are GLOBAL, reference layout) ---
+    if (s->diff_mode == MKB_DIFF_FIELD) {
+        const u64 iy0 = c->iy_offset;
+        const u64 nyg = c->ny_global ? c->ny_global : s->ny;
+        const size_t hs = host_double ? 8 : sizeof(TR);
+        if (s->nx > 1) {
+            if (!c->gx_field) return fail(MKB_ERR_INVALID, "gx_field is null");
+            // rows [iy0, iy0 + ny) of gx[(ny_global, nx - 1)]
+            const u64 ngx = (s->nx - 1) * s->ny;
+            const char* src = (const char*)c->gx_field + iy0 * (s->nx - 1) * hs;
+            CUDA_TRY(cudaMalloc(&s->d_gx, ngx * sizeof(TR)));
+            rc = host_double ? upload_convert<double, TR>(s, src, ngx, (TR*)s->d_gx)
+                             : upload_convert<TR, TR>(s, src, ngx, (TR*)s->d_gx);
+            if (rc) return rc;
+        }
+        if (nyg > 1) {
+            if (!c->gy_field) return fail(MKB_ERR_INVALID, "gy_field is null");
+            // Slab copy with ny + 1 rows: local row r <- global gy row iy0 - 1 + r
+            // (gy row j couples grid rows j and j + 1); missing rows stay zero.
+            CUDA_TRY(cudaMalloc(&s->d_gy, (s->ny + 1) * s->nx * sizeof(TR)));
+            CUDA_TRY(cudaMemset(s->d_gy, 0, (s->ny + 1) * s->nx * sizeof(TR)));
+            const u64 first = iy0 > 0 ? iy0 - 1 : 0;               // first global gy row
+            const u64 last = std::min<u64>(iy0 + s->ny - 1, nyg - 2);   // last global gy row
+            if (last >= first && nyg >= 2) {
+                const u64 rows = last - first + 1;
+                const char* src = (const char*)c->gy_field + first * s->nx * hs;
+                TR* dst = (TR*)s->d_gy + (first + 1 - iy0) * s->nx;
+                rc = host_double ? upload_convert<double, TR>(s, src, rows * s->nx, dst)
+                                 : upload_convert<TR, TR>(s, src, rows * s->nx, dst);
+                if (rc) return rc;
+            }
+        }
+    }
+
+    // --- connections -> CSR (stable: per-cell order = edge-list order) ---
+    if (s->diff_mode == MKB_DIFF_CONNECTIONS) {
+        const u64 ne = c->n_connections;
+        std::vector<u64> row(s->n + 1, 0);
+        for (u64 e = 0; e < ne; e++) {
+            u64 i = c->conn_i[e], j = c->conn_j[e];
+            if (i >= s->n || j >= s->n || i == j) {
+                return fail(MKB_ERR_INVALID, "invalid connection %llu: (%llu, %llu)", e, i, j);
+            }
+            row[i + 1]++;
+            row[j + 1]++;
+        }
+        for (u64 i = 0; i < s->n; i++) row[i + 1] += row[i];
+        std::vector<unsigned int> col(2 * ne + 1);
+        std::vector<TR> g(2 * ne + 1);
+        std::vector<u64> fill(row.begin(), row.end() - 1);
+        for (u64 e = 0; e < ne; e++) {
+            u64 i = c->conn_i[e], j = c->conn_j[e];
+            TR ge = host_double ? (TR)((const double*)c->conn_g)[e] : ((const TR*)c->conn_g)[e];
+            col[fill[i]] = (unsigned int)j;
+            g[fill[i]++] = ge;
+            col[fill[j]] = (unsigned int)i;
+            g[fill[j]++] = ge;
+        }
+        CUDA_TRY(cudaMalloc(&s->d_csr_row, (s->n + 1) * sizeof(u64)));
+        CUDA_TRY(cudaMalloc(&s->d_csr_col, (2 * ne + 1) * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&s->d_csr_g, (2 * ne + 1) * sizeof(TR)));
+        CUDA_TRY(cudaMemcpy(s->d_csr_row, row.data(), (s->n + 1) * sizeof(u64), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_csr_col, col.data(), (2 * ne + 1) * sizeof(unsigned int),
+                            cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_csr_g, g.data(), (2 * ne + 1) * sizeof(TR), cudaMemcpyHostToDevice));
+    }
+    return MKB_OK;
+}
+
+extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
+    if (!c || !out) return fail(MKB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (c->abi_version != MKB_ABI_VERSION) {
+        return fail(MKB_ERR_INVALID, "ABI version mismatch: library %d, caller %d", MKB_ABI_VERSION,
+                    c->abi_version);
+    }
+    if (c->precision != MKB_SINGLE && c->precision != MKB_DOUBLE) {
+        return fail(MKB_ERR_INVALID, "Only single and double precision are supported.");
+    }
+    if (c->host_precision != MKB_DOUBLE && c->host_precision != c->precision) {
+        return fail(MKB_ERR_INVALID, "host_precision must be 64 or equal to precision");
+    }
+    if (c->nx < 1 || c->ny < 1) {
+        return fail(MKB_ERR_INVALID, "The number of cells in any direction must be at least 1.");
+    }
+    if (c->n_state < 1 || c->n_inter < 0 || c->n_field < 0) return fail(MKB_ERR_INVALID, "bad model shape");
+    if (c->diffusion_mode < 0 || c->diffusion_mode > 3) return fail(MKB_ERR_INVALID, "bad diffusion_mode");
+    if (c->diffusion_mode != MKB_DIFF_NONE && (c->i_vm < 0 || c->i_vm >= c->n_state)) {
+        return fail(MKB_ERR_INVALID, "i_vm out of range");
+    }
+    if (c->diffusion_mode == MKB_DIFF_CONNECTIONS && c->ny != 1) {
+        return fail(MKB_ERR_INVALID, "Connections can only be specified in 1d mode.");
+    }
+    if (!c->cubin || !c->cubin_size || !c->kernel_name) return fail(MKB_ERR_INVALID, "no kernel image");
+    if (!(c->dt > 0)) return fail(MKB_ERR_INVALID, "Step size must be greater than zero.");
+    if (c->tmax < c->tmin) return fail(MKB_ERR_INVALID, "Simulation time can't be negative.");
+    if (c->block_x < 1 || c->block_y < 1 || c->block_x * c->block_y > 1024) {
+        return fail(MKB_ERR_INVALID, "bad block shape");
+    }
+
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            return fail(MKB_ERR_CUDA, "No CUDA device available (%s); this back-end has no CPU fallback.",
+                        cudaGetErrorString(e));
+        }
+    }
+    if (c->device < 0 || c->device >= ndev) return fail(MKB_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+
+    mkb_sim* s = new mkb_sim();
+    s->device = c->device;
+    s->precision = c->precision;
+    s->host_precision = c->host_precision;
+    s->rs = c->precision == MKB_DOUBLE ? 8 : 4;
+    s->hs = c->host_precision == MKB_DOUBLE ? 8 : 4;
+    s->n_state = c->n_state;
+    // Without diffusion nothing reads a neighbour's V: every state updates in place
+    s->i_vm = c->diffusion_mode == MKB_DIFF_NONE ? -1 : c->i_vm;
+    s->n_inter = c->n_inter;
+    s->n_field = c->n_field;
+    s->diff_mode = c->diffusion_mode;
+    s->nx = c->nx;
+    s->ny = c->ny;
+    s->n = c->nx * c->ny;
+    s->stride = (s->n + 31) / 32 * 32;
+    s->block_x = c->block_x;
+    s->block_y = c->block_y;
+    s->tmin = c->tmin;
+    s->tmax = c->tmax;
+    s->default_dt = c->dt;
+    s->log_interval = c->log_interval;
+    if (c->steps_per_call) {
+        s->steps_per_call = c->steps_per_call;
+    } else {
+        // openclsim.c:1046-1047
+        s->steps_per_call = std::max<u64>(1000, 500 + 200000 / s->n);
+    }
+
+#define INIT_TRY(expr)          \
+    do {                        \
+        int rc_ = (expr);       \
+        if (rc_) {              \
+            sim_destroy(s);     \
+            return rc_;         \
+        }                       \
+    } while (0)
+#define INIT_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            sim_destroy(s);                                                                  \
+            return fail(MKB_ERR_CUDA, "CUDA error %d (%s) at %s:%d: %s", (int)e_,            \
+                        cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_));   \
+        }                                                                                    \
+    } while (0)
+
+    INIT_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    INIT_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        INIT_CUDA(cudaEventCreateWithFlags(&s->ev_ring[i], cudaEventDisableTiming));
+        INIT_CUDA(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+    }
+    INIT_CUDA(cudaEventCreateWithFlags(&s->ev_rows, cudaEventDisableTiming));
+    INIT_CUDA(cudaEventCreate(&s->ev_t0));
+    INIT_CUDA(cudaEventCreate(&s->ev_t1));
+
+    // Model kernel
+    INIT_CUDA(cudaLibraryLoadData(&s->lib, c->cubin, nullptr, nullptr, 0, nullptr, nullptr, 0));
+    INIT_CUDA(cudaLibraryGetKernel(&s->kern, s->lib, c->kernel_name));
+
+    // Buffers
+    if (c->precision == MKB_DOUBLE) {
+        INIT_TRY(sim_init_typed<double>(s, c));
+    } else {
+        INIT_TRY(sim_init_typed<float>(s, c));
+    }
+
+    // Paced cells: rectangle stays symbolic, a list becomes a byte mask
+    s->grid.pace_x0 = s->grid.pace_x1 = s->grid.pace_y0 = s->grid.pace_y1 = 0;
+    if (c->diffusion_mode != MKB_DIFF_NONE) {
+        if (c->pace_rect) {
+            // openclsim.cl:260-274
+            s->grid.pace_x0 = c->pace_x;
+            s->grid.pace_x1 = c->pace_x + c->pace_nx;
+            s->grid.pace_y0 = c->pace_y;
+            s->grid.pace_y1 = c->pace_y + c->pace_ny;
+        } else {
+            std::vector<unsigned char> mask(s->n, 0);
+            const u64 cell0 = c->iy_offset * c->nx;
+            for (u64 i = 0; i < c->n_paced; i++) {
+                u64 cid = c->paced_cells[i];
+                if (cid >= cell0 && cid - cell0 < s->n) mask[cid - cell0] = 1;
+            }
+            INIT_CUDA(cudaMalloc(&s->d_mask, s->n));
+            INIT_CUDA(cudaMemcpy(s->d_mask, mask.data(), s->n, cudaMemcpyHostToDevice));
+        }
+    }
+
+    // Schedule ring
+    INIT_CUDA(cudaMalloc(&s->d_ring, 2 * kRingHalf * sizeof(MkbStepParams)));
+    INIT_CUDA(cudaHostAlloc(&s->h_ring, 2 * kRingHalf * sizeof(MkbStepParams), cudaHostAllocDefault));
+
+    // Grid arguments
+    MkbGridArgs& g = s->grid;
+    g.state = s->d_planes;
+    g.idiff = plane_ptr<char>(s, s->plane_idiff);
+    g.inter = plane_ptr<char>(s, s->plane_inter);
+    g.field = plane_ptr<char>(s, s->plane_field);
+    g.gx_field = s->d_gx;
+    // slab-relative: element [-nx .. -1] is the row shared with the slab above
+    g.gy_field = s->d_gy ? s->d_gy + s->nx * s->rs : nullptr;
+    g.paced_mask = s->d_mask;
+    g.csr_row = s->d_csr_row;
+    g.csr_col = s->d_csr_col;
+    g.csr_g = s->d_csr_g;
+    g.halo_lo = nullptr;
+    g.halo_hi = nullptr;
+    g.nx = s->nx;
+    g.ny = s->ny;
+    g.stride = s->stride;
+    g.iy_offset = c->iy_offset;
+    g.ny_global = c->ny_global ? c->ny_global : s->ny;
+    g.gx = c->gx;
+    g.gy = c->gy;
+    {
+        u64 bx = (s->nx + s->block_x - 1) / s->block_x;
+        u64 by = (s->ny + s->block_y - 1) / s->block_y;
+        if (bx * by > 0x7fffffffull) {
+            sim_destroy(s);
+            return fail(MKB_ERR_INVALID, "grid too large for one launch");
+        }
+        s->launch_grid = dim3((unsigned int)(bx * by), 1, 1);
+        s->launch_block = dim3((unsigned int)s->block_x, (unsigned int)s->block_y, 1);
+    }
+
+    // Logging tables
+    s->n_log = c->n_log;
+    s->row_stride = c->n_log + 1;
+    {
+        std::vector<GatherEntry> pre, post;
+        bool bad_log = false;
+        for (u64 j = 0; j < c->n_log && !bad_log; j++) {
+            GatherEntry e;
+            e.col = (unsigned int)j;
+            e.pad = 0;
+            u64 idx = c->log_index[j];
+            switch (c->log_kind[j]) {
+            case MKB_LOG_TIME:
+                s->time_cols.push_back((int)j);
+                break;
+            case MKB_LOG_PACE:
+                s->pace_cols.push_back((int)j);
+                break;
+            case MKB_LOG_IDIFF:
+                if (idx >= s->n || c->diffusion_mode == MKB_DIFF_NONE) { bad_log = true; break; }
+                e.off = s->plane_idiff * s->stride + idx;
+                post.push_back(e);
+                break;
+            case MKB_LOG_STATE: {
+                u64 cid = idx / (u64)s->n_state;
+                u64 k = idx % (u64)s->n_state;
+                if (cid >= s->n) { bad_log = true; break; }
+                if ((int)k == s->i_vm) {
+                    e.off = MKB_GATHER_V | cid;
+                } else {
+                    e.off = k * s->stride + cid;
+                }
+                pre.push_back(e);
+                s->logging_states = true;
+                break;
+            }
+            case MKB_LOG_INTER: {
+                if (s->n_inter == 0) { bad_log = true; break; }
+                u64 cid = idx / (u64)s->n_inter;
+                u64 k = idx % (u64)s->n_inter;
+                if (cid >= s->n) { bad_log = true; break; }
+                e.off = (s->plane_inter + k) * s->stride + cid;
+                post.push_back(e);
+                break;
+            }
+            default:
+                bad_log = true;
+                break;
+            }
+        }
+        if (bad_log) {
+            sim_destroy(s);
+            return fail(MKB_ERR_INVALID, "Unknown variables found in logging dictionary.");
+        }
+        s->store_aux = !post.empty();
+        if (s->logging_states) {
+            // Hidden NaN probe: first state of cell 0 (openclsim.c:1087)
+            GatherEntry e;
+            e.col = (unsigned int)c->n_log;
+            e.pad = 0;
+            e.off = (s->i_vm == 0) ? (MKB_GATHER_V | 0ull) : 0ull;
+            pre.push_back(e);
+        }
+        s->n_pre = pre.size();
+        s->n_post = post.size();
+        if (s->n_pre) {
+            INIT_CUDA(cudaMalloc(&s->d_tab_pre, s->n_pre * sizeof(GatherEntry)));
+            INIT_CUDA(cudaMemcpy(s->d_tab_pre, pre.data(), s->n_pre * sizeof(GatherEntry),
+                                 cudaMemcpyHostToDevice));
+        }
+        if (s->n_post) {
+            INIT_CUDA(cudaMalloc(&s->d_tab_post, s->n_post * sizeof(GatherEntry)));
+            INIT_CUDA(cudaMemcpy(s->d_tab_post, post.data(), s->n_post * sizeof(GatherEntry),
+                                 cudaMemcpyHostToDevice));
+        }
+    }
+    if (s->n_pre + s->n_post > 0) {
+        // Device row ring: two halves, ~64 MiB each at most
+        u64 row_bytes = s->row_stride * s->rs;
+        u64 half = std::max<u64>(1, std::min<u64>(4096, (64ull << 20) / row_bytes));
+        s->log_half = half;
+        s->log_cap = 2 * half;
+        INIT_CUDA(cudaMalloc(&s->d_log, s->log_cap * row_bytes));
+        INIT_CUDA(cudaMemsetAsync(s->d_log, 0, s->log_cap * row_bytes, s->stream));
+    }
+
+    // Pacing: openclsim.c:488-496
+    {
+        int rc = s->pacing.init(c->tmin, c->n_events, c->events);
+        if (rc == 0) rc = s->pacing.advance(c->tmin);
+        if (rc) {
+            sim_destroy(s);
+            if (rc == mkb::PACING_SIMULTANEOUS_EVENT) {
+                return fail(MKB_ERR_SIMULTANEOUS,
+                            "E-Pacing error: Event scheduled or re-occuring at the same time as another "
+                            "event.");
+            }
+            return fail(MKB_ERR_PACING, "E-Pacing error %d", rc);
+        }
+    }
+    s->tnext_pace = s->pacing.next_time();
+    s->engine_pace = s->pacing.level();
+    s->engine_time = c->tmin;               // openclsim.c:501
+    s->istep = 1;                           // openclsim.c:1018
+    s->inext_log = 0;
+    s->tnext_log = c->tmin;                 // openclsim.c:1021-1022
+    s->finished = !(c->tmax > c->tmin);
+
+    INIT_CUDA(cudaStreamSynchronize(s->stream));
+#undef INIT_TRY
+#undef INIT_CUDA
+    *out = s;
+    return MKB_OK;
+}
+
+static int ensure_host_rows(mkb_sim* s, u64 rows) {
+    if (rows <= s->h_log_cap) return MKB_OK;
+    // Estimate the whole run on first use, then grow geometrically
+    u64 want = rows;
+    if (s->h_log_cap == 0) {
+        double est = (s->tmax - s->tmin) / s->log_interval;
+        double est2 = 2.0 * (s->tmax - s->tmin) / s->default_dt;
+        double m = std::min(est, est2) + 16;
+        if (m > 0 && m < 4.0e9) want = std::max<u64>(rows, (u64)m);
+        // Do not pin more than 2 GiB speculatively
+        u64 row_bytes = s->row_stride * s->rs;
+        u64 lim = std::max<u64>(rows, (2ull << 30) / row_bytes);
+        want = std::min(want, std::max<u64>(lim, rows));
+    } else {
+        want = std::max(rows, s->h_log_cap * 2);
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->side));
+    char* p = nullptr;
+    CUDA_TRY(cudaHostAlloc(&p, want * s->row_stride * s->rs, cudaHostAllocDefault));
+    if (s->h_log) {
+        memcpy(p, s->h_log, s->rows_flushed * s->row_stride * s->rs);
+        cudaFreeHost(s->h_log);
+    }
+    s->h_log = p;
+    s->h_log_cap = want;
+    return MKB_OK;
+}
+
+// Issues the D2H copy of rows [rows_flushed, rows_written) on the side stream.
+static int flush_rows(mkb_sim* s) {
+    if (s->rows_flushed == s->rows_written) return MKB_OK;
+    int rc = ensure_host_rows(s, s->rows_written);
+    if (rc) return rc;
+    if (s->d_log) {
+        const u64 row_bytes = s->row_stride * s->rs;
+        const u64 slot = s->rows_flushed % s->log_cap;
+        const int half = (int)(slot / s->log_half);
+        const u64 nrows = s->rows_written - s->rows_flushed;
+        CUDA_TRY(cudaEventRecord(s->ev_rows, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->side, s->ev_rows, 0));
+        CUDA_TRY(cudaMemcpyAsync(s->h_log + s->rows_flushed * row_bytes, s->d_log + slot * row_bytes,
+                                 nrows * row_bytes, cudaMemcpyDeviceToHost, s->side));
+        CUDA_TRY(cudaEventRecord(s->ev_copied[half], s->side));
+        s->copied_pending[half] = true;
+    }
+    s->rows_flushed = s->rows_written;
+    return MKB_OK;
+}
+
+template <typename TR>
+static int finalize_rows(mkb_sim* s) {
+    // Host-known columns and the NaN probe, for rows that have landed
+    CUDA_TRY(cudaStreamSynchronize(s->side));
+    for (u64 r = s->rows_final; r < s->rows_flushed; r++) {
+        TR* row = (TR*)(s->h_log) + r * s->row_stride;
+        const u64 k = r - s->rows_final;
+        for (int col : s->time_cols) row[col] = (TR)s->row_time[k];
+        for (int col : s->pace_cols) row[col] = (TR)s->row_pace[k];
+        if (s->logging_states && !s->halted) {
+            TR probe = row[s->n_log];
+            if (probe != probe) {
+                // openclsim.c:1087-1089: the row with the NaN is kept, then the run stops
+                s->halted = true;
+                s->finished = true;
+                s->rows_flushed = s->rows_written = r + 1;
+                s->rows_final = r + 1;
+                s->row_time.clear();
+                s->row_pace.clear();
+                return MKB_OK;
+            }
+        }
+    }
+    s->rows_final = s->rows_flushed;
+    s->row_time.clear();
+    s->row_pace.clear();
+    return MKB_OK;
+}
+
+template <typename TR>
+static int sim_step_typed(mkb_sim* s) {
+    const double dt_min = 0;                    // openclsim.c:413
+    u64 steps_left = s->steps_per_call;
+    bool timing_started = false;
+
+    while (steps_left > 0 && !s->finished) {
+        // ---- Phase A: host schedule for up to kRingHalf steps ----
+        s->recs.clear();
+        while (s->recs.size() < (size_t)kRingHalf && steps_left > 0) {
+            StepRec rec;
+            // openclsim.c:1054
+            rec.logging = (s->engine_time >= s->tnext_log);
+            // openclsim.c:1057-1063
+            bool intermediary = false;
+            double dt = s->tmin + (double)s->istep * s->default_dt - s->engine_time;
+            double d = s->tmax - s->engine_time;
+            if (d > dt_min && d < dt) { dt = d; intermediary = true; }
+            d = s->tnext_pace - s->engine_time;
+            if (d > dt_min && d < dt) { dt = d; intermediary = true; }
+            d = s->tnext_log - s->engine_time;
+            if (d > dt_min && d < dt) { dt = d; intermediary = true; }
+            if (!intermediary) s->istep++;
+            rec.p.time = s->engine_time;
+            rec.p.dt = dt;
+            rec.p.pace = s->engine_pace;
+            rec.p.flags = (rec.logging && s->store_aux) ? MKB_FLAG_STORE_AUX : 0u;
+            rec.p.reserved = 0;
+            rec.log_time = (double)(TR)s->engine_time;
+            rec.log_pace = (double)(TR)s->engine_pace;
+            if (rec.logging) {
+                // openclsim.c:1134-1136
+                s->inext_log++;
+                s->tnext_log = s->tmin + (double)s->inext_log * s->log_interval;
+            }
+            // openclsim.c:1147-1155
+            s->engine_time += dt;
+            int prc = s->pacing.advance(s->engine_time);
+            if (prc == mkb::PACING_SIMULTANEOUS_EVENT) {
+                return fail(MKB_ERR_SIMULTANEOUS,
+                            "E-Pacing error: Event scheduled or re-occuring at the same time as another "
+                            "event.");
+            }
+            if (prc) return fail(MKB_ERR_PACING, "E-Pacing error %d", prc);
+            s->tnext_pace = s->pacing.next_time();
+            s->engine_pace = s->pacing.level();
+            s->recs.push_back(rec);
+            steps_left--;
+            // openclsim.c:1162
+            if (s->engine_time >= s->tmax) {
+                s->finished = true;
+                break;
+            }
+        }
+
+        // ---- Phase B: upload the schedule chunk, then launch in order ----
+        const int half = (int)(s->ring_chunk & 1);
+        MkbStepParams* h = s->h_ring + half * kRingHalf;
+        MkbStepParams* dring = s->d_ring + half * kRingHalf;
+        if (s->ring_chunk >= 2) {
+            // The H2D copy that last used this pinned half must have executed
+            CUDA_TRY(cudaEventSynchronize(s->ev_ring[half]));
+        }
+        for (size_t i = 0; i < s->recs.size(); i++) h[i] = s->recs[i].p;
+        if (!timing_started) {
+            CUDA_TRY(cudaEventRecord(s->ev_t0, s->stream));
+            timing_started = true;
+        }
+        CUDA_TRY(cudaMemcpyAsync(dring, h, s->recs.size() * sizeof(MkbStepParams),
+                                 cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaEventRecord(s->ev_ring[half], s->stream));
+        s->ring_chunk++;
+
+        for (size_t i = 0; i < s->recs.size(); i++) {
+            const StepRec& rec = s->recs[i];
+            const u64 vm_plane = (u64)std::max(s->i_vm, 0);
+            TR* v_in = plane_ptr<TR>(s, s->parity ? s->plane_alt_v : vm_plane);
+            TR* v_out = plane_ptr<TR>(s, s->parity ? vm_plane : s->plane_alt_v);
+            TR* row = nullptr;
+            const bool dev_row = rec.logging && s->d_log;
+            if (dev_row) {
+                const u64 slot = s->rows_written % s->log_cap;
+                if (slot % s->log_half == 0) {
+                    const int lh = (int)(slot / s->log_half);
+                    if (s->copied_pending[lh]) {
+                        // rows previously in this half must have left the device
+                        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_copied[lh], 0));
+                        s->copied_pending[lh] = false;
+                    }
+                }
+                row = (TR*)s->d_log + slot * s->row_stride;
+                if (s->n_pre) {
+                    // states at time t (openclsim.c:1079-1084)
+                    k_log_gather<TR><<<grid_for(s->n_pre), 256, 0, s->stream>>>(
+                        plane_ptr<TR>(s, 0), v_in, s->d_tab_pre, s->n_pre, row);
+                    s->launches++;
+                }
+            }
+            // fused diffusion + cell step: states -> t + dt (openclsim.c:1066-1096)
+            const MkbStepParams* sp = dring + i;
+            void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
+            CUDA_TRY(cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0,
+                                      s->stream));
+            s->launches++;
+            s->steps++;
+            s->parity ^= 1;
+            if (rec.logging) {
+                if (dev_row && s->n_post) {
+                    // idiff(t), intermediaries(t) (openclsim.c:1110-1119)
+                    k_log_gather<TR><<<grid_for(s->n_post), 256, 0, s->stream>>>(
+                        plane_ptr<TR>(s, 0), v_in, s->d_tab_post, s->n_post, row);
+                    s->launches++;
+                }
+                if (s->n_log > 0) {
+                    s->row_time.push_back(rec.log_time);
+                    s->row_pace.push_back(rec.log_pace);
+                    s->rows_written++;
+                    if (s->d_log && s->rows_written % s->log_half == 0) {
+                        int rc = flush_rows(s);
+                        if (rc) return rc;
+                    }
+                }
+            }
+        }
+    }
+
+    // End of call: drain, like the clFinish at openclsim.c:1172-1176
+    if (timing_started) CUDA_TRY(cudaEventRecord(s->ev_t1, s->stream));
+    int rc = flush_rows(s);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (timing_started) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
+        s->device_ms += ms;
+    }
+    return finalize_rows<TR>(s);
+}
+
+extern "C" int mkb_sim_step(mkb_sim* s, double* engine_time, int* halted) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int rc = MKB_OK;
+    if (!s->finished) {
+        rc = (s->precision == MKB_DOUBLE) ? sim_step_typed<double>(s) : sim_step_typed<float>(s);
+    }
+    if (engine_time) *engine_time = s->engine_time;
+    if (halted) *halted = s->halted ? 1 : 0;
+    if (rc) return rc;
+    return s->finished ? 0 : 1;
+}
+
+extern "C" int mkb_sim_log_view(mkb_sim* s, const void** data, uint64_t* rows, uint64_t* cols,
+                                uint64_t* row_stride) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (data) *data = s->h_log;
+    if (rows) *rows = s->rows_final;
+    if (cols) *cols = s->n_log;
+    if (row_stride) *row_stride = s->row_stride;
+    return MKB_OK;
+}
+
+extern "C" int mkb_sim_get_state(mkb_sim* s, void* state_out) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (!state_out) return fail(MKB_ERR_INVALID, "state_out is null");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (s->precision == MKB_DOUBLE) return download_aos<double, double>(s, state_out);
+    if (s->host_precision == MKB_DOUBLE) return download_aos<float, double>(s, state_out);
+    return download_aos<float, float>(s, state_out);
+}
+
+extern "C" int mkb_sim_counters(mkb_sim* s, uint64_t* kernel_launches, uint64_t* steps) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (kernel_launches) *kernel_launches = s->launches;
+    if (steps) *steps = s->steps;
+    return MKB_OK;
+}
+
+extern "C" int mkb_sim_device_ms(mkb_sim* s, double* ms) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (ms) *ms = s->device_ms;
+    return MKB_OK;
+}
+
+extern "C" void mkb_sim_clean(mkb_sim* s) { sim_destroy(s); }
