@@ -178,6 +178,10 @@ int mkb_sim_counters(mkb_sim* sim, uint64_t* kernel_launches, uint64_t* steps);
 /* Device time (ms) spent between the first and last step kernel of the calls
  * made so far, measured with CUDA events on the launching stream. */
 int mkb_sim_device_ms(mkb_sim* sim, double* ms);
+/* Changes the number of steps the next mkb_sim_step calls take (>= 1). */
+int mkb_sim_set_steps_per_call(mkb_sim* sim, uint64_t steps);
+/* Zeroes the launch / step counters and the accumulated device time. */
+int mkb_sim_reset_counters(mkb_sim* sim);
 void mkb_sim_clean(mkb_sim* sim);
 
 /* ---- pacing alone (unit tests; mirrors tests/ansic_event_based_pacing.c) ---- */

@@ -29,7 +29,8 @@ SYMBOLS = [
     'mkb_abi_version', 'mkb_last_error', 'mkb_free', 'mkb_device_count',
     'mkb_device_info', 'mkb_device_abi_header', 'mkb_jit_compile',
     'mkb_sim_init', 'mkb_sim_step', 'mkb_sim_log_view', 'mkb_sim_get_state',
-    'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_clean',
+    'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
+    'mkb_sim_reset_counters', 'mkb_sim_clean',
     'mkb_pacing_probe',
 ]
 
@@ -112,6 +113,8 @@ def library():
     lib.mkb_sim_counters.argtypes = [
         c_vp, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]
     lib.mkb_sim_device_ms.argtypes = [c_vp, ctypes.POINTER(ctypes.c_double)]
+    lib.mkb_sim_set_steps_per_call.argtypes = [c_vp, c_u64]
+    lib.mkb_sim_reset_counters.argtypes = [c_vp]
     lib.mkb_sim_clean.argtypes = [c_vp]
     lib.mkb_sim_clean.restype = None
     lib.mkb_pacing_probe.argtypes = [

@@ -1065,4 +1065,19 @@ extern "C" int mkb_sim_device_ms(mkb_sim* s, double* ms) {
     return MKB_OK;
 }
 
+extern "C" int mkb_sim_set_steps_per_call(mkb_sim* s, uint64_t steps) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (steps < 1) return fail(MKB_ERR_INVALID, "steps must be at least 1");
+    s->steps_per_call = steps;
+    return MKB_OK;
+}
+
+extern "C" int mkb_sim_reset_counters(mkb_sim* s) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    s->launches = 0;
+    s->steps = 0;
+    s->device_ms = 0;
+    return MKB_OK;
+}
+
 extern "C" void mkb_sim_clean(mkb_sim* s) { sim_destroy(s); }

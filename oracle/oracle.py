@@ -45,6 +45,17 @@ _REF = os.path.join(_HERE, '_ref')
 LOG_TIME, LOG_PACE, LOG_IDIFF, LOG_STATE, LOG_INTER = range(5)
 
 
+def _host_isa_tag():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('flags'):
+                    return hashlib.sha1(line.encode()).hexdigest()[:12]
+    except OSError:
+        pass
+    return 'unknown'
+
+
 def _compile(header_text, tag, ref_kernel, openmp, contract, opt):
     """Compiles driver.c against a model header; returns the .so path."""
     outdir = _REF if ref_kernel else _BUILD
@@ -56,7 +67,10 @@ def _compile(header_text, tag, ref_kernel, openmp, contract, opt):
     flags = [opt, '-fPIC', '-shared', '-std=gnu11',
              '-ffp-contract=' + ('fast' if contract else 'off'), '-w']
     if opt == '-O3':
+        # Timed CPU-baseline builds; the cache key must not let a binary
+        # built for another host's ISA be reused.
         flags.append('-march=native')
+        flags.append('-DORACLE_HOST_ISA_%s=1' % _host_isa_tag())
     if openmp:
         flags.append('-fopenmp')
     h = hashlib.sha1()

@@ -1,0 +1,427 @@
+"""
+Host-side tests that need no GPU: the C-ABI library loads and exports what
+include/myokit_b200.h declares, the JIT cross-compiles every kernel variant
+for sm_100a, the pacing system matches Myokit's, SimulationCUDA validates its
+arguments like the reference class (myokit/tests/test_simulation_opencl.py),
+and — on a machine without a GPU — running fails loudly instead of falling
+back to anything.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import myokit_b200
+from myokit_b200 import capi, kernelgen, simulation, workloads
+import myokit
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DP = myokit.DOUBLE_PRECISION
+SP = myokit.SINGLE_PRECISION
+HAS_GPU = capi.device_count() > 0
+
+
+def br():
+    return workloads.data_model('beeler-1977-model.mmt')
+
+
+# ---------------------------------------------------------------------------
+# C ABI
+# ---------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, 'include', 'myokit_b200.h')) as f:
+        text = f.read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    declared = set(re.findall(r'\b(mkb_[a-z_0-9]+)\s*\(', text))
+    assert len(declared) >= 15
+    lib = capi.library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(capi.SYMBOLS)
+    assert lib.mkb_abi_version() == capi.MKB_ABI_VERSION
+
+
+def test_config_struct_matches_header_size():
+    # Guard against the ctypes mirror drifting from the C struct: compile a
+    # one-liner with the real header and compare sizeof.
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, 's.c')
+        with open(src, 'w') as f:
+            f.write('#include <stdio.h>\n#include "myokit_b200.h"\n'
+                    'int main(){printf("%zu %zu", sizeof(mkb_sim_config), '
+                    'sizeof(mkb_device_info_t));return 0;}')
+        exe = os.path.join(d, 's')
+        subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'),
+                               src, '-o', exe])
+        out = subprocess.check_output([exe]).decode().split()
+    assert int(out[0]) == ctypes.sizeof(capi.SimConfig)
+    assert int(out[1]) == ctypes.sizeof(capi.DeviceInfo)
+
+
+def test_device_abi_header_is_embedded():
+    text = capi.library().mkb_device_abi_header().decode()
+    assert 'struct MkbGridArgs' in text and 'struct MkbStepParams' in text
+    with open(os.path.join(ROOT, 'myokit_b200', 'csrc',
+                           'mkb_device_abi.h')) as f:
+        assert f.read() == text
+
+
+def test_jit_reports_errors():
+    with pytest.raises(capi.BackendError) as e:
+        capi.jit_compile('this is not CUDA')
+    assert e.value.code == capi.MKB_ERR_JIT
+
+
+def test_pacing_probe_matches_myokit_pacing_system():
+    lib = capi.library()
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        p = myokit.Protocol()
+        t = 0.0
+        for k in range(rng.integers(1, 5)):
+            t += float(rng.integers(1, 40)) * 0.5
+            dur = float(rng.integers(1, 6)) * 0.25
+            if k == 0 and rng.random() < 0.5:
+                p.schedule(1.5, t, dur, t + dur + 50.0, int(rng.integers(0, 4)))
+                break
+            p.schedule(float(rng.integers(1, 4)), t, dur)
+            t += dur
+        ps = myokit.PacingSystem(p)
+        ev = np.array([[e.level(), e.start(), e.duration(), e.period(),
+                        e.multiplier()] for e in p.events()]).ravel()
+        times = np.cumsum(rng.uniform(0, 3, size=300))
+        want_l, want_n = [], []
+        for tt in times:
+            ps.advance(tt)
+            want_l.append(ps.pace())
+            want_n.append(ps.next_time())
+        levels = np.zeros(len(times))
+        tnext = np.zeros(len(times))
+        rc = lib.mkb_pacing_probe(
+            0.0, len(ev) // 5, ev.ctypes.data, len(times), times.ctypes.data,
+            levels.ctypes.data, tnext.ctypes.data)
+        assert rc == 0
+        assert list(levels) == want_l
+        assert list(tnext) == want_n
+
+
+def test_pacing_probe_simultaneous_events():
+    lib = capi.library()
+    ev = np.array([1.0, 10, 1, 0, 0, 2.0, 10, 1, 0, 0])
+    times = np.array([20.0])
+    out = np.zeros(1)
+    rc = lib.mkb_pacing_probe(0.0, 2, ev.ctypes.data, 1, times.ctypes.data,
+                              out.ctypes.data, out.ctypes.data)
+    assert rc == capi.MKB_ERR_SIMULTANEOUS
+    assert b'same time' in lib.mkb_last_error()
+
+
+# ---------------------------------------------------------------------------
+# Kernel generator
+# ---------------------------------------------------------------------------
+def variants():
+    m, p, _ = myokit.load('example')
+    S = myokit_b200.SimulationCUDA
+    out = {}
+    out['1d_fp64'] = workloads.c1_cable(S, 64)
+    out['2d_fp32'] = workloads.c2_planar(S, 32)
+    out['2d_hetero_rl_field'] = workloads.c3_hetero(S, nx=16)
+    s = S(m, p, ncells=16, precision=DP)
+    s.set_connections([(0, 1, 1.0), (1, 5, 2.0)])
+    out['connections'] = s
+    s = S(m, p, ncells=8, diffusion=False, precision=SP, native_maths=True)
+    out['no_diffusion_native'] = s
+    s = S(m, p, ncells=(8, 8), precision=DP)
+    s.set_paced_cell_list([(0, 0), (3, 4)])
+    out['paced_list'] = s
+    return out
+
+
+def test_every_kernel_variant_compiles_for_sm100a():
+    for name, s in variants().items():
+        src = s.kernel_source()
+        cubin, log = capi.jit_compile(src.code, src.options)
+        assert cubin[:4] == b'\x7fELF', name
+        assert src.kernel_name.encode() in cubin, name
+
+
+def test_generated_source_follows_reference_arithmetic():
+    s = variants()['1d_fp64']
+    code = s.kernel_source().code
+    # expression text comes from myokit's own CUDA writer
+    assert 'pow(V_m, 3.0)' in code
+    # zero-flux stencil forms, openclsim.cl:406-415
+    assert 'gx * (vc - vxp)' in code and 'gx * (2 * vc - vxm - vxp)' in code
+    # forward Euler update, V goes to the second V plane
+    assert 'v_out[cid] = V_V + dt * D_V;' in code
+    assert 'state[1ull * stride + cid] = V_m + dt * D_m;' in code
+    # Rush-Larsen update, openclsim.cl:362
+    code = variants()['2d_hetero_rl_field'].kernel_source().code
+    assert re.search(r'= V_\w+ - \(V_\w+ - V_\w+\) \* exp\(-dt / V_\w+\);', code)
+    assert 'gxf[cid - iy - 1] * (vc - vxm)' in code
+    # fp32: float literals and float maths
+    code = variants()['2d_fp32'].kernel_source().code
+    assert 'typedef float Real;' in code and 'expf(' in code
+    assert re.search(r'\d\.\d+f\b', code)
+    # native maths
+    code = variants()['no_diffusion_native'].kernel_source().code
+    assert '__expf(' in code
+
+
+def test_logged_intermediaries_are_stored_only_on_logged_steps():
+    m, p, _ = myokit.load('example')
+    s = myokit_b200.SimulationCUDA(m, p, ncells=8, precision=DP)
+    src = s.kernel_source([s._model.get('ica.ICa')])
+    assert src.n_inter == 1
+    assert 'if (store_aux) ((Real*)g.inter)[0ull * stride + cid] = V_ICa;' \
+        in src.code
+
+
+# ---------------------------------------------------------------------------
+# SimulationCUDA argument checking (reference: test_simulation_opencl.py)
+# ---------------------------------------------------------------------------
+def test_creation_errors():
+    m = br()
+    S = myokit_b200.SimulationCUDA
+    m2 = m.clone()
+    m2.label('membrane_potential').set_rhs(None)
+    with pytest.raises(myokit.MissingRhsError):
+        S(m2)
+    m2 = m.clone()
+    x = m2.get('ix1').add_variable('xx')
+    x.set_rhs('membrane.i_ion')
+    with pytest.raises(ValueError, match='interdependent'):
+        S(m2)
+    assert S(m, ncells=1).shape() == 1
+    assert S(m, ncells=50).shape() == 50
+    assert S(m, ncells=(2, 1)).shape() == (1, 2)
+    for bad in (None, (1,), (1, 1, 1)):
+        with pytest.raises(ValueError, match=r'scalar or a tuple \(nx, ny\)'):
+            S(m, ncells=bad)
+    for bad in (-1, 0, (0, 10), (10, 0), (-1, -1)):
+        with pytest.raises(ValueError, match='at least 1'):
+            S(m, ncells=bad)
+    with pytest.raises(ValueError, match='Only single and double'):
+        S(m, precision=SP + DP)
+    m2 = m.clone()
+    m2.label('membrane_potential').set_label(None)
+    with pytest.raises(ValueError, match='requires the membrane potential'):
+        S(m2)
+    m2.get('ina.INa').set_label('membrane_potential')
+    with pytest.raises(ValueError, match='must be a state variable'):
+        S(m2)
+    # without diffusion or RL the label is not needed
+    m2 = m.clone()
+    m2.label('membrane_potential').set_label(None)
+    S(m2, diffusion=False)
+
+
+def test_conductance_setters():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=4)
+    assert s.conductance() == 10
+    s.set_conductance(3)
+    assert s.conductance() == 3
+    with pytest.raises(ValueError, match='Invalid conductance gx'):
+        s.set_conductance(-1)
+    s2 = myokit_b200.SimulationCUDA(m, ncells=(4, 3))
+    assert s2.conductance() == (10, 5)
+    with pytest.raises(ValueError, match='Invalid conductance gy'):
+        s2.set_conductance(1, -1)
+    # fields: shapes (nx-1,) / (ny, nx-1), (ny-1, nx)
+    s.set_conductance_field([1, 2, 3])
+    assert s.conductance() is None
+    with pytest.raises(ValueError, match='must have length 3'):
+        s.set_conductance_field([1, 2])
+    with pytest.raises(ValueError, match='must be None'):
+        s.set_conductance_field([1, 2, 3], [1])
+    with pytest.raises(ValueError, match='negative'):
+        s.set_conductance_field([1, -2, 3])
+    s2.set_conductance_field(np.ones((3, 3)), np.ones((2, 4)))
+    assert s2.conductance() is None
+    with pytest.raises(ValueError, match=r'`gx` must have dimensions'):
+        s2.set_conductance_field(np.ones((3, 4)), np.ones((2, 4)))
+    with pytest.raises(ValueError, match=r'`gy` must be set'):
+        s2.set_conductance_field(np.ones((3, 3)))
+    with pytest.raises(ValueError, match=r'`gy` must have dimensions'):
+        s2.set_conductance_field(np.ones((3, 3)), np.ones((3, 4)))
+    with pytest.raises(ValueError, match='negative'):
+        s2.set_conductance_field(np.ones((3, 3)), -np.ones((2, 4)))
+    # set_conductance clears fields
+    s.set_conductance(7)
+    assert s.conductance() == 7
+    # alias from BASELINE.json's north_star
+    s.set_heterogeneity([1, 2, 3])
+    assert s.conductance() is None
+
+
+def test_connections_validation():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=4)
+    s.set_connections([(0, 1, 1.0), (2, 1, 0.5)])
+    assert s.conductance() is None
+    assert s.neighbors(1) == [0, 2]
+    with pytest.raises(ValueError, match='cannot be None'):
+        s.set_connections(None)
+    with pytest.raises(ValueError, match='list of 3-tuples'):
+        s.set_connections([(0, 1)])
+    for bad in [(0, 0, 1), (-1, 0, 1), (0, 4, 1), (0, -1, 1)]:
+        with pytest.raises(ValueError, match='Invalid connection'):
+            s.set_connections([bad])
+    with pytest.raises(ValueError, match='Duplicate connection'):
+        s.set_connections([(0, 1, 1), (1, 0, 1)])
+    with pytest.raises(ValueError, match='Invalid conductance'):
+        s.set_connections([(0, 1, -1)])
+    s2 = myokit_b200.SimulationCUDA(m, ncells=(4, 3))
+    with pytest.raises(RuntimeError, match='1d mode'):
+        s2.set_connections([(0, 1, 1)])
+
+
+def test_diffusion_disabled_methods_raise():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=4, diffusion=False)
+    for call in (s.conductance, lambda: s.is_paced(0), lambda: s.neighbors(0),
+                 s.set_conductance, lambda: s.set_conductance_field([1] * 3),
+                 lambda: s.set_connections([(0, 1, 1)]), s.set_paced_cells,
+                 lambda: s.set_paced_cell_list([0])):
+        with pytest.raises(RuntimeError, match='unavailable when diffusion'):
+            call()
+
+
+def test_paced_cells_and_neighbors():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=10)
+    assert [s.is_paced(i) for i in range(10)] == [True] * 5 + [False] * 5
+    s.set_paced_cells(2, x=3)
+    assert [i for i in range(10) if s.is_paced(i)] == [3, 4]
+    s.set_paced_cells(-2, x=5)          # left of x
+    assert [i for i in range(10) if s.is_paced(i)] == [3, 4]
+    s.set_paced_cells(2, x=-3)          # counted from the right
+    assert [i for i in range(10) if s.is_paced(i)] == [7, 8]
+    s.set_paced_cell_list([1, 9, 1])
+    assert [i for i in range(10) if s.is_paced(i)] == [1, 9]
+    with pytest.raises(IndexError):
+        s.set_paced_cell_list([10])
+    with pytest.raises(IndexError):
+        s.is_paced(10)
+    with pytest.raises(ValueError):
+        s.is_paced(0, 1)
+    assert s.neighbors(0) == [1]
+    assert s.neighbors(4) == [3, 5]
+    assert s.neighbors(9) == [8]
+    s2 = myokit_b200.SimulationCUDA(m, ncells=(4, 3))
+    assert s2.is_paced(3, 2)            # default 5 x 5 rectangle covers it
+    s2.set_paced_cells(1, 2, 1, 1)
+    assert [(x, y) for y in range(3) for x in range(4)
+            if s2.is_paced(x, y)] == [(1, 1), (1, 2)]
+    s2.set_paced_cell_list([(0, 0), (3, 2)])
+    assert s2.is_paced(3, 2) and not s2.is_paced(2, 2)
+    with pytest.raises(IndexError):
+        s2.set_paced_cell_list([(4, 0)])
+    with pytest.raises(ValueError):
+        s2.is_paced(0)
+    assert s2.neighbors(0, 0) == [(1, 0), (0, 1)]
+    assert s2.neighbors(1, 1) == [(0, 1), (2, 1), (1, 0), (1, 2)]
+    assert s2.neighbors(3, 2) == [(2, 2), (3, 1)]
+
+
+def test_state_handling():
+    m = br()
+    n = m.count_states()
+    s = myokit_b200.SimulationCUDA(m, ncells=(3, 2))
+    init = m.initial_values(True)
+    assert s.state() == init * 6
+    assert s.state(2, 1) == init
+    assert s.default_state(0, 0) == init
+    one = [float(i) for i in range(n)]
+    s.set_state(one, 1, 1)
+    assert s.state(1, 1) == one
+    assert s.state(0, 1) == init
+    # x changes first: cell (1, 1) is cell 1 + 1 * 3 = 4
+    assert s.state()[4 * n:5 * n] == one
+    s.set_state(one)
+    assert s.state() == one * 6
+    full = list(np.arange(6 * n, dtype=float))
+    s.set_state(full)
+    assert s.state(2, 0) == full[2 * n:3 * n]
+    with pytest.raises(ValueError, match='argument x'):
+        s.set_state(full, 1)
+    with pytest.raises(ValueError, match='same size'):
+        s.set_state(one[:-1])
+    with pytest.raises(IndexError):
+        s.set_state(one, 3, 0)
+    with pytest.raises(IndexError):
+        s.state(0, 2)
+    s.reset()
+    assert s.state() == init * 6
+    s.set_default_state(one, 0, 0)
+    s.reset()
+    assert s.state(0, 0) == one and s.state(1, 0) == init
+    s1 = myokit_b200.SimulationCUDA(m, ncells=3)
+    with pytest.raises(ValueError):
+        s1.state(0, 1)
+
+
+def test_fields_constants_time_step():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=(3, 2))
+    s.set_field('ina.gNaBar', np.ones((2, 3)))
+    with pytest.raises(ValueError, match='dimensions'):
+        s.set_field('ina.gNaBar', np.ones((3, 2)))
+    with pytest.raises(ValueError, match='Only constants'):
+        s.set_field('membrane.V', np.ones((2, 3)))
+    with pytest.raises(ValueError, match='Bound values'):
+        s.set_field('engine.pace', np.ones((2, 3)))
+    s.remove_field('ina.gNaBar')
+    with pytest.raises(KeyError):
+        s.remove_field('ina.gNaBar')
+    s.set_constant('ina.gNaBar', 3.5)
+    assert 'V_gNaBar = 3.5' in s.kernel_source().code
+    with pytest.raises(ValueError, match='not a literal'):
+        s.set_constant('membrane.i_ion', 1)
+    assert s.step_size() == 0.005
+    s.set_step_size(0.01)
+    assert s.step_size() == 0.01
+    with pytest.raises(ValueError, match='greater than zero'):
+        s.set_step_size(0)
+    assert s.time() == 0
+    s.set_time(3)
+    assert s.time() == 3
+    assert s.is_2d() and not myokit_b200.SimulationCUDA(m, ncells=3).is_2d()
+    assert s.monodomain_conductance(2, 3, 5, 0.1) == pytest.approx(
+        5 * 3 / (4 * 2 * 0.01))
+
+
+def test_run_argument_checks_and_zero_duration():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=2)
+    with pytest.raises(ValueError, match='negative'):
+        s.run(-1)
+    d = s.run(0)                # legal, never reaches the back-end
+    assert len(d) == 2 * m.count_states() + 1 + 1 + 2
+    with pytest.raises(ValueError, match='ProgressReporter'):
+        s.run(1, progress=12)
+
+
+@pytest.mark.skipif(HAS_GPU, reason='checks the no-GPU failure mode')
+def test_no_gpu_means_loud_failure_not_fallback():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=2)
+    with pytest.raises(capi.BackendError) as e:
+        s.run(1)
+    assert e.value.code == capi.MKB_ERR_CUDA
+    assert 'no CPU fallback' in str(e.value)
+    # and the product never touches the oracle
+    import sys
+    for name, mod in list(sys.modules.items()):
+        if name.startswith('myokit_b200'):
+            src = getattr(mod, '__file__', None)
+            if src and src.endswith('.py'):
+                with open(src) as f:
+                    text = f.read()
+                assert 'import oracle' not in text
+                assert 'from oracle' not in text

@@ -1,0 +1,506 @@
+"""
+Parity of the CUDA path (through libmyokit_b200.so) against the CPU oracle and
+the golden vectors of the reference's Simulation1d. Needs a B200.
+
+Tolerances are the north star's (BASELINE.json):
+  fp64: max |dV| <= 1e-6 mV per logged sample;
+  fp32: activation times within one dt;
+  spiral-type configurations: state within 1e-3 relative over a short horizon.
+Observed differences are far smaller (1e-12 mV for fp64); the asserts use the
+contract, the comments say what was measured.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import myokit_b200
+from myokit_b200 import capi, workloads
+import myokit
+
+from oracle.oracle import OracleSimulation
+from util import run_pair, max_abs_diff, configure
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+DP = myokit.DOUBLE_PRECISION
+SP = myokit.SINGLE_PRECISION
+PULSE = dict(duration=2, offset=1, period=1000)
+TOL_V = 1e-6
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    log = dict((k[4:], z[k]) for k in z.files if k.startswith('log:'))
+    return log, z['state']
+
+
+def example():
+    m, p, _ = myokit.load('example')
+    return m, p
+
+
+def test_device_is_blackwell_and_library_is_native():
+    assert capi.device_count() >= 1
+    info = capi.device_info(0)
+    assert info['compute_capability'][0] == 10, info
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[0]: LR1991 cable, fp64, 1 s of 1 Hz pacing
+# ---------------------------------------------------------------------------
+def test_c1_cable_fp64_one_second():
+    s = workloads.c1_cable(myokit_b200.SimulationCUDA, 128)
+    d = s.run(1000, log=['engine.time', 'membrane.V'], log_interval=1)
+    o = workloads.c1_cable(OracleSimulation, 128)
+    ol, ostate = o.run(1000, log=['engine.time', 'membrane.V'], log_interval=1)
+    assert len(d['engine.time']) == 1000
+    assert s.last_run_info()['steps'] == 200000 == o.last_steps
+    cl = dict((k, np.asarray(v)) for k, v in d.items())
+    assert max_abs_diff(cl, ol, ['engine.time']) == 0
+    assert cl['127.membrane.V'].max() > 0           # propagated
+    w = max_abs_diff(cl, ol, suffix='membrane.V')   # measured: ~2e-12
+    assert w <= TOL_V, w
+    assert np.max(np.abs(s.state_array() - ostate)) <= TOL_V
+
+
+@pytest.mark.parametrize('name,n,dt,dur,li,rl,paced,logvars', [
+    ('sim1d_lr91_c1', 128, 0.005, 120, 1, False, 5,
+     ['engine.time', 'engine.pace', 'membrane.V']),
+    ('sim1d_lr91_rl', 32, 0.01, 80, 1, True, 5,
+     ['engine.time', 'membrane.V', 'ina.m']),
+])
+def test_golden_reference_simulation1d(name, n, dt, dur, li, rl, paced,
+                                       logvars):
+    log, state = load_golden(name)
+    m, p = example()
+    s = myokit_b200.SimulationCUDA(m, p, ncells=n, precision=DP, rl=rl)
+    s.set_conductance(10)
+    s.set_paced_cells(paced)
+    s.set_step_size(dt)
+    d = s.run(dur, log=logvars, log_interval=li)
+    cl = dict((k, np.asarray(v)) for k, v in d.items())
+    assert set(cl.keys()) == set(log.keys())
+    assert max_abs_diff(cl, log, ['engine.time']) < 1e-17
+    assert max_abs_diff(cl, log) <= TOL_V
+    assert np.max(np.abs(s.state_array() - state)) <= TOL_V
+
+
+def test_golden_br77_reference_contract():
+    # Configuration of myokit/tests/test_simulation_opencl_vs_sim1d.py
+    log, state = load_golden('sim1d_br77')
+    m = workloads.data_model('beeler-1977-model.mmt')
+    p = myokit.pacing.blocktrain(duration=2, offset=1, period=1000)
+    s = myokit_b200.SimulationCUDA(m, p, ncells=10, precision=DP)
+    s.set_conductance(10)
+    s.set_paced_cells(3)
+    d = s.run(15, log=['engine.time', 'engine.pace', 'membrane.V',
+                       'membrane.i_diff', 'isi.Isi'], log_interval=0.5)
+    cl = dict((k, np.asarray(v)) for k, v in d.items())
+    assert max_abs_diff(cl, log, ['engine.time', 'engine.pace']) < 1e-17
+    # the reference asserts 1e-13 between two CPU builds; a GPU libm differs
+    # in the last ulp of exp/log, measured ~1e-12
+    assert max_abs_diff(cl, log) <= 1e-9
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[1]: LR1991 2-D planar wave, fp32, activation times
+# ---------------------------------------------------------------------------
+def activation_times(log, keys, times, threshold=-40.0):
+    out = []
+    for k in keys:
+        v = np.asarray(log[k])
+        idx = np.nonzero(v >= threshold)[0]
+        out.append(times[idx[0]] if len(idx) else np.nan)
+    return np.array(out)
+
+
+def test_c2_planar_fp32_activation_times_within_one_dt():
+    nx, ny, dt = 96, 24, 0.005
+    keys = ['%d.12.membrane.V' % x for x in range(nx)]
+    logspec = ['engine.time'] + keys
+    res = []
+    for cls in (myokit_b200.SimulationCUDA, OracleSimulation):
+        m, _ = example()
+        p = myokit.pacing.blocktrain(**PULSE)
+        s = cls(m, p, ncells=(nx, ny), precision=SP)
+        s.set_conductance(10, 10)
+        s.set_paced_cells(nx=5, ny=ny, x=0, y=0)
+        s.set_step_size(dt)
+        r = s.run(22, log=logspec, log_interval=dt)
+        r = r[0] if isinstance(r, tuple) else r
+        res.append(dict((k, np.asarray(v, dtype=np.float64))
+                        for k, v in r.items()))
+    a, b = res
+    assert len(a['engine.time']) == len(b['engine.time'])
+    assert np.array_equal(a['engine.time'], b['engine.time'])
+    ta = activation_times(a, keys, a['engine.time'])
+    tb = activation_times(b, keys, b['engine.time'])
+    assert not np.any(np.isnan(tb)), 'wave must cross the whole row'
+    assert np.max(np.abs(ta - tb)) <= dt * 1.0001     # measured: 0
+    assert ta[-1] > ta[0]
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[2] (crop): ORd-class fp64 RL, conductance + scalar fields
+# ---------------------------------------------------------------------------
+def test_c3_hetero_fields_rush_larsen_crop():
+    logspec = ['engine.time', 'membrane.V', 'ikr.IKr', 'membrane.i_diff']
+    a = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=40, ny=24)
+    d = a.run(8, log=logspec, log_interval=0.5)
+    b = workloads.c3_hetero(OracleSimulation, nx=40, ny=24)
+    ol, ostate = b.run(8, log=logspec, log_interval=0.5)
+    cl = dict((k, np.asarray(v)) for k, v in d.items())
+    assert cl['39.23.membrane.V'].max() > 0 or cl['30.12.membrane.V'].max() > 0
+    assert max_abs_diff(cl, ol, ['engine.time']) == 0
+    w = max_abs_diff(cl, ol, suffix='membrane.V')       # measured ~1e-12
+    assert w <= TOL_V, w
+    assert max_abs_diff(cl, ol, suffix='i_diff') <= 1e-6
+    assert max_abs_diff(cl, ol, suffix='IKr') <= 1e-9
+    rel = np.abs(a.state_array() - ostate) / (np.abs(ostate) + 1e-12)
+    assert rel.max() <= 1e-6
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[3] (proxy, crop): broken wave, fp32, 1e-3 relative
+# ---------------------------------------------------------------------------
+def test_c4_spiral_proxy_fp32_state_within_1e3():
+    nx = ny = 48
+    m, _ = example()
+    n = m.count_states()
+    init = np.array(m.initial_values(True))
+    # Prescribed broken wave: a depolarised band in the lower half with a
+    # refractory (inactivated) tail to one side of it
+    state = np.tile(init, nx * ny).reshape(ny, nx, n)
+    iv = m.get('membrane.V').index()
+    ih, ij = m.get('ina.h').index(), m.get('ina.j').index()
+    state[:ny // 2, 18:24, iv] = 10.0
+    state[:ny // 2, 10:18, ih] = 0.0
+    state[:ny // 2, 10:18, ij] = 0.0
+    state[:ny // 2, 10:18, iv] = -40.0
+    cfg = dict(conductance=(6, 6), paced_cells=(0, 0, 0, 0),
+               state=state.ravel())
+    cl, cs, ol, os_ = run_pair(m, None, (nx, ny), 20,
+                               ['engine.time', 'membrane.V'], 2.0,
+                               precision=SP, cfg=cfg)
+    V = np.array([cl['%d.%d.membrane.V' % (x, y)][-1]
+                  for y in range(ny) for x in range(nx)]).reshape(ny, nx)
+    assert V.max() - V.min() > 50         # there is a wave, and it is 2-d
+    assert np.std(V[:, 30]) > 1
+    scale = np.abs(os_).reshape(-1, n).max(axis=0)
+    rel = np.abs(cs - os_).reshape(-1, n) / scale
+    assert rel.max() <= 1e-3, rel.max()   # measured ~1e-5
+
+
+# ---------------------------------------------------------------------------
+# Connections
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('precision,tol', [(DP, 1e-9), (SP, 1e-4)])
+def test_connections_equal_conductance(precision, tol):
+    # myokit/tests/test_simulation_opencl.py:394-528
+    m, _ = example()
+    p = myokit.pacing.blocktrain(**PULSE)
+    n = 24
+    logspec = ['engine.time', 'membrane.V']
+    s1 = myokit_b200.SimulationCUDA(m, p, ncells=n, precision=precision)
+    s1.set_conductance(9)
+    s1.set_paced_cells(3)
+    d1 = s1.run(10, log=logspec, log_interval=0.5)
+    s2 = myokit_b200.SimulationCUDA(m, p, ncells=n, precision=precision)
+    s2.set_connections([(i, i + 1, 9) for i in range(n - 1)])
+    s2.set_paced_cells(3)
+    d2 = s2.run(10, log=logspec, log_interval=0.5)
+    a = dict((k, np.asarray(v, dtype=np.float64)) for k, v in d1.items())
+    b = dict((k, np.asarray(v, dtype=np.float64)) for k, v in d2.items())
+    assert a['%d.membrane.V' % (n - 1)].max() > 0
+    assert max_abs_diff(a, b) < tol
+
+
+def test_connections_arbitrary_graph_vs_oracle():
+    m, _ = example()
+    p = myokit.pacing.blocktrain(**PULSE)
+    n = 40
+    rng = np.random.default_rng(7)
+    conns = [(i, i + 1, 8.0) for i in range(n - 1)]
+    seen = set((i, i + 1) for i in range(n - 1))
+    while len(conns) < n + 25:
+        i, j = sorted(int(x) for x in rng.integers(0, n, size=2))
+        if i != j and (i, j) not in seen:
+            seen.add((i, j))
+            conns.append((j, i, float(rng.uniform(0.1, 3))))
+    cfg = dict(connections=conns, paced_cells=(4,))
+    cl, cs, ol, os_ = run_pair(m, p, n, 8, ['engine.time', 'membrane.V',
+                                            'membrane.i_diff'], 0.5, cfg=cfg)
+    assert max_abs_diff(cl, ol, suffix='membrane.V') <= TOL_V
+    assert max_abs_diff(cl, ol, suffix='i_diff') <= 1e-6
+    assert np.max(np.abs(cs - os_)) <= TOL_V
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs[4]-style population: uncoupled cells with per-cell fields
+# ---------------------------------------------------------------------------
+def test_uncoupled_population_with_fields():
+    m = workloads.data_model('decker-2009.mmt')
+    p = myokit.pacing.blocktrain(**PULSE)
+    n = 300
+    rng = np.random.default_rng(42)
+    fields = {
+        'ikr.Gbar': 0.0138542 * (1 - rng.uniform(0, 1, n)),
+        'ina.Gbar': 9.075 * (1 - 0.5 * rng.uniform(0, 1, n)),
+        'ik1.Gbar': 0.5 * (1 - 0.5 * rng.uniform(0, 1, n)),
+    }
+    cfg = dict(fields=fields)
+    cl, cs, ol, os_ = run_pair(m, p, n, 6, ['engine.time', 'membrane.V'],
+                               0.5, diffusion=False, rl=True, cfg=cfg)
+    assert cl['0.membrane.V'].max() > 0
+    assert not np.array_equal(cl['0.membrane.V'], cl['1.membrane.V'])
+    assert max_abs_diff(cl, ol, suffix='membrane.V') <= TOL_V
+    rel = np.abs(cs - os_) / (np.abs(os_) + 1e-12)
+    assert rel.max() <= 1e-6
+
+
+# ---------------------------------------------------------------------------
+# Logging, schedule, pacing selections
+# ---------------------------------------------------------------------------
+def test_logging_all_kinds_and_intermediary_steps():
+    m, _ = example()
+    p = myokit.pacing.blocktrain(duration=0.5, offset=0.25, period=3)
+    cfg = dict(conductance=(10, 5), paced_cell_list=[(0, 0), (1, 1), (5, 3)])
+    logspec = ['engine.time', 'engine.pace', 'membrane.V', 'membrane.i_diff',
+               'ica.ICa', 'ina.m', '2.1.ik.IK']
+    # log_interval 0.1 with dt 0.005 produces sub-ulp intermediary steps
+    cl, cs, ol, os_ = run_pair(m, p, (8, 5), 7, logspec, 0.1, cfg=cfg)
+    assert len(cl['engine.time']) == 70
+    assert set(cl.keys()) == set(ol.keys())
+    assert '2.1.ik.IK' in cl and '0.0.ik.IK' not in cl
+    assert max_abs_diff(cl, ol, ['engine.time', 'engine.pace']) == 0
+    assert max_abs_diff(cl, ol) <= TOL_V
+    assert cl['engine.pace'].max() == 1
+    assert np.max(np.abs(cs - os_)) <= TOL_V
+
+
+def test_log_interval_periodic_and_continuation():
+    # myokit/tests/test_simulation_log_interval.py:21-62
+    m, p = example()
+    s = myokit_b200.SimulationCUDA(m, p, ncells=2, precision=DP)
+    d = s.run(10, log=['engine.time'], log_interval=0.5)
+    t = np.asarray(d['engine.time'])
+    assert len(t) == 20
+    assert np.max(np.abs(t - np.arange(0, 10, 0.5))) < 1e-2
+    d = s.run(10, log=d, log_interval=0.5)       # append to the same log
+    t = np.asarray(d['engine.time'])
+    assert len(t) == 40
+    assert np.max(np.abs(t - np.arange(0, 20, 0.5))) < 1e-2
+    assert s.time() == 20
+    # log every step
+    s.reset()
+    d = s.run(1, log=['engine.time', '0.membrane.V'], log_interval=0)
+    assert len(d['engine.time']) == 200
+
+
+def test_fp32_time_is_logged_as_float():
+    m, p = example()
+    s = myokit_b200.SimulationCUDA(m, p, ncells=2, precision=SP)
+    d = s.run(3, log=['engine.time'], log_interval=0.3)
+    assert d['engine.time'].typecode == 'f'
+    o = OracleSimulation(m, p, ncells=2, precision=SP)
+    ol, _ = o.run(3, log=['engine.time'], log_interval=0.3)
+    assert np.array_equal(np.asarray(d['engine.time'], dtype=np.float64),
+                          ol['engine.time'])
+
+
+def test_paced_rectangle_outside_grid_and_negative_time():
+    m, _ = example()
+    p = myokit.pacing.blocktrain(duration=1, offset=-4, period=1000)
+    cfg = dict(conductance=(4, 4), paced_cells=(-3, 4, -2, 1), time=-5)
+    cl, cs, ol, os_ = run_pair(m, p, (9, 6), 6, ['engine.time', 'engine.pace',
+                                                 'membrane.V'], 0.5, cfg=cfg)
+    assert cl['engine.time'][0] == -5
+    assert max_abs_diff(cl, ol) <= TOL_V
+    # cells (4..6, 1..4) are the paced ones: they lead
+    assert cl['5.2.membrane.V'].max() > cl['0.0.membrane.V'].max() - 200
+    assert np.max(np.abs(cs - os_)) <= TOL_V
+
+
+def test_state_indexing_x_fastest():
+    m, _ = example()
+    n = m.count_states()
+    s = myokit_b200.SimulationCUDA(m, None, ncells=(4, 3), precision=DP)
+    s.set_conductance(0, 0)
+    x = np.array(m.initial_values(True))
+    x2 = x.copy()
+    x2[m.get('membrane.V').index()] = 20.0
+    s.set_state(x2, 3, 1)
+    d = s.run(0.01, log=['membrane.V'], log_interval=0.005)
+    assert d['3.1.membrane.V'][0] == 20.0
+    assert d['1.2.membrane.V'][0] == x[0]
+    st = np.asarray(s.state()).reshape(12, n)
+    assert abs(st[3 + 1 * 4, 0] - 20.0) < 5
+    assert abs(st[0, 0] - x[0]) < 1
+
+
+def test_run_pre_reset_semantics():
+    m, p = example()
+    s = myokit_b200.SimulationCUDA(m, p, ncells=4, precision=DP)
+    init = s.state()
+    s.pre(5)
+    assert s.time() == 0
+    assert s.state() != init
+    assert s.default_state() == s.state()
+    after_pre = s.state()
+    s.run(5)
+    assert s.time() == 5
+    assert s.state() != after_pre
+    s.reset()
+    assert s.time() == 0 and s.state() == after_pre
+    # two runs of 5 == one run of 10
+    a = myokit_b200.SimulationCUDA(m, p, ncells=4, precision=DP)
+    a.run(5)
+    a.run(5)
+    b = myokit_b200.SimulationCUDA(m, p, ncells=4, precision=DP)
+    b.run(10)
+    assert a.state() == b.state()
+
+
+def test_protocol_swap_and_no_protocol():
+    m, _ = example()
+    s = myokit_b200.SimulationCUDA(m, None, ncells=3, precision=DP)
+    d = s.run(3, log=['engine.pace', '0.membrane.V'], log_interval=0.5)
+    assert max(d['engine.pace']) == 0
+    s.set_protocol(myokit.pacing.blocktrain(duration=2, offset=0, period=10))
+    s.reset()
+    d = s.run(3, log=['engine.pace', '0.membrane.V'], log_interval=0.5)
+    assert max(d['engine.pace']) == 1
+    assert max(d['0.membrane.V']) > 0
+
+
+def test_progress_and_cancel():
+    m, p = example()
+
+    class Counter(myokit.ProgressReporter):
+        def __init__(self, cancel_at=None):
+            self.calls, self.cancel_at = 0, cancel_at
+
+        def enter(self, msg=None):
+            pass
+
+        def exit(self):
+            pass
+
+        def update(self, f):
+            self.calls += 1
+            assert 0 <= f <= 1
+            return self.cancel_at is None or self.calls < self.cancel_at
+
+    s = myokit_b200.SimulationCUDA(m, p, ncells=2, precision=DP)
+    c = Counter()
+    s.run(30, progress=c)       # 6000 steps, >= 1000 per call
+    assert c.calls >= 2
+    with pytest.raises(myokit.SimulationCancelledError):
+        s.run(30, progress=Counter(cancel_at=1))
+
+
+def test_nan_halts_and_reports():
+    m, p = example()
+    s = myokit_b200.SimulationCUDA(m, p, ncells=4, precision=DP)
+    x = np.array(m.initial_values(True))
+    x[0] = np.nan
+    s.set_state(x, 0)
+    with pytest.raises(myokit.SimulationError, match='Numerical error'):
+        s.run(20, log=['engine.time', 'membrane.V'], log_interval=1)
+    s.set_state(x, 0)
+    d = s.run(20, log=['engine.time', 'membrane.V'], log_interval=1,
+              report_nan=False)
+    # the reference stops right after the first logged NaN (openclsim.c:1087)
+    assert len(d['engine.time']) == 1
+
+
+def test_set_constant_and_field_override():
+    m, _ = example()
+    p = myokit.pacing.blocktrain(**PULSE)
+    cfg = dict(constants={'ina.gNa': 8.0}, paced_cells=(2,))
+    cl, cs, ol, os_ = run_pair(m, p, 6, 5, ['engine.time', 'membrane.V'], 0.5,
+                               cfg=cfg)
+    assert max_abs_diff(cl, ol) <= TOL_V
+    base, _, _, _ = run_pair(m, p, 6, 5, ['engine.time', 'membrane.V'], 0.5,
+                             cfg=dict(paced_cells=(2,)))
+    assert max_abs_diff(cl, base) > 1e-3
+
+
+def test_run_fields_matches_run():
+    m, _ = example()
+    p = myokit.pacing.blocktrain(**PULSE)
+
+    def make():
+        s = myokit_b200.SimulationCUDA(m, p, ncells=(10, 6), precision=DP)
+        s.set_paced_cells(2, 6, 0, 0)
+        return s
+    a = make()
+    d = a.run(4, log=['engine.time', 'membrane.V', 'ica.ICa',
+                      'membrane.i_diff'], log_interval=0.5)
+    b = make()
+    t, f = b.run_fields(4, ['membrane.V', 'ica.ICa', 'membrane.i_diff'],
+                        log_interval=0.5)
+    assert np.array_equal(t, np.asarray(d['engine.time']))
+    assert f['membrane.V'].shape == (8, 6, 10)
+    for name in ('membrane.V', 'ica.ICa', 'membrane.i_diff'):
+        for (x, y) in ((0, 0), (9, 5), (3, 4)):
+            assert np.array_equal(f[name][:, y, x],
+                                  np.asarray(d['%d.%d.%s' % (x, y, name)]))
+    assert a.state() == b.state()
+    block = myokit.DataBlock2d(10, 6, t)
+    block.set2d('membrane.V', f['membrane.V'])
+
+
+# ---------------------------------------------------------------------------
+# Full-size, size-independent properties
+# ---------------------------------------------------------------------------
+def test_full_size_uniform_tissue_equals_single_cell():
+    # 2048 x 2048 LR1991 fp64, every cell paced, homogeneous conduction:
+    # idiff must be exactly 0 everywhere, every cell must follow the same
+    # trajectory bit for bit, and that trajectory is the 1-cell oracle's.
+    n = 2048
+    m, _ = example()
+    p = myokit.pacing.blocktrain(duration=1, offset=0.5, period=1000)
+    s = myokit_b200.SimulationCUDA(m, p, ncells=(n, n), precision=DP)
+    s.set_conductance(10, 7)
+    s.set_paced_cells(n, n, 0, 0)
+    t, f = s.run_fields(2.5, ['membrane.V', 'membrane.i_diff'],
+                        log_interval=0.5)
+    V = f['membrane.V']
+    assert V.shape == (5, n, n)
+    assert np.all(f['membrane.i_diff'] == 0)
+    assert np.all(V == V[:, :1, :1])
+    assert V[-1, 0, 0] > 0
+    o = OracleSimulation(m, p, ncells=1, precision=DP)
+    o.set_paced_cells(1)
+    ol, ostate = o.run(2.5, log=['engine.time', 'membrane.V'],
+                       log_interval=0.5)
+    assert np.array_equal(t, ol['engine.time'])
+    assert np.max(np.abs(V[:, 7, 1999] - ol['0.membrane.V'])) <= TOL_V
+    st = s.state_array().reshape(n * n, -1)
+    assert np.all(st == st[0])
+    assert np.max(np.abs(st[0] - ostate)) <= TOL_V
+
+
+def test_full_size_blocked_rows_do_not_couple():
+    # 1024 x 1024 with gy = 0 everywhere and identical rows: each row is an
+    # independent cable, so all rows stay identical and equal the oracle's
+    # 1-d cable of the same length (tests the y-halo path with zero coupling
+    # and the x-direction stencil at full row length).
+    nx, ny = 1024, 1024
+    m, _ = example()
+    p = myokit.pacing.blocktrain(duration=1, offset=0.5, period=1000)
+    s = myokit_b200.SimulationCUDA(m, p, ncells=(nx, ny), precision=DP)
+    s.set_conductance_field(np.full((ny, nx - 1), 10.0), np.zeros((ny - 1, nx)))
+    s.set_paced_cells(5, ny, 0, 0)
+    t, f = s.run_fields(3, ['membrane.V'], log_interval=1)
+    V = f['membrane.V']
+    assert np.all(V == V[:, :1, :])
+    o = OracleSimulation(m, p, ncells=nx, precision=DP)
+    o.set_conductance(10)
+    o.set_paced_cells(5)
+    ol, _ = o.run(3, log=['membrane.V'], log_interval=1)
+    ref = np.array([ol['%d.membrane.V' % x] for x in range(nx)]).T
+    assert np.max(np.abs(V[:, 513, :] - ref)) <= TOL_V
