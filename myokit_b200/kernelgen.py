@@ -75,11 +75,236 @@ class _NativeCudaExpressionWriter(CudaExpressionWriter):
         return '__fdividef(' + self.ex(e[0]) + ', ' + self.ex(e[1]) + ')'
 
 
+def _integer_exponent(e):
+    """Returns k if ``e`` is a literal with a small integer value, else None."""
+    try:
+        if not e.is_literal():
+            return None
+        x = e.eval()
+    except Exception:
+        return None
+    if x != x or x in (float('inf'), float('-inf')):
+        return None
+    k = int(x)
+    if k != x or abs(k) > 32:
+        return None
+    return k
+
+
+class _PowMixin:
+    """
+    ``pow(x, k)`` with a small integer literal ``k`` becomes a fixed
+    square-and-multiply chain (``mkb_powi<k>``): 2-7 multiplications instead
+    of the ~100-instruction general ``pow``. Differs from ``pow`` by at most
+    a few ulp; covered by the parity tests against the oracle (which keeps
+    ``pow``). Exponent 0.5 becomes ``sqrt``. Anything else stays ``pow``.
+    """
+    _pow_multiply = True
+
+    def _ex_power(self, e):
+        if self._pow_multiply:
+            k = _integer_exponent(e[1])
+            if k is not None:
+                return 'mkb_powi<%d>(%s)' % (k, self.ex(e[0]))
+            # half-integer exponents: x^(k + 1/2) = x^k * sqrt(x)
+            try:
+                x2 = 2 * e[1].eval() if e[1].is_literal() else None
+            except Exception:
+                x2 = None
+            if x2 is not None and x2 == int(x2) and 0 < x2 <= 15:
+                k = (int(x2) - 1) // 2
+                sq = 'sqrtf' if self._sp else 'sqrt'
+                if k == 0:
+                    return '%s(%s)' % (sq, self.ex(e[0]))
+                return 'mkb_powh<%d>(%s)' % (k, self.ex(e[0]))
+        return super()._ex_power(e)
+
+
+class _DivMixin:
+    """Optional branch-free division (``mkb_div``), see the kernel prelude."""
+    _fast_div = False
+
+    def _ex_divide(self, e):
+        if self._fast_div:
+            return 'mkb_div(' + self.ex(e[0]) + ', ' + self.ex(e[1]) + ')'
+        return super()._ex_divide(e)
+
+
+class _ConstPoolMixin:
+    """
+    Double-precision literals that do not fit an instruction immediate go to
+    one ``__constant__`` table (``mkb_k``), in order of first use. sm_100a has
+    no 64-bit immediates: ptxas otherwise builds every such literal from two
+    32-bit moves (UMOV / IMAD.MOV), which was ~30% of all issued instructions
+    of a large fp64 model; from the table two adjacent constants arrive with
+    one uniform 128-bit load (LDCU.128) or are used as c-bank operands.
+    Literals whose low 32 mantissa bits are zero (1.0, 0.5, -80.0, ...) stay
+    in the instruction stream, where they are free.
+    """
+    _pool = None        # list of floats, or None when pooling is off
+
+    @staticmethod
+    def _is_cheap(x):
+        import struct
+        bits = struct.unpack('<Q', struct.pack('<d', x))[0]
+        return (bits & 0xffffffff) == 0
+
+    def pool_ref(self, x):
+        x = float(x)
+        if self._pool is None or x != x or self._is_cheap(x):
+            return None
+        key = x.hex()
+        i = self._pool_index.get(key)
+        if i is None:
+            i = len(self._pool)
+            self._pool.append(x)
+            self._pool_index[key] = i
+        return 'mkb_k[%d]' % i
+
+    def enable_pool(self):
+        self._pool = []
+        self._pool_index = {}
+
+    def _ex_number(self, e):
+        if self._pool is not None:
+            ref = self.pool_ref(e.eval())
+            if ref is not None:
+                return ref
+        return super()._ex_number(e)
+
+
+class _ExpMixin:
+    """Optional in-line double-precision exp (``mkb_exp``), see the prelude."""
+    _fast_exp = False
+
+    def _ex_exp(self, e):
+        if self._fast_exp and not self._sp:
+            return self._ex_function(e, 'mkb_exp')
+        return super()._ex_exp(e)
+
+
+class _Writer(_ConstPoolMixin, _PowMixin, _DivMixin, _ExpMixin,
+              CudaExpressionWriter):
+    pass
+
+
+class _NativeWriter(_PowMixin, _NativeCudaExpressionWriter):
+    pass
+
+
+_PRELUDE = r"""
+// x^k for a compile-time integer k: square-and-multiply, fixed order.
+template <int N>
+__device__ __forceinline__ Real mkb_powi(Real x) {
+    if constexpr (N < 0) {
+        return (Real)1 / mkb_powi<-N>(x);
+    } else if constexpr (N == 0) {
+        return (Real)1;
+    } else if constexpr (N == 1) {
+        return x;
+    } else if constexpr (N % 2 == 0) {
+        const Real h = mkb_powi<N / 2>(x);
+        return h * h;
+    } else {
+        return x * mkb_powi<N - 1>(x);
+    }
+}
+
+// x^(K + 1/2) = x^K * sqrt(x)
+template <int K>
+__device__ __forceinline__ Real mkb_powh(Real x) {
+    return mkb_powi<K>(x) * sqrt(x);
+}
+
+// Branch-free division (option fast_div): hardware reciprocal seed (~2^-23),
+// one Newton step on the reciprocal (~2^-46), then one residual correction of
+// the quotient (error ~2^-92 before the final rounding): within 1 ulp, not
+// guaranteed correctly rounded. Operands and quotient must be in the normal
+// range (|x| in [2^-1000, 2^1000]); b = 0, inf and NaN behave like IEEE;
+// denormal divisors are not supported.
+__device__ __forceinline__ double mkb_div(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    double q = a * r;
+    const double d = fma(-b, q, a);
+    const double q2 = fma(d, r, q);
+    // keep 0/inf/NaN results of a * r (d is NaN there)
+    return (d == d) ? q2 : q;
+}
+__device__ __forceinline__ float mkb_div(float a, float b) {
+    return __fdividef(a, b);
+}
+
+// exp(x) in double precision (option fast_exp): Cody-Waite reduction with a
+// fused multiply-add, degree-11 polynomial (scripts/gen_exp_coeffs.py, max
+// error 0.85 ulp against mpmath for |x| < 708), exponent inserted with one
+// integer add, no branches. The coefficients live in constant memory so they
+// arrive as c-bank operands / paired uniform loads instead of two 32-bit
+// moves each. Outside the normal range the result saturates instead of
+// following IEEE: x < -708 gives a value below 2.3e-308 (not a denormal or
+// 0), x > 709.7 gives a huge finite value or NaN (not +inf); NaN gives NaN;
+// |x| >= 2^31 and infinities are not supported.
+__constant__ double mkb_exp_c[14] = {
+@EXP_TABLE@
+};
+__device__ __forceinline__ double mkb_exp(double x) {
+    double t = fma(x, mkb_exp_c[0], mkb_exp_c[1]);
+    const int n = __double2loint(t);
+    t -= mkb_exp_c[1];
+    double r = fma(t, mkb_exp_c[2], x);
+    r = fma(t, mkb_exp_c[3], r);
+    double p = mkb_exp_c[4];
+#pragma unroll
+    for (int k = 5; k < 14; k++) p = fma(p, r, mkb_exp_c[k]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int nc = min(max(n, -1021), 1024);
+    const double y = __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
+    return y;
+}
+"""
+
+
+# Output of scripts/gen_exp_coeffs.py (degree 11, c11 .. c2)
+_EXP_COEFFS = [
+    '0x1.af632a0f7e2cep-26', '0x1.28b4101c77212p-22', '0x1.71ddf56d8deb5p-19',
+    '0x1.a01991a10d9aep-16', '0x1.a01a01b1461c5p-13', '0x1.6c16c1880029fp-10',
+    '0x1.111111110f21ep-7', '0x1.555555554f0bap-5', '0x1.555555555555ap-3',
+    '0x1.0000000000011p-1',
+]
+_EXP_TABLE = [
+    ('0x1.71547652b82fep+0', 'log2(e)'),
+    ('0x1.8p+52', '1.5 * 2^52: round-to-nearest-integer shift'),
+    ('-0x1.62e42fefa39efp-1', '-ln2, high part'),
+    ('-0x1.abc9e3b39803fp-56', '-ln2, low part'),
+] + [(c, 'c%d' % (11 - i)) for i, c in enumerate(_EXP_COEFFS)]
+_PRELUDE = _PRELUDE.replace('@EXP_TABLE@', '\n'.join(
+    '    %r,  // %s' % (float.fromhex(h), name) for h, name in _EXP_TABLE))
+
+
 def default_block(nx, ny, precision):
     """Thread-block tile ``(bx, by)`` for a grid of ``nx * ny`` cells."""
     if ny <= 1:
-        return (128, 1)
-    return (32, 4)
+        return (128, 1) if nx <= 4096 else (256, 1)
+    if nx >= 64:
+        return (64, 4)
+    return (32, 8) if ny >= 8 else (32, 4)
+
+
+def default_options(precision, n_state):
+    """
+    Generator defaults, from sweeps on a B200 (profiles/): double precision
+    uses the in-line division and exp and asks for two resident 256-thread
+    CTAs per SM (128 registers per thread) with states loaded 32 equations
+    ahead of use.
+    """
+    if precision == myokit.SINGLE_PRECISION:
+        return dict(min_blocks=None, fast_div=False, fast_exp=False,
+                    load_ahead=32)
+    return dict(min_blocks=2 if n_state > 16 else None, fast_div=True,
+                fast_exp=True, load_ahead=32)
 
 
 class KernelSource:
@@ -105,7 +330,9 @@ class KernelSource:
 
 def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              diffusion_mode, paced_list, block, native_maths=False, fmad=True,
-             max_registers=None):
+             max_registers=None, pow_multiply=True, fast_div=False,
+             lazy_state=True, min_blocks=None, fast_exp=False,
+             const_pool=True, load_ahead=8):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -113,16 +340,73 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     ``inter_log`` and ``fields`` are lists of variables in storage order;
     ``rl_states`` maps state -> (inf, tau); ``paced_list`` is True when paced
     cells are an explicit list (byte mask) instead of a rectangle.
+
+    Code-shape options (none changes which operations are evaluated or their
+    order, except ``pow_multiply`` / ``fast_div`` / ``fast_exp``, which swap a
+    library routine for a cheaper one of equal or near-equal accuracy):
+
+    ``lazy_state`` / ``load_ahead``
+        Load each state ``load_ahead`` equations before its first use and
+        store its new value as soon as it exists (short live ranges, loads
+        still ahead of use), instead of all loads first and all stores last.
+    ``min_blocks``
+        Second argument of ``__launch_bounds__``: resident CTAs per SM the
+        register allocation must allow.
+    ``const_pool``
+        Double-precision literals in a ``__constant__`` table.
     """
     sp = (precision == myokit.SINGLE_PRECISION)
     if native_maths and sp:
-        w = _NativeCudaExpressionWriter(precision)
+        w = _NativeWriter(precision)
     else:
-        w = CudaExpressionWriter(precision)
+        w = _Writer(precision)
+        w._fast_div = bool(fast_div)
+        w._fast_exp = bool(fast_exp)
+        if const_pool and not sp:
+            w.enable_pool()
+    w._pow_multiply = bool(pow_multiply)
+    pooled = getattr(w, '_pool', None) is not None
     fields = list(fields)
     inter_log = list(inter_log)
     bx, by = block
     diffusion = diffusion_mode != DIFF_NONE
+
+    equations = model.solvable_order()
+    del equations['*remaining*']
+
+    # Double precision: constants that do not depend on a field are evaluated
+    # here (host double arithmetic, the same values a compiler's constant
+    # folding produces up to the last ulp of log/exp/pow) and enter the
+    # kernel as literals / constant-table entries at their point of use.
+    folded = {}
+    if pooled:
+        field_dep = set(fields)
+        for group in equations.values():
+            for eq in group.equations(const=True):
+                var = eq.lhs.var()
+                if var in field_dep:
+                    continue
+                dep = False
+                for ref in eq.rhs.references():
+                    if ref.var() in field_dep:
+                        dep = True
+                        break
+                if dep:
+                    field_dep.add(var)
+                    continue
+                try:
+                    x = float(eq.rhs.eval())
+                except Exception:
+                    x = float('nan')
+                if x == x and x not in (float('inf'), float('-inf')):
+                    folded[var] = x
+
+    def number(x):
+        ref = w.pool_ref(x)
+        if ref is not None:
+            return ref
+        t = repr(float(x))
+        return '(' + t + ')' if t[0] == '-' else t
 
     def v(var):
         # openclsim.cl:99-113
@@ -132,20 +416,171 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             var = var.var()
         if var in bound_variables:
             return bound_variables[var]
+        if var in folded:
+            return number(folded[var])
         return 'V_' + var.uname()
     w.set_lhs_function(v)
-
-    equations = model.solvable_order()
-    del equations['*remaining*']
 
     n_state = model.count_states()
     vm = model.label('membrane_potential') if diffusion else None
     i_vm = vm.index() if vm is not None else -1
     real = 'float' if sp else 'double'
-    exp = 'expf' if sp else 'exp'
+    exp = 'expf' if sp else ('mkb_exp' if fast_exp else 'exp')
     if native_maths and sp:
         exp = '__expf'
+    states = list(model.states())
+    state_set = set(states)
+    inter_index = dict((var, k) for k, var in enumerate(inter_log))
 
+    def state_load(var, guarded=False):
+        k = var.index()
+        if k == i_vm:
+            return '    const Real %s = vc;' % v(var)
+        src = 'state[%dull * stride + cid]' % k
+        if guarded:
+            src = 'active ? %s : (Real)0' % src
+        return '    const Real %s = %s;' % (v(var), src)
+
+    def state_update(var):
+        # openclsim.cl:358-364
+        k = var.index()
+        if var in rl_states:
+            inf, tau = rl_states[var]
+            inf, tau, x = v(inf), v(tau), v(var)
+            rhs = '%s - (%s - %s) * %s(-dt / %s)' % (inf, inf, x, exp, tau)
+        else:
+            rhs = '%s + dt * %s' % (v(var), v(var.lhs()))
+        if k == i_vm:
+            return '    v_out[cid] = %s;' % rhs
+        return '    state[%dull * stride + cid] = %s;' % (k, rhs)
+
+    # Equations to emit, in the reference's order (openclsim.cl:235-243)
+    todo = []       # (component name or None, equation)
+    for name, group in equations.items():
+        first = True
+        for eq in group.equations(const=False):
+            var = eq.lhs.var()
+            if var in rl_states or var in bound_variables:
+                continue
+            todo.append((name if first else None, eq))
+            first = False
+
+    def refs(expr):
+        out = []
+        for ref in expr.references():
+            if isinstance(ref, myokit.Name) and ref.var() in state_set:
+                out.append(ref.var())
+        return sorted(set(out), key=lambda x: x.index())
+
+    # ------------------------------------------------------------------
+    # Section: model body (equations, loads, stores)
+    # ------------------------------------------------------------------
+    early = []      # state loads hoisted above the stencil (guarded)
+    body = []
+    if not lazy_state:
+        for var in states:
+            early.append(state_load(var, guarded=True))
+        for name, eq in todo:
+            if name:
+                body.append('    // Component: %s' % name)
+            var = eq.lhs.var()
+            body.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+            if var in inter_index and not eq.lhs.is_derivative():
+                body.append(
+                    '    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                    % (inter_index[var], v(eq.lhs)))
+        body.append('    // Update (openclsim.cl:358-364)')
+        for var in states:
+            body.append(state_update(var))
+    else:
+        # Same equations, same order, same arithmetic; only the position of
+        # the loads and stores differs. No thread reads another thread's
+        # states except V, which is double-buffered, and a state is loaded
+        # exactly once, so a store can never be observed by a load of the
+        # same step.
+        first_use = {}
+        for i, (name, eq) in enumerate(todo):
+            for r in refs(eq.rhs):
+                first_use.setdefault(r, i)
+        for var in states:      # never referenced: needed by its own update
+            first_use.setdefault(var, len(todo))
+        order = sorted(states, key=lambda x: (first_use[x], x.index()))
+        loaded = set()
+        have = set()
+        done = set()
+        ahead = max(int(load_ahead), 0)
+
+        def emit_loads(limit, dest, guarded):
+            for var in order:
+                if var in loaded:
+                    continue
+                if first_use[var] <= limit:
+                    dest.append(state_load(var, guarded))
+                    loaded.add(var)
+
+        def flush_updates():
+            for var in states:
+                if var in done:
+                    continue
+                if var in rl_states:
+                    ready = all(x in have for x in rl_states[var])
+                else:
+                    ready = ('D', var) in have
+                if ready:
+                    if var not in loaded:
+                        body.append(state_load(var))
+                        loaded.add(var)
+                    body.append(state_update(var))
+                    done.add(var)
+
+        emit_loads(ahead, early, True)
+        for i, (name, eq) in enumerate(todo):
+            if name:
+                body.append('    // Component: %s' % name)
+            emit_loads(i + ahead, body, False)
+            var = eq.lhs.var()
+            body.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+            if eq.lhs.is_derivative():
+                have.add(('D', var))
+            else:
+                have.add(var)
+                if var in inter_index:
+                    body.append(
+                        '    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                        % (inter_index[var], v(eq.lhs)))
+            flush_updates()
+        emit_loads(len(todo), body, False)
+        flush_updates()
+        missing = [x.qname() for x in states if x not in done]
+        if missing:     # pragma: no cover
+            raise RuntimeError('No update generated for: ' + ', '.join(missing))
+
+    # Constants that stay in the kernel (fields' dependants, single precision)
+    consts = []
+    for k, var in enumerate(fields):
+        early.append(
+            '    const Real %s = active ? ((const Real*)g.field)[%dull * stride + cid] : (Real)0;'
+            % (v(var), k))
+    consts.append('    // Literal constants (openclsim.cl:173-178)')
+    for group in equations.values():
+        for eq in group.equations(const=True):
+            if isinstance(eq.rhs, myokit.Number):
+                var = eq.lhs.var()
+                if var not in fields and var not in folded:
+                    consts.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+    consts.append('    // Calculated constants (openclsim.cl:181-186): folded (by the')
+    consts.append('    // compiler, or on the host for double precision) unless they')
+    consts.append('    // depend on a field')
+    for group in equations.values():
+        for eq in group.equations(const=True):
+            if not isinstance(eq.rhs, myokit.Number):
+                var = eq.lhs.var()
+                if var not in fields and var not in folded:
+                    consts.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+
+    # ------------------------------------------------------------------
+    # Assembly
+    # ------------------------------------------------------------------
     out = []
     p = out.append
     p('// Generated by myokit_b200.kernelgen for sm_100a — do not edit.')
@@ -154,8 +589,19 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('typedef %s Real;' % real)
     p('#define MKB_BX %d' % bx)
     p('#define MKB_BY %d' % by)
-    p('')
-    p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
+    p(_PRELUDE)
+    if pooled and w._pool:
+        p('// Model constants (double precision), in order of first use')
+        p('__constant__ double mkb_k[%d] = {' % len(w._pool))
+        for x in w._pool:
+            p('    %r,' % x)
+        p('};')
+        p('')
+    if min_blocks:
+        p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY, %d)'
+          % int(min_blocks))
+    else:
+        p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
     p('%s(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
     p('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
     p('{')
@@ -175,16 +621,36 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
     p('    (void)time; (void)pace_in; (void)store_aux; (void)v_in; (void)v_out;')
     p('')
+    if diffusion:
+        p('    const Real vc = active ? v_in[cid] : (Real)0;')
+    if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+        p('    const unsigned long long iyg = iy + g.iy_offset;  // global row')
+        p('    const unsigned long long nyg = g.ny_global;')
+    if diffusion_mode == DIFF_FIELD:
+        p('    // Edge conductances, gx[(ny, nx-1)], gy[(ny-1, nx)] (openclsim.cl:')
+        p('    // 475-482); both pointers are slab-relative: gyf[-nx .. -1] is the')
+        p('    // gy row that couples this slab\'s first row to the slab above it.')
+        p('    // Loaded here so they are in flight together with everything else.')
+        p('    const Real* const gxf = (const Real*)g.gx_field;')
+        p('    const Real* const gyf = (const Real*)g.gy_field;')
+        p('    const bool has_xm = active && nx > 1 && ix > 0;')
+        p('    const bool has_xp = active && nx > 1 && ix < nx - 1;')
+        p('    const bool has_ym = active && nyg > 1 && iyg > 0;')
+        p('    const bool has_yp = active && nyg > 1 && iyg < nyg - 1;')
+        p('    const Real gxm = has_xm ? gxf[cid - iy - 1] : (Real)0;')
+        p('    const Real gxp = has_xp ? gxf[cid - iy] : (Real)0;')
+        p('    const Real gym = has_ym ? gyf[(long long)cid - (long long)nx] : (Real)0;')
+        p('    const Real gyp = has_yp ? gyf[cid] : (Real)0;')
+    p('    // Loads issued ahead of use: fields and the first states')
+    for line in early:
+        p(line)
+    p('')
 
     if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
-        # --- V tile with halo in shared memory --------------------------
         p('    // V(t) tile + one-cell halo in shared memory. Out-of-grid halo')
         p('    // entries hold the cell\'s own V and are never used: the edge')
         p('    // formulas below drop those terms exactly as openclsim.cl does.')
-        p('    const unsigned long long iyg = iy + g.iy_offset;  // global row')
-        p('    const unsigned long long nyg = g.ny_global;')
         p('    __shared__ Real tile[MKB_BY + 2][MKB_BX + 2];')
-        p('    const Real vc = active ? v_in[cid] : (Real)0;')
         p('    tile[ty + 1][tx + 1] = vc;')
         p('    if (active) {')
         p('        if (tx == 0) tile[ty + 1][0] = (ix > 0) ? v_in[cid - 1] : vc;')
@@ -224,25 +690,16 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('        else idiff += gy * (2 * vc - vym - vyp);')
             p('    }')
         else:
-            p('    // openclsim.cl:469-486 (diff_hetero); gx[(ny, nx-1)], gy[(ny-1, nx)].')
-            p('    // Both pointers are slab-relative: gyf[-nx .. -1] is the gy row that')
-            p('    // couples this slab\'s first row to the slab above it.')
-            p('    const Real* const gxf = (const Real*)g.gx_field;')
-            p('    const Real* const gyf = (const Real*)g.gy_field;')
+            p('    // openclsim.cl:469-486 (diff_hetero)')
             p('    idiff = 0.0;')
-            p('    if (nx > 1) {')
-            p('        if (ix > 0) { idiff += gxf[cid - iy - 1] * (vc - vxm); }')
-            p('        if (ix < nx - 1) { idiff += gxf[cid - iy] * (vc - vxp); }')
-            p('    }')
-            p('    if (nyg > 1) {')
-            p('        if (iyg > 0) idiff += gyf[(long long)cid - (long long)nx] * (vc - vym);')
-            p('        if (iyg < nyg - 1) idiff += gyf[cid] * (vc - vyp);')
-            p('    }')
+            p('    if (has_xm) { idiff += gxm * (vc - vxm); }')
+            p('    if (has_xp) { idiff += gxp * (vc - vxp); }')
+            p('    if (has_ym) idiff += gym * (vc - vym);')
+            p('    if (has_yp) idiff += gyp * (vc - vyp);')
     elif diffusion_mode == DIFF_CONNECTIONS:
         p('    if (!active) return;')
         p('    // openclsim.cl:537-556 as a per-cell CSR gather: same terms')
         p('    // g * (V_i - V_j), summed in edge-list order, no atomics.')
-        p('    const Real vc = v_in[cid];')
         p('    Real idiff = 0;')
         p('    {')
         p('        const Real* const cg = (const Real*)g.csr_g;')
@@ -255,7 +712,6 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    if (!active) return;')
     p('')
 
-    # --- pacing ---------------------------------------------------------
     if diffusion:
         p('    // openclsim.cl:249-280, 322-329')
         if paced_list:
@@ -272,73 +728,17 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    const Real pace = pace_in;')
     p('    (void)pace;')
     p('')
-
-    # --- fields, constants, states --------------------------------------
-    p('    // Scalar fields (set_field): one plane each')
-    for k, var in enumerate(fields):
-        p('    const Real %s = ((const Real*)g.field)[%dull * stride + cid];'
-          % (v(var), k))
-    p('    // Literal constants (openclsim.cl:173-178)')
-    for group in equations.values():
-        for eq in group.equations(const=True):
-            if isinstance(eq.rhs, myokit.Number):
-                if eq.lhs.var() not in fields:
-                    p('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
-    p('    // Calculated constants (openclsim.cl:181-186); folded at compile')
-    p('    // time unless they depend on a field')
-    for group in equations.values():
-        for eq in group.equations(const=True):
-            if not isinstance(eq.rhs, myokit.Number):
-                if eq.lhs.var() not in fields:
-                    p('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
-    p('    // States at time t')
-    for var in model.states():
-        k = var.index()
-        if k == i_vm:
-            p('    const Real %s = vc;' % v(var))
-        else:
-            p('    const Real %s = state[%dull * stride + cid];' % (v(var), k))
+    for line in consts:
+        p(line)
     p('')
-
-    # --- equations --------------------------------------------------------
-    inter_index = dict((var, k) for k, var in enumerate(inter_log))
-    for name, group in equations.items():
-        eqs = []
-        for eq in group.equations(const=False):
-            var = eq.lhs.var()
-            if var in rl_states or var in bound_variables:
-                continue
-            eqs.append(eq)
-        if not eqs:
-            continue
-        p('    // Component: %s' % name)
-        for eq in eqs:
-            var = eq.lhs.var()
-            p('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
-            if var in inter_index and not eq.lhs.is_derivative():
-                p('    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
-                  % (inter_index[var], v(eq.lhs)))
-    p('')
-
-    # --- update -----------------------------------------------------------
-    p('    // Update (openclsim.cl:358-364)')
-    for var in model.states():
-        k = var.index()
-        if var in rl_states:
-            inf, tau = rl_states[var]
-            inf, tau, x = v(inf), v(tau), v(var)
-            rhs = '%s - (%s - %s) * %s(-dt / %s)' % (inf, inf, x, exp, tau)
-        else:
-            rhs = '%s + dt * %s' % (v(var), v(var.lhs()))
-        if k == i_vm:
-            p('    v_out[cid] = %s;' % rhs)
-        else:
-            p('    state[%dull * stride + cid] = %s;' % (k, rhs))
+    for line in body:
+        p(line)
     p('}')
     p('')
+    code = '\n'.join(out)
 
     options = ['--fmad=true' if fmad else '--fmad=false']
     if max_registers:
         options.append('--maxrregcount=%d' % int(max_registers))
-    return KernelSource('\n'.join(out), block, n_state, i_vm, len(inter_log),
+    return KernelSource(code, block, n_state, i_vm, len(inter_log),
                         len(fields), diffusion_mode, options)

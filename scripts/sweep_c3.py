@@ -1,0 +1,42 @@
+"""Kernel-option sweep on the C3 workload: compile stats here, timings on a GPU."""
+import os, sys, time, re, json
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R)
+import myokit_b200, myokit
+from myokit_b200 import workloads, capi
+
+grid = int(os.environ.get('SWEEP_GRID', '2048'))
+steps = int(os.environ.get('SWEEP_STEPS', '20'))
+variants = [
+    ('default', dict()),
+    ('la64', dict(load_ahead=64)),
+    ('la1000', dict(load_ahead=1000)),
+    ('b128x2', dict(block=(128, 2))),
+    ('b32x8', dict(block=(32, 8))),
+    ('b256x1', dict(block=(256, 1))),
+    ('mb3', dict(min_blocks=3)),
+    ('b32x4 mb4', dict(block=(32, 4), min_blocks=4)),
+    ('b64x2 mb4', dict(block=(64, 2), min_blocks=4)),
+    ('b64x6 mb1', dict(block=(64, 6), min_blocks=1)),
+    ('nopool', dict(const_pool=False)),
+    ('libdevice exp', dict(fast_exp=False)),
+]
+only = os.environ.get('SWEEP_ONLY')
+gpu = capi.device_count() > 0
+for name, opts in variants:
+    if only and only not in name:
+        continue
+    s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=grid if gpu else 16)
+    s.set_kernel_options(**opts)
+    src = s.kernel_source()
+    t0 = time.time()
+    cubin, log = capi.jit_compile(src.code, src.options + ('--ptxas-options=-v',))
+    m = re.search(r"Compiling entry function 'mkb_cell_step'.*?Used (\d+) registers", log, re.S)
+    sp = re.search(r"mkb_cell_step\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores", log, re.S)
+    line = '%-22s regs %s stack/spill %s cubin %d KB compile %.1fs' % (
+        name, m.group(1) if m else '?', sp.groups() if sp else '?', len(cubin) // 1024, time.time() - t0)
+    if gpu:
+        info = s.benchmark_steps(steps, warmup=3)
+        ms = info['device_ms'] / info['steps']
+        line += '  %.3f ms/step  %.3e cell-steps/s' % (ms, grid * grid / ms * 1e3)
+    print(line, flush=True)
