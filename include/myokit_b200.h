@@ -184,6 +184,23 @@ int mkb_sim_set_steps_per_call(mkb_sim* sim, uint64_t steps);
 int mkb_sim_reset_counters(mkb_sim* sim);
 void mkb_sim_clean(mkb_sim* sim);
 
+/* ---- row-slab sharding over several GPUs (no reference equivalent) ----
+ * A slab (iy_offset / ny_global in mkb_sim_config) with neighbours owns an
+ * "exchange block" in its own HBM: ghost rows of V (3 slots) and arrival flags.
+ * Neighbouring slabs write their boundary rows straight into it from the step
+ * kernel (peer stores over NVLink) and bump the flags; the step kernel of the
+ * owner waits on the flags. Sequence per rank: mkb_sim_init; halo_export;
+ * exchange handles (any transport, e.g. torch.distributed); halo_connect;
+ * barrier; mkb_sim_step ... */
+int mkb_sim_halo_info(mkb_sim* sim, int* has_lower, int* has_upper, uint64_t* bytes);
+/* ipc_handle_64: 64 bytes (cudaIpcMemHandle_t) for another process;
+ * device_pointer: the raw pointer, for a neighbour in the same process. */
+int mkb_sim_halo_export(mkb_sim* sim, void* ipc_handle_64, void** device_pointer);
+/* lower / upper: the neighbours' exports (rows below iy_offset / above the
+ * slab); direct = 0: pointers to 64-byte IPC handles, direct = 1: pointers to
+ * device pointers of sims living in this process. Null where no neighbour. */
+int mkb_sim_halo_connect(mkb_sim* sim, const void* lower, const void* upper, int direct);
+
 /* ---- pacing alone (unit tests; mirrors tests/ansic_event_based_pacing.c) ---- */
 int mkb_pacing_probe(double t0, int n_events, const double* events,
                      int n_times, const double* times,

@@ -30,7 +30,8 @@ SYMBOLS = [
     'mkb_device_info', 'mkb_device_abi_header', 'mkb_jit_compile',
     'mkb_sim_init', 'mkb_sim_step', 'mkb_sim_log_view', 'mkb_sim_get_state',
     'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
-    'mkb_sim_reset_counters', 'mkb_sim_clean',
+    'mkb_sim_reset_counters', 'mkb_sim_clean', 'mkb_sim_halo_info',
+    'mkb_sim_halo_export', 'mkb_sim_halo_connect',
     'mkb_pacing_probe',
 ]
 
@@ -117,6 +118,11 @@ def library():
     lib.mkb_sim_reset_counters.argtypes = [c_vp]
     lib.mkb_sim_clean.argtypes = [c_vp]
     lib.mkb_sim_clean.restype = None
+    lib.mkb_sim_halo_info.argtypes = [
+        c_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+        ctypes.POINTER(c_u64)]
+    lib.mkb_sim_halo_export.argtypes = [c_vp, c_vp, ctypes.POINTER(c_vp)]
+    lib.mkb_sim_halo_connect.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int]
     lib.mkb_pacing_probe.argtypes = [
         ctypes.c_double, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]
     if lib.mkb_abi_version() != MKB_ABI_VERSION:

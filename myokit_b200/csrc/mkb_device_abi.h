@@ -32,7 +32,7 @@ struct MkbStepParams {
     double dt;
     double pace;
     unsigned int flags;
-    unsigned int reserved;
+    unsigned int step;      /* 1-based index of this step within the run */
 };
 
 struct MkbGridArgs {
@@ -47,9 +47,26 @@ struct MkbGridArgs {
     const unsigned long long* csr_row;  /* [n+1] */
     const unsigned int* csr_col;        /* [nnz] */
     const void* csr_g;                  /* Real[nnz], signed per CSR entry */
-    /* V rows owned by neighbouring slabs (multi-GPU), else null */
-    const void* halo_lo;            /* Real[nx]: global row iy_offset-1 */
-    const void* halo_hi;            /* Real[nx]: global row iy_offset+ny */
+    /* Row-slab sharding (multi-GPU), all null on a single GPU.
+     * halo_lo / halo_hi: THIS GPU's ghost rows, Real[3][nx] each (slot =
+     *   step % 3): V(t_step) of global row iy_offset-1 / iy_offset+ny,
+     *   written by the neighbouring GPU's step kernel with peer stores over
+     *   NVLink; flag_lo / flag_hi: unsigned[n column blocks], the last step
+     *   whose row segment has landed (written by the neighbour after a
+     *   system-scope fence).
+     * peer_*: the same four arrays of the neighbouring GPUs, mapped into this
+     *   process (cudaIpcOpenMemHandle or direct peer access): this GPU's
+     *   first row goes to the lower neighbour's halo_hi, its last row to the
+     *   upper neighbour's halo_lo. */
+    const void* halo_lo;
+    const void* halo_hi;
+    const unsigned int* flag_lo;
+    const unsigned int* flag_hi;
+    void* peer_lo_halo_hi;
+    void* peer_hi_halo_lo;
+    unsigned int* peer_lo_flag_hi;
+    unsigned int* peer_hi_flag_lo;
+    unsigned int* halo_error;       /* set when a ghost-row wait times out */
     unsigned long long nx;          /* cells in x */
     unsigned long long ny;          /* rows in this slab */
     unsigned long long stride;      /* plane stride in elements */

@@ -127,6 +127,11 @@ __global__ void k_log_gather(const TR* __restrict__ base, const TR* __restrict__
     }
 }
 
+__global__ void k_fill_u32(unsigned int* p, u64 n, unsigned int value) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = value;
+}
+
 // ---------------------------------------------------------------------------
 // Library-level API
 // ---------------------------------------------------------------------------
@@ -235,6 +240,11 @@ extern "C" int mkb_pacing_probe(double t0, int n_events, const double* events, i
 // Simulation object
 // ---------------------------------------------------------------------------
 static const int kRingHalf = 1024;      // schedule entries per ring half
+// At most 2 * kThrottle step kernels are in flight per simulation. The driver's
+// launch queue is finite and a full queue blocks the launching thread inside
+// the runtime; with slabs of several GPUs driven from one process that could
+// stop the very thread whose kernels the queued ones are waiting for.
+static const int kThrottle = 128;
 
 struct StepRec {
     MkbStepParams p;
@@ -258,6 +268,9 @@ struct mkb_sim {
     cudaEvent_t ev_ring[2] = {nullptr, nullptr};
     cudaEvent_t ev_rows = nullptr, ev_copied[2] = {nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_throttle[2] = {nullptr, nullptr};
+    u64 throttle_count = 0;             // groups of kThrottle launches issued
+    u64 issued = 0;                     // step kernels launched in this run
     bool copied_pending[2] = {false, false};
 
     // device memory
@@ -297,6 +310,16 @@ struct mkb_sim {
     u64 h_log_cap = 0;                  // rows
     std::vector<double> row_time, row_pace;     // for rows >= rows_final
 
+    // row-slab halo exchange (multi-GPU)
+    char* d_xchg = nullptr;             // [halo_lo 3*nx][halo_hi 3*nx][flag_lo nbx][flag_hi nbx][error]
+    size_t xchg_bytes = 0;
+    u64 nbx = 0;                        // column blocks = flags per side
+    void* peer_lo_base = nullptr;       // neighbour exchange blocks as mapped here
+    void* peer_hi_base = nullptr;
+    bool peer_lo_ipc = false, peer_hi_ipc = false;
+    bool has_lo = false, has_hi = false;
+    u64 step_index = 0;                 // steps taken in this run (1-based in the kernel)
+
     // counters
     u64 launches = 0, steps = 0;
     double device_ms = 0;
@@ -325,11 +348,15 @@ static void sim_destroy(mkb_sim* s) {
     cudaFree(s->d_tab_pre);
     cudaFree(s->d_tab_post);
     cudaFree(s->d_log);
+    if (s->peer_lo_base && s->peer_lo_ipc) cudaIpcCloseMemHandle(s->peer_lo_base);
+    if (s->peer_hi_base && s->peer_hi_ipc) cudaIpcCloseMemHandle(s->peer_hi_base);
+    cudaFree(s->d_xchg);
     if (s->h_ring) cudaFreeHost(s->h_ring);
     if (s->h_log) cudaFreeHost(s->h_log);
     for (int i = 0; i < 2; i++) {
         if (s->ev_ring[i]) cudaEventDestroy(s->ev_ring[i]);
         if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+        if (s->ev_throttle[i]) cudaEventDestroy(s->ev_throttle[i]);
     }
     if (s->ev_rows) cudaEventDestroy(s->ev_rows);
     if (s->ev_t0) cudaEventDestroy(s->ev_t0);
@@ -471,7 +498,8 @@ static int sim_init_typed(mkb_sim* s, const mkb_sim_config* c) {
             // Slab copy with ny + 1 rows: local row r <- global gy row iy0 - 1 + r
             // (gy row j couples grid rows j and j + 1); missing rows stay zero.
             CUDA_TRY(cudaMalloc(&s->d_gy, (s->ny + 1) * s->nx * sizeof(TR)));
-            CUDA_TRY(cudaMemset(s->d_gy, 0, (s->ny + 1) * s->nx * sizeof(TR)));
+            CUDA_TRY(cudaMemsetAsync(s->d_gy, 0, (s->ny + 1) * s->nx * sizeof(TR), s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
             const u64 first = iy0 > 0 ? iy0 - 1 : 0;               // first global gy row
             const u64 last = std::min<u64>(iy0 + s->ny - 1, nyg - 2);   // last global gy row
             if (last >= first && nyg >= 2) {
@@ -517,6 +545,22 @@ static int sim_init_typed(mkb_sim* s, const mkb_sim_config* c) {
                             cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(s->d_csr_g, g.data(), (2 * ne + 1) * sizeof(TR), cudaMemcpyHostToDevice));
     }
+    return MKB_OK;
+}
+
+// CUDA loads kernels lazily: the first launch of a kernel may need a
+// context-wide synchronisation. A step kernel that is spinning on a
+// neighbour's arrival flag would then wait for a kernel that cannot be loaded
+// while it runs. Everything that can be launched during stepping is therefore
+// loaded up front.
+template <typename TR>
+static int preload_kernels(mkb_sim* s) {
+    cudaFuncAttributes a;
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)s->kern));
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_log_gather<TR>));
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_fill_u32));
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_soa_to_aos<TR, TR>));
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_soa_to_aos<TR, double>));
     return MKB_OK;
 }
 
@@ -614,6 +658,7 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     for (int i = 0; i < 2; i++) {
         INIT_CUDA(cudaEventCreateWithFlags(&s->ev_ring[i], cudaEventDisableTiming));
         INIT_CUDA(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+        INIT_CUDA(cudaEventCreateWithFlags(&s->ev_throttle[i], cudaEventDisableTiming));
     }
     INIT_CUDA(cudaEventCreateWithFlags(&s->ev_rows, cudaEventDisableTiming));
     INIT_CUDA(cudaEventCreate(&s->ev_t0));
@@ -625,8 +670,10 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
 
     // Buffers
     if (c->precision == MKB_DOUBLE) {
+        INIT_TRY(preload_kernels<double>(s));
         INIT_TRY(sim_init_typed<double>(s, c));
     } else {
+        INIT_TRY(preload_kernels<float>(s));
         INIT_TRY(sim_init_typed<float>(s, c));
     }
 
@@ -670,6 +717,29 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     g.csr_g = s->d_csr_g;
     g.halo_lo = nullptr;
     g.halo_hi = nullptr;
+    g.flag_lo = nullptr;
+    g.flag_hi = nullptr;
+    g.peer_lo_halo_hi = nullptr;
+    g.peer_hi_halo_lo = nullptr;
+    g.peer_lo_flag_hi = nullptr;
+    g.peer_hi_flag_lo = nullptr;
+    g.halo_error = nullptr;
+    {
+        const u64 nyg = c->ny_global ? c->ny_global : s->ny;
+        s->has_lo = c->iy_offset > 0;
+        s->has_hi = c->iy_offset + s->ny < nyg;
+        s->nbx = (s->nx + s->block_x - 1) / s->block_x;
+        if ((s->has_lo || s->has_hi) &&
+            (s->diff_mode == MKB_DIFF_HOMOGENEOUS || s->diff_mode == MKB_DIFF_FIELD)) {
+            // Exchange block: this GPU's ghost rows and arrival flags
+            const size_t halo = 3 * s->nx * s->rs;
+            const size_t flags = s->nbx * sizeof(unsigned int);
+            s->xchg_bytes = 2 * halo + 2 * flags + 256;
+            INIT_CUDA(cudaMalloc(&s->d_xchg, s->xchg_bytes));
+            INIT_CUDA(cudaMemsetAsync(s->d_xchg, 0, s->xchg_bytes, s->stream));
+            g.halo_error = (unsigned int*)(s->d_xchg + 2 * halo + 2 * flags);
+        }
+    }
     g.nx = s->nx;
     g.ny = s->ny;
     g.stride = s->stride;
@@ -908,7 +978,7 @@ static int sim_step_typed(mkb_sim* s) {
             rec.p.dt = dt;
             rec.p.pace = s->engine_pace;
             rec.p.flags = (rec.logging && s->store_aux) ? MKB_FLAG_STORE_AUX : 0u;
-            rec.p.reserved = 0;
+            rec.p.step = (unsigned int)(++s->step_index);
             rec.log_time = (double)(TR)s->engine_time;
             rec.log_pace = (double)(TR)s->engine_pace;
             if (rec.logging) {
@@ -956,6 +1026,12 @@ static int sim_step_typed(mkb_sim* s) {
 
         for (size_t i = 0; i < s->recs.size(); i++) {
             const StepRec& rec = s->recs[i];
+            if (s->issued++ % kThrottle == 0) {
+                const int slot = (int)(s->throttle_count & 1);
+                if (s->throttle_count >= 2) CUDA_TRY(cudaEventSynchronize(s->ev_throttle[slot]));
+                CUDA_TRY(cudaEventRecord(s->ev_throttle[slot], s->stream));
+                s->throttle_count++;
+            }
             const u64 vm_plane = (u64)std::max(s->i_vm, 0);
             TR* v_in = plane_ptr<TR>(s, s->parity ? s->plane_alt_v : vm_plane);
             TR* v_out = plane_ptr<TR>(s, s->parity ? vm_plane : s->plane_alt_v);
@@ -1017,11 +1093,22 @@ static int sim_step_typed(mkb_sim* s) {
         CUDA_TRY(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
         s->device_ms += ms;
     }
+    if (s->grid.halo_error) {
+        unsigned int err = 0;
+        CUDA_TRY(cudaMemcpy(&err, s->grid.halo_error, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            return fail(MKB_ERR_CUDA, "Timed out waiting for a neighbouring GPU's boundary row "
+                                      "(a rank stopped stepping or was never connected).");
+        }
+    }
     return finalize_rows<TR>(s);
 }
 
 extern "C" int mkb_sim_step(mkb_sim* s, double* engine_time, int* halted) {
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (s->d_xchg && ((s->has_lo && !s->peer_lo_base) || (s->has_hi && !s->peer_hi_base))) {
+        return fail(MKB_ERR_STATE, "Row slab not connected to its neighbours (mkb_sim_halo_connect).");
+    }
     CUDA_TRY(cudaSetDevice(s->device));
     int rc = MKB_OK;
     if (!s->finished) {
@@ -1078,6 +1165,112 @@ extern "C" int mkb_sim_reset_counters(mkb_sim* s) {
     s->steps = 0;
     s->device_ms = 0;
     return MKB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Row-slab halo exchange
+// ---------------------------------------------------------------------------
+extern "C" int mkb_sim_halo_info(mkb_sim* s, int* has_lower, int* has_upper, uint64_t* bytes) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (has_lower) *has_lower = (s->d_xchg && s->has_lo) ? 1 : 0;
+    if (has_upper) *has_upper = (s->d_xchg && s->has_hi) ? 1 : 0;
+    if (bytes) *bytes = s->xchg_bytes;
+    return MKB_OK;
+}
+
+extern "C" int mkb_sim_halo_export(mkb_sim* s, void* ipc_handle_64, void** device_pointer) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (!s->d_xchg) return fail(MKB_ERR_STATE, "This simulation has no neighbouring slabs.");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (ipc_handle_64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_xchg));
+        memcpy(ipc_handle_64, &h, 64);
+    }
+    if (device_pointer) *device_pointer = s->d_xchg;
+    return MKB_OK;
+}
+
+template <typename TR>
+static int halo_connect_typed(mkb_sim* s) {
+    MkbGridArgs& g = s->grid;
+    const size_t halo = 3 * s->nx * s->rs;
+    const size_t flags = s->nbx * sizeof(unsigned int);
+    // Own block
+    g.halo_lo = s->has_lo ? s->d_xchg : nullptr;
+    g.halo_hi = s->has_hi ? s->d_xchg + halo : nullptr;
+    g.flag_lo = (const unsigned int*)(s->d_xchg + 2 * halo);
+    g.flag_hi = (const unsigned int*)(s->d_xchg + 2 * halo + flags);
+    // Neighbours' blocks have the same layout (same nx, same column blocks)
+    if (s->peer_lo_base) {
+        char* b = (char*)s->peer_lo_base;
+        g.peer_lo_halo_hi = b + halo;
+        g.peer_lo_flag_hi = (unsigned int*)(b + 2 * halo + flags);
+    }
+    if (s->peer_hi_base) {
+        char* b = (char*)s->peer_hi_base;
+        g.peer_hi_halo_lo = b;
+        g.peer_hi_flag_lo = (unsigned int*)(b + 2 * halo);
+    }
+    // Deliver V(tmin) of the boundary rows into the neighbours' slot for step 1
+    const TR* v = plane_ptr<TR>(s, s->parity ? s->plane_alt_v : (u64)std::max(s->i_vm, 0));
+    const size_t row = s->nx * s->rs;
+    const int grid = (int)((s->nbx + 255) / 256);
+    if (s->peer_lo_base) {
+        CUDA_TRY(cudaMemcpyAsync((char*)g.peer_lo_halo_hi + 1 * row, v, row, cudaMemcpyDefault, s->stream));
+        k_fill_u32<<<grid, 256, 0, s->stream>>>(g.peer_lo_flag_hi, s->nbx, 1u);
+        s->launches++;
+    }
+    if (s->peer_hi_base) {
+        CUDA_TRY(cudaMemcpyAsync((char*)g.peer_hi_halo_lo + 1 * row, v + (s->ny - 1) * s->nx, row,
+                                 cudaMemcpyDefault, s->stream));
+        k_fill_u32<<<grid, 256, 0, s->stream>>>(g.peer_hi_flag_lo, s->nbx, 1u);
+        s->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return MKB_OK;
+}
+
+extern "C" int mkb_sim_halo_connect(mkb_sim* s, const void* lower, const void* upper, int direct) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (!s->d_xchg) return fail(MKB_ERR_STATE, "This simulation has no neighbouring slabs.");
+    if (s->step_index != 0) return fail(MKB_ERR_STATE, "halo_connect must precede the first step");
+    if ((s->has_lo && !lower) || (s->has_hi && !upper)) {
+        return fail(MKB_ERR_INVALID, "missing neighbour handle");
+    }
+    CUDA_TRY(cudaSetDevice(s->device));
+    const void* in[2] = {s->has_lo ? lower : nullptr, s->has_hi ? upper : nullptr};
+    void** out[2] = {&s->peer_lo_base, &s->peer_hi_base};
+    bool* ipc[2] = {&s->peer_lo_ipc, &s->peer_hi_ipc};
+    for (int k = 0; k < 2; k++) {
+        if (!in[k]) continue;
+        if (direct) {
+            // Same process: `in` is the neighbour's device pointer
+            void* ptr = *(void* const*)in[k];
+            cudaPointerAttributes attr;
+            CUDA_TRY(cudaPointerGetAttributes(&attr, ptr));
+            if (attr.device != s->device) {
+                int can = 0;
+                CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, attr.device));
+                if (!can) return fail(MKB_ERR_CUDA, "GPU %d cannot access GPU %d", s->device, attr.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+                cudaGetLastError();
+            }
+            *out[k] = ptr;
+            *ipc[k] = false;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, in[k], 64);
+            void* ptr = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            *out[k] = ptr;
+            *ipc[k] = true;
+        }
+    }
+    return s->precision == MKB_DOUBLE ? halo_connect_typed<double>(s) : halo_connect_typed<float>(s);
 }
 
 extern "C" void mkb_sim_clean(mkb_sim* s) { sim_destroy(s); }

@@ -185,7 +185,21 @@ class _ExpMixin:
 
 class _Writer(_ConstPoolMixin, _PowMixin, _DivMixin, _ExpMixin,
               CudaExpressionWriter):
-    pass
+    """
+    The writer used for all but ``native_maths`` kernels. ``fold`` (set by
+    :func:`generate`) maps a constant sub-expression to its text, or returns
+    None: the in-line division / exp contain ``asm`` and cannot be folded by
+    the compiler, so constant sub-trees are folded here.
+    """
+    fold = None
+
+    def ex(self, e):
+        if self.fold is not None and not isinstance(
+                e, (myokit.Number, myokit.Name)):
+            text = self.fold(e)
+            if text is not None:
+                return text
+        return super().ex(e)
 
 
 class _NativeWriter(_PowMixin, _NativeCudaExpressionWriter):
@@ -207,6 +221,22 @@ __device__ __forceinline__ Real mkb_powi(Real x) {
         return h * h;
     } else {
         return x * mkb_powi<N - 1>(x);
+    }
+}
+
+// Ghost-row arrival: spin (with back-off) until the neighbouring GPU has
+// delivered the row for `step`; gives up after ~10 s and raises halo_error so
+// a stalled neighbour surfaces as an error instead of a hung GPU.
+__device__ __forceinline__ void mkb_wait_flag(
+    const unsigned int* flag, unsigned int step, unsigned int* error) {
+    const volatile unsigned int* f = flag;
+    unsigned int spins = 0;
+    while (*f < step) {
+        __nanosleep(spins < 64 ? 20 : 200);
+        if (++spins > 50000000u) {
+            if (error) atomicExch(error, 1u);
+            break;
+        }
     }
 }
 
@@ -332,7 +362,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              diffusion_mode, paced_list, block, native_maths=False, fmad=True,
              max_registers=None, pow_multiply=True, fast_div=False,
              lazy_state=True, min_blocks=None, fast_exp=False,
-             const_pool=True, load_ahead=8):
+             const_pool=True, load_ahead=8, slab=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -354,6 +384,11 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         register allocation must allow.
     ``const_pool``
         Double-precision literals in a ``__constant__`` table.
+    ``slab``
+        Row-slab variant for multi-GPU grids: boundary row blocks run first,
+        wait for the neighbouring GPU's ghost row (arrival flags), and push
+        their new V row into the neighbour's ghost buffer with peer stores
+        followed by a system-scope fence and a flag write.
     """
     sp = (precision == myokit.SINGLE_PRECISION)
     if native_maths and sp:
@@ -370,6 +405,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     inter_log = list(inter_log)
     bx, by = block
     diffusion = diffusion_mode != DIFF_NONE
+    slab = bool(slab) and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD)
 
     equations = model.solvable_order()
     del equations['*remaining*']
@@ -421,6 +457,23 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         return 'V_' + var.uname()
     w.set_lhs_function(v)
 
+    def fold(e):
+        # Constant sub-expression (only folded constants and literals)?
+        if isinstance(e, myokit.Condition):
+            return None
+        for ref in e.references():
+            if not isinstance(ref, myokit.Name) or ref.var() not in folded:
+                return None
+        try:
+            x = float(e.eval())
+        except Exception:
+            return None
+        if x != x or x in (float('inf'), float('-inf')):
+            return None
+        return number(x)
+    if pooled:
+        w.fold = fold
+
     n_state = model.count_states()
     vm = model.label('membrane_potential') if diffusion else None
     i_vm = vm.index() if vm is not None else -1
@@ -447,9 +500,23 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         if var in rl_states:
             inf, tau = rl_states[var]
             inf, tau, x = v(inf), v(tau), v(var)
-            rhs = '%s - (%s - %s) * %s(-dt / %s)' % (inf, inf, x, exp, tau)
+            arg = '-dt / %s' % tau
+            if fast_div and not sp and not native_maths:
+                arg = 'mkb_div(-dt, %s)' % tau
+            rhs = '%s - (%s - %s) * %s(%s)' % (inf, inf, x, exp, arg)
         else:
             rhs = '%s + dt * %s' % (v(var), v(var.lhs()))
+        if k == i_vm and slab:
+            return (
+                '    {\n'
+                '        const Real vnew = %s;\n'
+                '        v_out[cid] = vnew;\n'
+                '        // boundary rows go straight into the neighbouring GPU\'s ghost row\n'
+                '        if (iy == 0 && g.peer_lo_halo_hi)\n'
+                '            ((Real*)g.peer_lo_halo_hi)[((step + 1u) %% 3u) * nx + ix] = vnew;\n'
+                '        if (iy == ny - 1 && g.peer_hi_halo_lo)\n'
+                '            ((Real*)g.peer_hi_halo_lo)[((step + 1u) %% 3u) * nx + ix] = vnew;\n'
+                '    }' % rhs)
         if k == i_vm:
             return '    v_out[cid] = %s;' % rhs
         return '    state[%dull * stride + cid] = %s;' % (k, rhs)
@@ -610,7 +677,27 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    const unsigned long long nbx = (nx + MKB_BX - 1) / MKB_BX;')
     p('    const unsigned long long bid = blockIdx.x;')
     p('    const unsigned long long ix = (bid % nbx) * MKB_BX + tx;')
-    p('    const unsigned long long iy = (bid / nbx) * MKB_BY + ty;')
+    if slab:
+        p('    // Boundary row blocks first: their rows reach the neighbouring GPUs')
+        p('    // while the interior is still being computed.')
+        p('    const unsigned long long nby = (ny + MKB_BY - 1) / MKB_BY;')
+        p('    const unsigned long long byr = bid / nbx;')
+        p('    const unsigned long long byb = (byr == 0) ? 0 : ((byr == 1) ? nby - 1 : byr - 1);')
+        p('    const unsigned long long iy = byb * MKB_BY + ty;')
+        p('    const unsigned int step = sp->step;')
+        p('    const unsigned long long bxb = bid % nbx;')
+        p('    const bool wait_lo = (byb == 0) && g.halo_lo;')
+        p('    const bool wait_hi = (byb == nby - 1) && g.halo_hi;')
+        p('    if (wait_lo || wait_hi) {')
+        p('        if (tx == 0 && ty == 0) {')
+        p('            if (wait_lo) mkb_wait_flag(g.flag_lo + bxb, step, g.halo_error);')
+        p('            if (wait_hi) mkb_wait_flag(g.flag_hi + bxb, step, g.halo_error);')
+        p('            __threadfence();')
+        p('        }')
+        p('        __syncthreads();')
+        p('    }')
+    else:
+        p('    const unsigned long long iy = (bid / nbx) * MKB_BY + ty;')
     p('    const bool active = (ix < nx) && (iy < ny);')
     p('    const unsigned long long cid = ix + iy * nx;')
     p('    Real* const state = (Real*)g.state;')
@@ -659,18 +746,27 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('        if (ty == 0) {')
         p('            Real vn = vc;')
         p('            if (iy > 0) vn = v_in[cid - nx];')
-        p('            else if (iyg > 0 && g.halo_lo) vn = ((const Real*)g.halo_lo)[ix];')
+        if slab:
+            p('            else if (iyg > 0 && g.halo_lo) vn = __ldcg((const Real*)g.halo_lo + (step % 3u) * nx + ix);')
+        else:
+            p('            else if (iyg > 0 && g.halo_lo) vn = ((const Real*)g.halo_lo)[ix];')
         p('            tile[0][tx + 1] = vn;')
         p('        }')
         p('        if (ty == MKB_BY - 1 || iy == ny - 1) {')
         p('            Real vn = vc;')
         p('            if (iy < ny - 1) vn = v_in[cid + nx];')
-        p('            else if (iyg < nyg - 1 && g.halo_hi) vn = ((const Real*)g.halo_hi)[ix];')
+        if slab:
+            p('            else if (iyg < nyg - 1 && g.halo_hi) vn = __ldcg((const Real*)g.halo_hi + (step % 3u) * nx + ix);')
+        else:
+            p('            else if (iyg < nyg - 1 && g.halo_hi) vn = ((const Real*)g.halo_hi)[ix];')
         p('            tile[ty + 2][tx + 1] = vn;')
         p('        }')
         p('    }')
         p('    __syncthreads();')
-        p('    if (!active) return;')
+        if slab:
+            p('    if (active) {')
+        else:
+            p('    if (!active) return;')
         p('    const Real vxm = tile[ty + 1][tx], vxp = tile[ty + 1][tx + 2];')
         p('    const Real vym = tile[ty][tx + 1], vyp = tile[ty + 2][tx + 1];')
         p('    Real idiff;')
@@ -733,6 +829,20 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('')
     for line in body:
         p(line)
+    if slab:
+        p('    }   // active')
+        p('    // Publish the boundary rows: data first, then (after a system-scope')
+        p('    // fence by every writer and a CTA barrier) the arrival flag.')
+        p('    const bool send_lo = (byb == 0) && g.peer_lo_halo_hi;')
+        p('    const bool send_hi = (byb == nby - 1) && g.peer_hi_halo_lo;')
+        p('    if (send_lo || send_hi) {')
+        p('        __threadfence_system();')
+        p('        __syncthreads();')
+        p('        if (tx == 0 && ty == 0) {')
+        p('            if (send_lo) *((volatile unsigned int*)g.peer_lo_flag_hi + bxb) = step + 1u;')
+        p('            if (send_hi) *((volatile unsigned int*)g.peer_hi_flag_lo + bxb) = step + 1u;')
+        p('        }')
+        p('    }')
     p('}')
     p('')
     code = '\n'.join(out)

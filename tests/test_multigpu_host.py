@@ -1,0 +1,127 @@
+"""
+Host-side logic of the multi-GPU (row-slab) path on CPU: world_size 2 over
+gloo, one process per rank, exactly as torchrun would start them. Checks the
+communicator, the slab partition, slicing of global inputs, the local log
+table, and that running without a GPU still fails loudly on every rank.
+"""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+import myokit_b200
+from myokit_b200 import multigpu
+import myokit
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import os, sys, json
+    sys.path.insert(0, %r)
+    import numpy as np
+    import torch.distributed as dist
+    dist.init_process_group('gloo')
+    import myokit_b200, myokit
+    from myokit_b200 import multigpu, capi
+    comm = multigpu.TorchComm()
+    assert comm.size == 2
+    got = comm.allgather(('rank', comm.rank, b'x' * 64))
+    assert [g[1] for g in got] == [0, 1]
+    comm.barrier()
+
+    m, p, _ = myokit.load('example')
+    nx, ny = 6, 5
+    s = myokit_b200.SimulationCUDA(m, p, ncells=(nx, ny), precision=myokit.DOUBLE_PRECISION, comm=comm)
+    x0, snx, y0, sny = s.local_shape()
+    rows = multigpu.slab_rows(ny, 2)
+    assert (y0, y0 + sny) == rows[comm.rank] and (x0, snx) == (0, nx)
+    n = m.count_states()
+    assert len(s.state_array()) == sny * nx * n
+
+    # global state in, local slab kept
+    full = np.arange(nx * ny * n, dtype=float)
+    s.set_state(full)
+    want = full.reshape(ny, nx, n)[y0:y0 + sny].reshape(-1)
+    assert np.array_equal(s.state_array(), want)
+    # single-cell access is global-indexed; remote cells raise
+    own = (2, y0)
+    other = (2, rows[1 - comm.rank][0])
+    assert s.state(*own) == list(full.reshape(ny, nx, n)[own[1], own[0]])
+    try:
+        s.state(*other)
+        raise SystemExit('expected IndexError')
+    except IndexError:
+        pass
+    # fields are given globally and sliced per rank
+    g = np.arange(nx * ny, dtype=float).reshape(ny, nx)
+    s.set_field('ina.gNa', g)
+    assert np.array_equal(s._local_slice(s._fields[s._model.get('ina.gNa')]), g[y0:y0 + sny].reshape(-1))
+    # the log table only holds this rank's cells, numbered locally
+    log = myokit.prepare_log(['engine.time', 'membrane.V'], s._model, dims=(nx, ny), global_vars=['engine.time', 'engine.pace'])
+    keys, kinds, index = s._log_table(log, [])
+    assert keys[0] == 'engine.time' and len(keys) == 1 + sny * nx
+    assert '0.%%d.membrane.V' %% y0 in keys and ('0.%%d.membrane.V' %% other[1]) not in keys
+    k = keys.index('3.%%d.membrane.V' %% (y0 + 1))
+    assert kinds[k] == capi.LOG_STATE and index[k] == (3 + 1 * nx) * n + 0
+    # slab kernels are generated for coupled grids only
+    assert 'mkb_wait_flag(g.flag_lo' in s.kernel_source().code
+    u = myokit_b200.SimulationCUDA(m, p, ncells=10, diffusion=False, comm=comm)
+    assert u.local_shape() == ((0, 5, 0, 1), (5, 5, 0, 1))[comm.rank]
+    assert 'g.flag_lo' not in u.kernel_source().code
+    try:
+        myokit_b200.SimulationCUDA(m, p, ncells=10, comm=comm)
+        raise SystemExit('expected ValueError')
+    except ValueError:
+        pass
+
+    # gather_rows reassembles slabs
+    loc = g[y0:y0 + sny][None]
+    assert np.array_equal(multigpu.gather_rows(comm, loc), g[None])
+
+    # no GPU here: the run must fail on every rank, not fall back
+    if capi.device_count() == 0:
+        try:
+            s.run(1)
+            raise SystemExit('expected BackendError')
+        except capi.BackendError as e:
+            assert 'no CPU fallback' in str(e)
+    dist.barrier()
+    print('RANK_OK', comm.rank)
+''') % ROOT
+
+
+def test_two_ranks_over_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    env = dict(os.environ)
+    env.pop('CUDA_VISIBLE_DEVICES', None)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+           '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', '29531', str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert 'RANK_OK 0' in r.stdout and 'RANK_OK 1' in r.stdout
+
+
+def test_thread_comm_and_slab_rows():
+    assert multigpu.slab_rows(10, 4) == [(0, 2), (2, 5), (5, 7), (7, 10)]
+
+    def work(comm):
+        vals = comm.allgather(comm.rank * 10)
+        comm.barrier()
+        return vals
+    out = multigpu.run_threads(3, work)
+    assert out == [[0, 10, 20]] * 3
+
+    def boom(comm):
+        if comm.rank == 1:
+            raise KeyError('x')
+        comm.barrier()
+    try:
+        multigpu.run_threads(2, boom)
+        assert False
+    except KeyError:
+        pass
