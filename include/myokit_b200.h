@@ -65,6 +65,12 @@ extern "C" {
 #define MKB_LOG_IDIFF 2          /* index = cid */
 #define MKB_LOG_STATE 3          /* index = cid * n_state + k */
 #define MKB_LOG_INTER 4          /* index = cid * n_inter + k */
+/* Whole-field entries (no reference equivalent; the reference needs one dict
+ * key per cell): one entry expands to n_cells consecutive columns, cell-id
+ * order, copied plane-to-row on the device without an index table. */
+#define MKB_LOG_STATE_FIELD 5    /* index = k: state k of every cell */
+#define MKB_LOG_INTER_FIELD 6    /* index = k: logged intermediary k of every cell */
+#define MKB_LOG_IDIFF_FIELD 7    /* diffusion current of every cell */
 
 typedef struct mkb_sim mkb_sim;
 
@@ -140,6 +146,20 @@ typedef struct mkb_sim_config {
     int use_graphs;             /* 1: replay batches of steps as CUDA graphs */
 } mkb_sim_config;
 
+/* A run on the state that is already resident on the device (mkb_sim_rearm):
+ * the time span, step size, protocol and log selection of mkb_sim_config. */
+typedef struct mkb_run_config {
+    double tmin, tmax;
+    double dt;
+    double log_interval;
+    int n_events;
+    const double* events;
+    uint64_t n_log;
+    const int32_t* log_kind;
+    const uint64_t* log_index;
+    uint64_t steps_per_call;
+} mkb_run_config;
+
 /* ---- library ---- */
 int mkb_abi_version(void);
 const char* mkb_last_error(void);
@@ -161,14 +181,20 @@ int mkb_jit_compile(const char* source, const char* options,
 
 /* ---- simulation (replaces sim_init / sim_step / sim_clean) ---- */
 int mkb_sim_init(const mkb_sim_config* cfg, mkb_sim** out);
+/* Starts another run from the state the device holds (the reference keeps
+ * its state in a Python list between runs, openclsim.py:1104,1149; here it
+ * stays in HBM). Row slabs: call on every rank, barrier, mkb_sim_halo_seed,
+ * barrier, then step. */
+int mkb_sim_rearm(mkb_sim* sim, const mkb_run_config* run);
 /* Runs up to steps_per_call time steps. Returns 1 while t < tmax, 0 when the
  * run has finished (final state available), < 0 on error. *engine_time gets
  * the current time. *halted (may be null) is set when a NaN was found in the
  * first state of cell 0 at a logged step (openclsim.c:1087). */
 int mkb_sim_step(mkb_sim* sim, double* engine_time, int* halted);
 /* Logged rows so far: pinned host matrix of Real; element (r, c) of the log is
- * data[r * row_stride + c] for c < cols (= n_log). Valid until mkb_sim_clean
- * or the next mkb_sim_step. */
+ * data[r * row_stride + c] for c < cols. Columns follow the order of the log
+ * entries; a *_FIELD entry takes n_cells columns. Valid until mkb_sim_clean,
+ * mkb_sim_rearm or the next mkb_sim_step. */
 int mkb_sim_log_view(mkb_sim* sim, const void** data, uint64_t* rows, uint64_t* cols,
                      uint64_t* row_stride);
 /* Copies the state, reference layout [cid * n_state + k], host_precision. */
@@ -200,6 +226,9 @@ int mkb_sim_halo_export(mkb_sim* sim, void* ipc_handle_64, void** device_pointer
  * slab); direct = 0: pointers to 64-byte IPC handles, direct = 1: pointers to
  * device pointers of sims living in this process. Null where no neighbour. */
 int mkb_sim_halo_connect(mkb_sim* sim, const void* lower, const void* upper, int direct);
+/* After mkb_sim_rearm (and a barrier): delivers the boundary rows of the
+ * current state to the neighbours again. mkb_sim_halo_connect includes it. */
+int mkb_sim_halo_seed(mkb_sim* sim);
 
 /* ---- pacing alone (unit tests; mirrors tests/ansic_event_based_pacing.c) ---- */
 int mkb_pacing_probe(double t0, int n_events, const double* events,

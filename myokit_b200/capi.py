@@ -23,6 +23,7 @@ MKB_ERR_SIMULTANEOUS = -5
 MKB_ERR_STATE = -6
 
 LOG_TIME, LOG_PACE, LOG_IDIFF, LOG_STATE, LOG_INTER = range(5)
+LOG_STATE_FIELD, LOG_INTER_FIELD, LOG_IDIFF_FIELD = 5, 6, 7
 
 # Every symbol include/myokit_b200.h declares
 SYMBOLS = [
@@ -31,7 +32,8 @@ SYMBOLS = [
     'mkb_sim_init', 'mkb_sim_step', 'mkb_sim_log_view', 'mkb_sim_get_state',
     'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
     'mkb_sim_reset_counters', 'mkb_sim_clean', 'mkb_sim_halo_info',
-    'mkb_sim_halo_export', 'mkb_sim_halo_connect',
+    'mkb_sim_halo_export', 'mkb_sim_halo_connect', 'mkb_sim_halo_seed',
+    'mkb_sim_rearm',
     'mkb_pacing_probe',
 ]
 
@@ -72,6 +74,16 @@ class SimConfig(ctypes.Structure):
         ('n_log', c_u64), ('log_kind', c_vp), ('log_index', c_vp),
         ('iy_offset', c_u64), ('ny_global', c_u64),
         ('steps_per_call', c_u64), ('use_graphs', ctypes.c_int),
+    ]
+
+
+class RunConfig(ctypes.Structure):
+    _fields_ = [
+        ('tmin', ctypes.c_double), ('tmax', ctypes.c_double),
+        ('dt', ctypes.c_double), ('log_interval', ctypes.c_double),
+        ('n_events', ctypes.c_int), ('events', c_vp),
+        ('n_log', c_u64), ('log_kind', c_vp), ('log_index', c_vp),
+        ('steps_per_call', c_u64),
     ]
 
 
@@ -123,6 +135,8 @@ def library():
         ctypes.POINTER(c_u64)]
     lib.mkb_sim_halo_export.argtypes = [c_vp, c_vp, ctypes.POINTER(c_vp)]
     lib.mkb_sim_halo_connect.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int]
+    lib.mkb_sim_halo_seed.argtypes = [c_vp]
+    lib.mkb_sim_rearm.argtypes = [c_vp, ctypes.POINTER(RunConfig)]
     lib.mkb_pacing_probe.argtypes = [
         ctypes.c_double, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]
     if lib.mkb_abi_version() != MKB_ABI_VERSION:

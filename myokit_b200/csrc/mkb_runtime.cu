@@ -297,7 +297,13 @@ struct mkb_sim {
     bool finished = false, halted = false;
 
     // logging
-    u64 n_log = 0, row_stride = 0;      // row_stride = n_log + 1 (hidden NaN probe)
+    u64 n_log = 0, row_stride = 0;      // columns; row_stride = n_log + 1 (hidden NaN probe)
+    struct FieldCopy {
+        u64 plane;                      // plane index, or ~0ull for the current V plane
+        u64 col;                        // first column in the row
+    };
+    std::vector<FieldCopy> pre_fields, post_fields;
+    u64 h_log_bytes = 0;                // capacity of h_log in bytes
     std::vector<int> time_cols, pace_cols;
     GatherEntry* d_tab_pre = nullptr;   // states at t (before the step kernel)
     GatherEntry* d_tab_post = nullptr;  // idiff / intermediaries at t (after it)
@@ -564,6 +570,179 @@ static int preload_kernels(mkb_sim* s) {
     return MKB_OK;
 }
 
+// Prepares a run on the state that is resident on the device: log tables and
+// rings, pacing (openclsim.c:488-496), schedule (:501, :1018-1022). Used by
+// mkb_sim_init and mkb_sim_rearm.
+static int arm_run(mkb_sim* s, const mkb_run_config* r) {
+    if (!(r->dt > 0)) return fail(MKB_ERR_INVALID, "Step size must be greater than zero.");
+    if (r->tmax < r->tmin) return fail(MKB_ERR_INVALID, "Simulation time can't be negative.");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->side));
+
+    // Drop the previous run's log
+    cudaFree(s->d_tab_pre);
+    cudaFree(s->d_tab_post);
+    cudaFree(s->d_log);
+    s->d_tab_pre = s->d_tab_post = nullptr;
+    s->d_log = nullptr;
+    // (the pinned host matrix is kept and reused when it is large enough)
+    s->h_log_cap = 0;
+    s->pre_fields.clear();
+    s->post_fields.clear();
+    s->time_cols.clear();
+    s->pace_cols.clear();
+    s->row_time.clear();
+    s->row_pace.clear();
+    s->rows_written = s->rows_flushed = s->rows_final = 0;
+    s->copied_pending[0] = s->copied_pending[1] = false;
+    s->logging_states = false;
+    s->store_aux = false;
+    s->log_cap = s->log_half = 0;
+
+    s->tmin = r->tmin;
+    s->tmax = r->tmax;
+    s->default_dt = r->dt;
+    s->log_interval = r->log_interval;
+    if (r->steps_per_call) {
+        s->steps_per_call = r->steps_per_call;
+    } else {
+        s->steps_per_call = std::max<u64>(1000, 500 + 200000 / s->n);   // openclsim.c:1046-1047
+    }
+
+    // Logging tables
+    std::vector<GatherEntry> pre, post;
+    u64 col = 0;
+    for (u64 j = 0; j < r->n_log; j++) {
+        GatherEntry e;
+        e.col = (unsigned int)col;
+        e.pad = 0;
+        e.off = 0;
+        const u64 idx = r->log_index[j];
+        bool bad = false;
+        u64 width = 1;
+        if (col > 0xfffffff0ull) return fail(MKB_ERR_INVALID, "too many log columns");
+        switch (r->log_kind[j]) {
+        case MKB_LOG_TIME:
+            s->time_cols.push_back((int)col);
+            break;
+        case MKB_LOG_PACE:
+            s->pace_cols.push_back((int)col);
+            break;
+        case MKB_LOG_STATE_FIELD: {
+            if (idx >= (u64)s->n_state) { bad = true; break; }
+            mkb_sim::FieldCopy f;
+            f.plane = ((int)idx == s->i_vm) ? ~0ull : idx;
+            f.col = col;
+            s->pre_fields.push_back(f);
+            s->logging_states = true;
+            width = s->n;
+            break;
+        }
+        case MKB_LOG_INTER_FIELD: {
+            if (idx >= (u64)s->n_inter) { bad = true; break; }
+            mkb_sim::FieldCopy f;
+            f.plane = s->plane_inter + idx;
+            f.col = col;
+            s->post_fields.push_back(f);
+            width = s->n;
+            break;
+        }
+        case MKB_LOG_IDIFF_FIELD: {
+            if (s->diff_mode == MKB_DIFF_NONE) { bad = true; break; }
+            mkb_sim::FieldCopy f;
+            f.plane = s->plane_idiff;
+            f.col = col;
+            s->post_fields.push_back(f);
+            width = s->n;
+            break;
+        }
+        case MKB_LOG_IDIFF:
+            if (idx >= s->n || s->diff_mode == MKB_DIFF_NONE) { bad = true; break; }
+            e.off = s->plane_idiff * s->stride + idx;
+            post.push_back(e);
+            break;
+        case MKB_LOG_STATE: {
+            const u64 cid = idx / (u64)s->n_state;
+            const u64 k = idx % (u64)s->n_state;
+            if (cid >= s->n) { bad = true; break; }
+            e.off = ((int)k == s->i_vm) ? (MKB_GATHER_V | cid) : (k * s->stride + cid);
+            pre.push_back(e);
+            s->logging_states = true;
+            break;
+        }
+        case MKB_LOG_INTER: {
+            if (s->n_inter == 0) { bad = true; break; }
+            const u64 cid = idx / (u64)s->n_inter;
+            const u64 k = idx % (u64)s->n_inter;
+            if (cid >= s->n) { bad = true; break; }
+            e.off = (s->plane_inter + k) * s->stride + cid;
+            post.push_back(e);
+            break;
+        }
+        default:
+            bad = true;
+            break;
+        }
+        if (bad) return fail(MKB_ERR_INVALID, "Unknown variables found in logging dictionary.");
+        col += width;
+    }
+    s->n_log = col;
+    s->row_stride = col + 1;
+    s->store_aux = !post.empty() || !s->post_fields.empty();
+    if (s->logging_states) {
+        // Hidden NaN probe: first state of cell 0 (openclsim.c:1087)
+        GatherEntry e;
+        e.col = (unsigned int)s->n_log;
+        e.pad = 0;
+        e.off = (s->i_vm == 0) ? (MKB_GATHER_V | 0ull) : 0ull;
+        pre.push_back(e);
+    }
+    s->n_pre = pre.size();
+    s->n_post = post.size();
+    if (s->n_pre) {
+        CUDA_TRY(cudaMalloc(&s->d_tab_pre, s->n_pre * sizeof(GatherEntry)));
+        CUDA_TRY(cudaMemcpyAsync(s->d_tab_pre, pre.data(), s->n_pre * sizeof(GatherEntry),
+                                 cudaMemcpyHostToDevice, s->stream));
+    }
+    if (s->n_post) {
+        CUDA_TRY(cudaMalloc(&s->d_tab_post, s->n_post * sizeof(GatherEntry)));
+        CUDA_TRY(cudaMemcpyAsync(s->d_tab_post, post.data(), s->n_post * sizeof(GatherEntry),
+                                 cudaMemcpyHostToDevice, s->stream));
+    }
+    if (s->n_pre + s->n_post + s->pre_fields.size() + s->post_fields.size() > 0) {
+        // Device row ring: two halves, ~64 MiB each at most
+        const u64 row_bytes = s->row_stride * s->rs;
+        const u64 half = std::max<u64>(1, std::min<u64>(4096, (64ull << 20) / row_bytes));
+        s->log_half = half;
+        s->log_cap = 2 * half;
+        CUDA_TRY(cudaMalloc(&s->d_log, s->log_cap * row_bytes));
+        CUDA_TRY(cudaMemsetAsync(s->d_log, 0, s->log_cap * row_bytes, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));     // tables copied from stack vectors
+
+    // Pacing: openclsim.c:488-496
+    int rc = s->pacing.init(r->tmin, r->n_events, r->events);
+    if (rc == 0) rc = s->pacing.advance(r->tmin);
+    if (rc == mkb::PACING_SIMULTANEOUS_EVENT) {
+        return fail(MKB_ERR_SIMULTANEOUS,
+                    "E-Pacing error: Event scheduled or re-occuring at the same time as another event.");
+    }
+    if (rc) return fail(MKB_ERR_PACING, "E-Pacing error %d", rc);
+    s->tnext_pace = s->pacing.next_time();
+    s->engine_pace = s->pacing.level();
+    s->engine_time = r->tmin;               // openclsim.c:501
+    s->istep = 1;                           // openclsim.c:1018
+    s->inext_log = 0;
+    s->tnext_log = r->tmin;                 // openclsim.c:1021-1022
+    s->finished = !(r->tmax > r->tmin);
+    s->halted = false;
+    s->step_index = 0;
+    s->issued = 0;
+    s->throttle_count = 0;
+    s->ring_chunk = 0;
+    return MKB_OK;
+}
+
 extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     if (!c || !out) return fail(MKB_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -758,113 +937,22 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
         s->launch_block = dim3((unsigned int)s->block_x, (unsigned int)s->block_y, 1);
     }
 
-    // Logging tables
-    s->n_log = c->n_log;
-    s->row_stride = c->n_log + 1;
+    // Logging, pacing and schedule of the first run
     {
-        std::vector<GatherEntry> pre, post;
-        bool bad_log = false;
-        for (u64 j = 0; j < c->n_log && !bad_log; j++) {
-            GatherEntry e;
-            e.col = (unsigned int)j;
-            e.pad = 0;
-            u64 idx = c->log_index[j];
-            switch (c->log_kind[j]) {
-            case MKB_LOG_TIME:
-                s->time_cols.push_back((int)j);
-                break;
-            case MKB_LOG_PACE:
-                s->pace_cols.push_back((int)j);
-                break;
-            case MKB_LOG_IDIFF:
-                if (idx >= s->n || c->diffusion_mode == MKB_DIFF_NONE) { bad_log = true; break; }
-                e.off = s->plane_idiff * s->stride + idx;
-                post.push_back(e);
-                break;
-            case MKB_LOG_STATE: {
-                u64 cid = idx / (u64)s->n_state;
-                u64 k = idx % (u64)s->n_state;
-                if (cid >= s->n) { bad_log = true; break; }
-                if ((int)k == s->i_vm) {
-                    e.off = MKB_GATHER_V | cid;
-                } else {
-                    e.off = k * s->stride + cid;
-                }
-                pre.push_back(e);
-                s->logging_states = true;
-                break;
-            }
-            case MKB_LOG_INTER: {
-                if (s->n_inter == 0) { bad_log = true; break; }
-                u64 cid = idx / (u64)s->n_inter;
-                u64 k = idx % (u64)s->n_inter;
-                if (cid >= s->n) { bad_log = true; break; }
-                e.off = (s->plane_inter + k) * s->stride + cid;
-                post.push_back(e);
-                break;
-            }
-            default:
-                bad_log = true;
-                break;
-            }
-        }
-        if (bad_log) {
-            sim_destroy(s);
-            return fail(MKB_ERR_INVALID, "Unknown variables found in logging dictionary.");
-        }
-        s->store_aux = !post.empty();
-        if (s->logging_states) {
-            // Hidden NaN probe: first state of cell 0 (openclsim.c:1087)
-            GatherEntry e;
-            e.col = (unsigned int)c->n_log;
-            e.pad = 0;
-            e.off = (s->i_vm == 0) ? (MKB_GATHER_V | 0ull) : 0ull;
-            pre.push_back(e);
-        }
-        s->n_pre = pre.size();
-        s->n_post = post.size();
-        if (s->n_pre) {
-            INIT_CUDA(cudaMalloc(&s->d_tab_pre, s->n_pre * sizeof(GatherEntry)));
-            INIT_CUDA(cudaMemcpy(s->d_tab_pre, pre.data(), s->n_pre * sizeof(GatherEntry),
-                                 cudaMemcpyHostToDevice));
-        }
-        if (s->n_post) {
-            INIT_CUDA(cudaMalloc(&s->d_tab_post, s->n_post * sizeof(GatherEntry)));
-            INIT_CUDA(cudaMemcpy(s->d_tab_post, post.data(), s->n_post * sizeof(GatherEntry),
-                                 cudaMemcpyHostToDevice));
-        }
+        mkb_run_config r;
+        memset(&r, 0, sizeof(r));
+        r.tmin = c->tmin;
+        r.tmax = c->tmax;
+        r.dt = c->dt;
+        r.log_interval = c->log_interval;
+        r.n_events = c->n_events;
+        r.events = c->events;
+        r.n_log = c->n_log;
+        r.log_kind = c->log_kind;
+        r.log_index = c->log_index;
+        r.steps_per_call = c->steps_per_call;
+        INIT_TRY(arm_run(s, &r));
     }
-    if (s->n_pre + s->n_post > 0) {
-        // Device row ring: two halves, ~64 MiB each at most
-        u64 row_bytes = s->row_stride * s->rs;
-        u64 half = std::max<u64>(1, std::min<u64>(4096, (64ull << 20) / row_bytes));
-        s->log_half = half;
-        s->log_cap = 2 * half;
-        INIT_CUDA(cudaMalloc(&s->d_log, s->log_cap * row_bytes));
-        INIT_CUDA(cudaMemsetAsync(s->d_log, 0, s->log_cap * row_bytes, s->stream));
-    }
-
-    // Pacing: openclsim.c:488-496
-    {
-        int rc = s->pacing.init(c->tmin, c->n_events, c->events);
-        if (rc == 0) rc = s->pacing.advance(c->tmin);
-        if (rc) {
-            sim_destroy(s);
-            if (rc == mkb::PACING_SIMULTANEOUS_EVENT) {
-                return fail(MKB_ERR_SIMULTANEOUS,
-                            "E-Pacing error: Event scheduled or re-occuring at the same time as another "
-                            "event.");
-            }
-            return fail(MKB_ERR_PACING, "E-Pacing error %d", rc);
-        }
-    }
-    s->tnext_pace = s->pacing.next_time();
-    s->engine_pace = s->pacing.level();
-    s->engine_time = c->tmin;               // openclsim.c:501
-    s->istep = 1;                           // openclsim.c:1018
-    s->inext_log = 0;
-    s->tnext_log = c->tmin;                 // openclsim.c:1021-1022
-    s->finished = !(c->tmax > c->tmin);
 
     INIT_CUDA(cudaStreamSynchronize(s->stream));
 #undef INIT_TRY
@@ -875,29 +963,35 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
 
 static int ensure_host_rows(mkb_sim* s, u64 rows) {
     if (rows <= s->h_log_cap) return MKB_OK;
+    const u64 row_bytes = s->row_stride * s->rs;
     // Estimate the whole run on first use, then grow geometrically
     u64 want = rows;
     if (s->h_log_cap == 0) {
         double est = (s->tmax - s->tmin) / s->log_interval;
         double est2 = 2.0 * (s->tmax - s->tmin) / s->default_dt;
-        double m = std::min(est, est2) + 16;
+        double m = std::min(est, est2) + 2;
         if (m > 0 && m < 4.0e9) want = std::max<u64>(rows, (u64)m);
         // Do not pin more than 2 GiB speculatively
-        u64 row_bytes = s->row_stride * s->rs;
         u64 lim = std::max<u64>(rows, (2ull << 30) / row_bytes);
         want = std::min(want, std::max<u64>(lim, rows));
+        if (s->h_log && want * row_bytes <= s->h_log_bytes) {
+            // the previous run's pinned matrix is large enough: reuse it
+            s->h_log_cap = s->h_log_bytes / row_bytes;
+            return MKB_OK;
+        }
     } else {
         want = std::max(rows, s->h_log_cap * 2);
     }
     CUDA_TRY(cudaStreamSynchronize(s->side));
     char* p = nullptr;
-    CUDA_TRY(cudaHostAlloc(&p, want * s->row_stride * s->rs, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&p, want * row_bytes, cudaHostAllocDefault));
     if (s->h_log) {
-        memcpy(p, s->h_log, s->rows_flushed * s->row_stride * s->rs);
+        if (s->h_log_cap) memcpy(p, s->h_log, s->rows_flushed * row_bytes);
         cudaFreeHost(s->h_log);
     }
     s->h_log = p;
     s->h_log_cap = want;
+    s->h_log_bytes = want * row_bytes;
     return MKB_OK;
 }
 
@@ -1054,6 +1148,11 @@ static int sim_step_typed(mkb_sim* s) {
                         plane_ptr<TR>(s, 0), v_in, s->d_tab_pre, s->n_pre, row);
                     s->launches++;
                 }
+                for (const mkb_sim::FieldCopy& f : s->pre_fields) {
+                    const TR* src = (f.plane == ~0ull) ? v_in : plane_ptr<TR>(s, f.plane);
+                    CUDA_TRY(cudaMemcpyAsync(row + f.col, src, s->n * sizeof(TR),
+                                             cudaMemcpyDeviceToDevice, s->stream));
+                }
             }
             // fused diffusion + cell step: states -> t + dt (openclsim.c:1066-1096)
             const MkbStepParams* sp = dring + i;
@@ -1069,6 +1168,13 @@ static int sim_step_typed(mkb_sim* s) {
                     k_log_gather<TR><<<grid_for(s->n_post), 256, 0, s->stream>>>(
                         plane_ptr<TR>(s, 0), v_in, s->d_tab_post, s->n_post, row);
                     s->launches++;
+                }
+                if (dev_row) {
+                    for (const mkb_sim::FieldCopy& f : s->post_fields) {
+                        CUDA_TRY(cudaMemcpyAsync(row + f.col, plane_ptr<TR>(s, f.plane),
+                                                 s->n * sizeof(TR), cudaMemcpyDeviceToDevice,
+                                                 s->stream));
+                    }
                 }
                 if (s->n_log > 0) {
                     s->row_time.push_back(rec.log_time);
@@ -1193,6 +1299,35 @@ extern "C" int mkb_sim_halo_export(mkb_sim* s, void* ipc_handle_64, void** devic
 }
 
 template <typename TR>
+static int halo_seed_typed(mkb_sim* s);
+
+extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (!r) return fail(MKB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    int rc = arm_run(s, r);
+    if (rc) return rc;
+    if (s->d_xchg) {
+        // Arrival flags restart from zero; the caller barriers, then reseeds
+        const size_t halo = 3 * s->nx * s->rs;
+        CUDA_TRY(cudaMemsetAsync(s->d_xchg + 2 * halo, 0, s->xchg_bytes - 2 * halo, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    return MKB_OK;
+}
+
+extern "C" int mkb_sim_halo_seed(mkb_sim* s) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (!s->d_xchg) return MKB_OK;
+    if (s->step_index != 0) return fail(MKB_ERR_STATE, "halo_seed must precede the first step");
+    if ((s->has_lo && !s->peer_lo_base) || (s->has_hi && !s->peer_hi_base)) {
+        return fail(MKB_ERR_STATE, "Row slab not connected to its neighbours (mkb_sim_halo_connect).");
+    }
+    CUDA_TRY(cudaSetDevice(s->device));
+    return s->precision == MKB_DOUBLE ? halo_seed_typed<double>(s) : halo_seed_typed<float>(s);
+}
+
+template <typename TR>
 static int halo_connect_typed(mkb_sim* s) {
     MkbGridArgs& g = s->grid;
     const size_t halo = 3 * s->nx * s->rs;
@@ -1213,7 +1348,13 @@ static int halo_connect_typed(mkb_sim* s) {
         g.peer_hi_halo_lo = b;
         g.peer_hi_flag_lo = (unsigned int*)(b + 2 * halo);
     }
-    // Deliver V(tmin) of the boundary rows into the neighbours' slot for step 1
+    return halo_seed_typed<TR>(s);
+}
+
+// Delivers V(tmin) of the boundary rows into the neighbours' slot for step 1.
+template <typename TR>
+static int halo_seed_typed(mkb_sim* s) {
+    MkbGridArgs& g = s->grid;
     const TR* v = plane_ptr<TR>(s, s->parity ? s->plane_alt_v : (u64)std::max(s->i_vm, 0));
     const size_t row = s->nx * s->rs;
     const int grid = (int)((s->nbx + 255) / 256);

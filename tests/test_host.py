@@ -52,14 +52,16 @@ def test_config_struct_matches_header_size():
         src = os.path.join(d, 's.c')
         with open(src, 'w') as f:
             f.write('#include <stdio.h>\n#include "myokit_b200.h"\n'
-                    'int main(){printf("%zu %zu", sizeof(mkb_sim_config), '
-                    'sizeof(mkb_device_info_t));return 0;}')
+                    'int main(){printf("%zu %zu %zu", sizeof(mkb_sim_config), '
+                    'sizeof(mkb_device_info_t), sizeof(mkb_run_config));'
+                    'return 0;}')
         exe = os.path.join(d, 's')
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'),
                                src, '-o', exe])
         out = subprocess.check_output([exe]).decode().split()
     assert int(out[0]) == ctypes.sizeof(capi.SimConfig)
     assert int(out[1]) == ctypes.sizeof(capi.DeviceInfo)
+    assert int(out[2]) == ctypes.sizeof(capi.RunConfig)
 
 
 def test_device_abi_header_is_embedded():

@@ -370,6 +370,48 @@ def test_run_pre_reset_semantics():
     assert np.allclose(a.state(), b.state(), rtol=1e-12, atol=1e-12)
 
 
+def test_state_stays_on_device_between_runs():
+    # Consecutive runs re-arm the resident back-end instead of uploading the
+    # state again; every way of looking at or changing the state must still
+    # see exactly what a fresh simulation would.
+    m, p = example()
+
+    def make():
+        s = myokit_b200.SimulationCUDA(m, p, ncells=(12, 5), precision=DP)
+        s.set_paced_cells(2, 5, 0, 0)
+        return s
+    a = make()
+    a.run(20, log=myokit.LOG_NONE)
+    assert a.last_run_info()['state_uploaded']
+    d1 = a.run(45, log=['engine.time', 'engine.pace', 'membrane.V'])
+    assert not a.last_run_info()['state_uploaded']
+    b = make()
+    b.run(20, log=myokit.LOG_NONE)
+    b.set_state(b.state())              # forces download + fresh upload
+    d2 = b.run(45, log=['engine.time', 'engine.pace', 'membrane.V'])
+    assert b.last_run_info()['state_uploaded']
+    for k in d1:
+        assert np.array_equal(np.array(d1[k]), np.array(d2[k])), k
+    assert max(d1['engine.pace']) == 1      # the 50 ms stimulus was seen
+    assert a.state() == b.state()
+    assert a.time() == 65
+    # a setter between runs invalidates the resident copy
+    a.set_conductance(3, 3)
+    b.set_conductance(3, 3)
+    a.run(5)
+    b.run(5)
+    assert a.state() == b.state()
+    # changing the log selection to an intermediary variable rebuilds the
+    # kernel (new planes) but keeps the state
+    d3 = a.run(2, log=['engine.time', 'ica.ICa'])
+    d4 = b.run(2, log=['engine.time', 'ica.ICa'])
+    assert np.array_equal(np.array(d3['3.2.ica.ICa']), np.array(d4['3.2.ica.ICa']))
+    a.reset()
+    assert a.time() == 0 and a.state() == make().state()
+    a.close()
+    assert a.state() == make().state()
+
+
 def test_protocol_swap_and_no_protocol():
     m, _ = example()
     s = myokit_b200.SimulationCUDA(m, None, ncells=3, precision=DP)
