@@ -245,6 +245,11 @@ static const int kRingHalf = 1024;      // schedule entries per ring half
 // the runtime; with slabs of several GPUs driven from one process that could
 // stop the very thread whose kernels the queued ones are waiting for.
 static const int kThrottle = 128;
+// Steps replayed by one CUDA graph launch (even, so the V ping-pong parity is
+// the same before and after): one driver call and one device-side launch
+// chain instead of kGraphSteps separate launches. Matters when a step is only
+// a few microseconds of work (small and medium grids).
+static const int kGraphSteps = 64;
 
 struct StepRec {
     MkbStepParams p;
@@ -316,6 +321,18 @@ struct mkb_sim {
     u64 h_log_cap = 0;                  // rows
     std::vector<double> row_time, row_pace;     // for rows >= rows_final
 
+    // CUDA graphs of kGraphSteps plain (non-logging) steps
+    struct GraphSlot {
+        cudaGraphExec_t exec[2] = {nullptr, nullptr};   // by V parity at entry
+        MkbStepParams* h_stage = nullptr;               // pinned, kGraphSteps entries
+        MkbStepParams* d_params = nullptr;              // device, kGraphSteps entries
+        cudaEvent_t done = nullptr;
+        bool pending = false;
+    };
+    GraphSlot gslot[2];
+    bool use_graphs = false;
+    u64 graph_seq = 0, graph_launches = 0;
+
     // row-slab halo exchange (multi-GPU)
     char* d_xchg = nullptr;             // [halo_lo 3*nx][halo_hi 3*nx][flag_lo nbx][flag_hi nbx][error]
     size_t xchg_bytes = 0;
@@ -354,6 +371,15 @@ static void sim_destroy(mkb_sim* s) {
     cudaFree(s->d_tab_pre);
     cudaFree(s->d_tab_post);
     cudaFree(s->d_log);
+    for (int i = 0; i < 2; i++) {
+        mkb_sim::GraphSlot& gs = s->gslot[i];
+        for (int p = 0; p < 2; p++) {
+            if (gs.exec[p]) cudaGraphExecDestroy(gs.exec[p]);
+        }
+        if (gs.h_stage) cudaFreeHost(gs.h_stage);
+        cudaFree(gs.d_params);
+        if (gs.done) cudaEventDestroy(gs.done);
+    }
     if (s->peer_lo_base && s->peer_lo_ipc) cudaIpcCloseMemHandle(s->peer_lo_base);
     if (s->peer_hi_base && s->peer_hi_ipc) cudaIpcCloseMemHandle(s->peer_hi_base);
     cudaFree(s->d_xchg);
@@ -803,6 +829,7 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     s->stride = (s->n + 31) / 32 * 32;
     s->block_x = c->block_x;
     s->block_y = c->block_y;
+    s->use_graphs = c->use_graphs != 0;
     s->tmin = c->tmin;
     s->tmax = c->tmax;
     s->default_dt = c->dt;
@@ -861,10 +888,14 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     if (c->diffusion_mode != MKB_DIFF_NONE) {
         if (c->pace_rect) {
             // openclsim.cl:260-274
-            s->grid.pace_x0 = c->pace_x;
-            s->grid.pace_x1 = c->pace_x + c->pace_nx;
-            s->grid.pace_y0 = c->pace_y;
-            s->grid.pace_y1 = c->pace_y + c->pace_ny;
+            // clamped to what a 32-bit compare in the kernel can hold
+            auto clamp32 = [](int64_t v) {
+                return (long long)std::max<int64_t>(-(1ll << 30), std::min<int64_t>(v, 1ll << 30));
+            };
+            s->grid.pace_x0 = clamp32(c->pace_x);
+            s->grid.pace_x1 = clamp32(c->pace_x + c->pace_nx);
+            s->grid.pace_y0 = clamp32(c->pace_y);
+            s->grid.pace_y1 = clamp32(c->pace_y + c->pace_ny);
         } else {
             std::vector<unsigned char> mask(s->n, 0);
             const u64 cell0 = c->iy_offset * c->nx;
@@ -929,11 +960,15 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     {
         u64 bx = (s->nx + s->block_x - 1) / s->block_x;
         u64 by = (s->ny + s->block_y - 1) / s->block_y;
-        if (bx * by > 0x7fffffffull) {
+        // (column blocks, row blocks mod 32768, row blocks / 32768): the kernel
+        // reads its block coordinates without an integer division
+        const u64 gy = std::min<u64>(by, 32768);
+        const u64 gz = (by + gy - 1) / gy;
+        if (bx > 0x7fffffffull || gz > 65535) {
             sim_destroy(s);
             return fail(MKB_ERR_INVALID, "grid too large for one launch");
         }
-        s->launch_grid = dim3((unsigned int)(bx * by), 1, 1);
+        s->launch_grid = dim3((unsigned int)bx, (unsigned int)gy, (unsigned int)gz);
         s->launch_block = dim3((unsigned int)s->block_x, (unsigned int)s->block_y, 1);
     }
 
@@ -1045,6 +1080,46 @@ static int finalize_rows(mkb_sim* s) {
     return MKB_OK;
 }
 
+// Builds (once per slot and entry parity) the graph
+//   [H2D: staged step parameters -> device] -> step kernel x kGraphSteps
+// by stream capture. Each node has its parameter pointer and its V planes
+// baked in; the per-step scalars travel through the staged copy.
+template <typename TR>
+static int graph_get(mkb_sim* s, int slot, int parity, cudaGraphExec_t* out) {
+    mkb_sim::GraphSlot& gs = s->gslot[slot];
+    if (!gs.h_stage) {
+        CUDA_TRY(cudaHostAlloc(&gs.h_stage, kGraphSteps * sizeof(MkbStepParams), cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc(&gs.d_params, kGraphSteps * sizeof(MkbStepParams)));
+        CUDA_TRY(cudaEventCreateWithFlags(&gs.done, cudaEventDisableTiming));
+    }
+    if (!gs.exec[parity]) {
+        const u64 vm_plane = (u64)std::max(s->i_vm, 0);
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaMemcpyAsync(gs.d_params, gs.h_stage, kGraphSteps * sizeof(MkbStepParams),
+                                        cudaMemcpyHostToDevice, s->stream);
+        int par = parity;
+        for (int j = 0; e == cudaSuccess && j < kGraphSteps; j++) {
+            TR* v_in = plane_ptr<TR>(s, par ? s->plane_alt_v : vm_plane);
+            TR* v_out = plane_ptr<TR>(s, par ? vm_plane : s->plane_alt_v);
+            const MkbStepParams* sp = gs.d_params + j;
+            void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
+            e = cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0, s->stream);
+            par ^= 1;
+        }
+        cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
+        if (e == cudaSuccess) e = e2;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&gs.exec[parity], graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            gs.exec[parity] = nullptr;
+            return fail(MKB_ERR_CUDA, "CUDA graph construction failed: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = gs.exec[parity];
+    return MKB_OK;
+}
+
 template <typename TR>
 static int sim_step_typed(mkb_sim* s) {
     const double dt_min = 0;                    // openclsim.c:413
@@ -1119,6 +1194,33 @@ static int sim_step_typed(mkb_sim* s) {
         s->ring_chunk++;
 
         for (size_t i = 0; i < s->recs.size(); i++) {
+            if (s->use_graphs && i + kGraphSteps <= s->recs.size()) {
+                bool plain = true;
+                for (int j = 0; j < kGraphSteps && plain; j++) plain = !s->recs[i + j].logging;
+                if (plain) {
+                    const int slot = (int)(s->graph_seq & 1);
+                    mkb_sim::GraphSlot& gs = s->gslot[slot];
+                    cudaGraphExec_t exec = nullptr;
+                    int grc = graph_get<TR>(s, slot, s->parity, &exec);
+                    if (grc) return grc;
+                    if (gs.pending) {
+                        // the launch that last used this slot's staging area
+                        CUDA_TRY(cudaEventSynchronize(gs.done));
+                        gs.pending = false;
+                    }
+                    for (int j = 0; j < kGraphSteps; j++) gs.h_stage[j] = s->recs[i + j].p;
+                    CUDA_TRY(cudaGraphLaunch(exec, s->stream));
+                    CUDA_TRY(cudaEventRecord(gs.done, s->stream));
+                    gs.pending = true;
+                    s->graph_seq++;
+                    s->graph_launches++;
+                    s->launches += kGraphSteps;
+                    s->steps += kGraphSteps;
+                    s->issued += kGraphSteps;
+                    i += kGraphSteps - 1;       // parity unchanged: kGraphSteps is even
+                    continue;
+                }
+            }
             const StepRec& rec = s->recs[i];
             if (s->issued++ % kThrottle == 0) {
                 const int slot = (int)(s->throttle_count & 1);

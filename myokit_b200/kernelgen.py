@@ -331,7 +331,9 @@ def default_options(precision, n_state):
     ahead of use.
     """
     if precision == myokit.SINGLE_PRECISION:
-        return dict(min_blocks=None, fast_div=False, fast_exp=False,
+        # __fdividef: 2 ulp, inside the 2.5 ulp OpenCL allows its single-
+        # precision division (the reference's arithmetic contract for fp32)
+        return dict(min_blocks=None, fast_div=True, fast_exp=False,
                     load_ahead=32)
     return dict(min_blocks=2 if n_state > 16 else None, fast_div=True,
                 fast_exp=True, load_ahead=32)
@@ -672,20 +674,23 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('%s(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
     p('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
     p('{')
+    p('    // 32-bit indices (64-bit integer arithmetic is emulated on the GPU);')
+    p('    // only the flat cell id, which can pass 2^32, is 64-bit. The launch')
+    p('    // grid is (column blocks, row blocks mod 32768, row blocks / 32768).')
     p('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
-    p('    const unsigned long long nx = g.nx, ny = g.ny, stride = g.stride;')
-    p('    const unsigned long long nbx = (nx + MKB_BX - 1) / MKB_BX;')
-    p('    const unsigned long long bid = blockIdx.x;')
-    p('    const unsigned long long ix = (bid % nbx) * MKB_BX + tx;')
+    p('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+    p('    const unsigned long long stride = g.stride;')
+    p('    const unsigned int nby = (ny + MKB_BY - 1) / MKB_BY;')
+    p('    const unsigned int byr = blockIdx.y + blockIdx.z * gridDim.y;')
+    p('    if (byr >= nby) return;')
+    p('    const unsigned int bxb = blockIdx.x;')
+    p('    const unsigned int ix = bxb * MKB_BX + tx;')
     if slab:
         p('    // Boundary row blocks first: their rows reach the neighbouring GPUs')
         p('    // while the interior is still being computed.')
-        p('    const unsigned long long nby = (ny + MKB_BY - 1) / MKB_BY;')
-        p('    const unsigned long long byr = bid / nbx;')
-        p('    const unsigned long long byb = (byr == 0) ? 0 : ((byr == 1) ? nby - 1 : byr - 1);')
-        p('    const unsigned long long iy = byb * MKB_BY + ty;')
+        p('    const unsigned int byb = (byr == 0) ? 0 : ((byr == 1) ? nby - 1 : byr - 1);')
+        p('    const unsigned int iy = byb * MKB_BY + ty;')
         p('    const unsigned int step = sp->step;')
-        p('    const unsigned long long bxb = bid % nbx;')
         p('    const bool wait_lo = (byb == 0) && g.halo_lo;')
         p('    const bool wait_hi = (byb == nby - 1) && g.halo_hi;')
         p('    if (wait_lo || wait_hi) {')
@@ -697,9 +702,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('        __syncthreads();')
         p('    }')
     else:
-        p('    const unsigned long long iy = (bid / nbx) * MKB_BY + ty;')
+        p('    const unsigned int iy = byr * MKB_BY + ty;')
     p('    const bool active = (ix < nx) && (iy < ny);')
-    p('    const unsigned long long cid = ix + iy * nx;')
+    p('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
     p('    Real* const state = (Real*)g.state;')
     p('    // Per-step scalars, cast like openclsim.c:1063,1148,1155')
     p('    const Real time = (Real)sp->time;')
@@ -711,8 +716,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     if diffusion:
         p('    const Real vc = active ? v_in[cid] : (Real)0;')
     if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
-        p('    const unsigned long long iyg = iy + g.iy_offset;  // global row')
-        p('    const unsigned long long nyg = g.ny_global;')
+        p('    const unsigned int iyg = iy + (unsigned int)g.iy_offset;  // global row')
+        p('    const unsigned int nyg = (unsigned int)g.ny_global;')
     if diffusion_mode == DIFF_FIELD:
         p('    // Edge conductances, gx[(ny, nx-1)], gy[(ny-1, nx)] (openclsim.cl:')
         p('    // 475-482); both pointers are slab-relative: gyf[-nx .. -1] is the')
@@ -814,11 +819,11 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('    const Real pace = g.paced_mask[cid] ? pace_in : (Real)0;')
         else:
             if diffusion_mode == DIFF_CONNECTIONS:
-                p('    const long long pix = (long long)ix, piy = 0;')
+                p('    const int pix = (int)ix, piy = 0;')
             else:
-                p('    const long long pix = (long long)ix, piy = (long long)iyg;')
-            p('    const Real pace = (pix >= g.pace_x0 && pix < g.pace_x1 &&')
-            p('                       piy >= g.pace_y0 && piy < g.pace_y1) ? pace_in : (Real)0;')
+                p('    const int pix = (int)ix, piy = (int)iyg;')
+            p('    const Real pace = (pix >= (int)g.pace_x0 && pix < (int)g.pace_x1 &&')
+            p('                       piy >= (int)g.pace_y0 && piy < (int)g.pace_y1) ? pace_in : (Real)0;')
         p('    if (store_aux) ((Real*)g.idiff)[cid] = idiff;')
     else:
         p('    const Real pace = pace_in;')

@@ -1,0 +1,42 @@
+"""Throughput of the other BASELINE configurations (device-resident timing)."""
+import os, sys, time
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R)
+import numpy as np
+import myokit_b200, myokit
+from myokit_b200 import workloads
+
+S = myokit_b200.SimulationCUDA
+
+
+def report(name, s, steps, warmup=20, **opts):
+    if opts:
+        s.set_kernel_options(**opts)
+    info = s.benchmark_steps(steps, warmup=warmup)
+    ms = info['device_ms'] / info['steps']
+    print('%-34s %9d cells  %8.4f ms/step  %.3e cell-steps/s  (%d launches)' % (
+        name, info['cells'], ms, info['cells'] / ms * 1e3, info['kernel_launches']), flush=True)
+
+
+which = sys.argv[1:] or ['c1', 'c2', 'c4', 'c5']
+if 'c1' in which:
+    report('C1 LR91 1-D 128 fp64', workloads.c1_cable(S, 128), 20000)
+    report('C1-like LR91 1-D 16384 fp64', workloads.c1_cable(S, 16384), 5000)
+if 'c2' in which:
+    report('C2 LR91 512^2 fp32', workloads.c2_planar(S, 512), 5000)
+    report('C2 LR91 512^2 fp32 b32x8', workloads.c2_planar(S, 512), 5000, block=(32, 8))
+    report('C2 LR91 512^2 fp32 b128x2', workloads.c2_planar(S, 512), 5000, block=(128, 2))
+    report('C2 LR91 2048^2 fp32', workloads.c2_planar(S, 2048), 500)
+if 'c4' in which:
+    report('C4-proxy LR91 8192^2 fp32', workloads.c2_planar(S, 8192), 50, warmup=5)
+    report('C4-proxy LR91 8192^2 fp32 fdiv', workloads.c2_planar(S, 8192), 50, warmup=5, fast_div=True)
+    report('C4-proxy LR91 8192^2 fp32 mb4', workloads.c2_planar(S, 8192), 50, warmup=5, min_blocks=4)
+if 'c5' in which:
+    m = workloads.data_model('decker-2009.mmt')
+    p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)
+    n = 1 << 20
+    s = S(m, p, ncells=n, diffusion=False, precision=myokit.DOUBLE_PRECISION, rl=True)
+    rng = np.random.default_rng(42)
+    for var, base in (('ikr.Gbar', 0.0138542), ('ina.Gbar', 9.075), ('ik1.Gbar', 0.5)):
+        s.set_field(var, base * (1 - rng.uniform(0, 1, n)))
+    report('C5-i decker 1M uncoupled fp64 RL', s, 200, warmup=5)

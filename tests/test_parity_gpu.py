@@ -412,6 +412,31 @@ def test_state_stays_on_device_between_runs():
     assert a.state() == make().state()
 
 
+def test_graph_replay_equals_single_launches():
+    # Batches of 64 plain steps are replayed as CUDA graphs; logging steps and
+    # remainders are single launches. Same kernels, same order: same bits.
+    m, _ = example()
+    p = myokit.pacing.blocktrain(duration=0.7, offset=0.3, period=2.9)
+    out = []
+    for graphs in (True, False):
+        s = myokit_b200.SimulationCUDA(m, p, ncells=(20, 9), precision=DP)
+        s.set_kernel_options(use_graphs=graphs)
+        s.set_paced_cells(3, 9, 0, 0)
+        d = s.run(11, log=['engine.time', 'engine.pace', 'membrane.V',
+                           'ica.ICa'], log_interval=0.7)
+        d2 = s.run(4.2, log=['engine.time', 'membrane.V'], log_interval=1.9)
+        out.append((dict((k, np.array(v)) for k, v in d.items()),
+                    dict((k, np.array(v)) for k, v in d2.items()),
+                    s.state_array(), s.last_run_info()))
+    (a1, a2, sa, ia), (b1, b2, sb, ib) = out
+    assert ia['steps'] == ib['steps'] and ia['kernel_launches'] == ib['kernel_launches']
+    for x, y in ((a1, b1), (a2, b2)):
+        assert set(x) == set(y)
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
+    assert np.array_equal(sa, sb)
+
+
 def test_protocol_swap_and_no_protocol():
     m, _ = example()
     s = myokit_b200.SimulationCUDA(m, None, ncells=3, precision=DP)
