@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MKB_ABI_VERSION 1
+#define MKB_ABI_VERSION 2
 
 /* Error codes */
 #define MKB_OK               0
@@ -96,7 +96,9 @@ typedef struct mkb_sim_config {
     const void* cubin;
     size_t cubin_size;
     const char* kernel_name;    /* "mkb_cell_step" */
-    int block_x, block_y;       /* thread-block tile the kernel was generated for */
+    int block_x, block_y;       /* thread block the kernel was generated for */
+    int cells_per_thread;       /* x-adjacent cells per thread (0 or 1: one) */
+    int rows_per_thread;        /* rows per thread (0 or 1: one) */
 
     /* Model shape */
     int n_state;

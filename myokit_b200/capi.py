@@ -13,7 +13,7 @@ c_u64 = ctypes.c_uint64
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
 
-MKB_ABI_VERSION = 1
+MKB_ABI_VERSION = 2
 MKB_OK = 0
 MKB_ERR_INVALID = -1
 MKB_ERR_CUDA = -2
@@ -55,6 +55,7 @@ class SimConfig(ctypes.Structure):
         ('cubin', c_vp), ('cubin_size', ctypes.c_size_t),
         ('kernel_name', ctypes.c_char_p),
         ('block_x', ctypes.c_int), ('block_y', ctypes.c_int),
+        ('cells_per_thread', ctypes.c_int), ('rows_per_thread', ctypes.c_int),
         ('n_state', ctypes.c_int), ('i_vm', ctypes.c_int),
         ('n_inter', ctypes.c_int), ('n_field', ctypes.c_int),
         ('nx', c_u64), ('ny', c_u64),

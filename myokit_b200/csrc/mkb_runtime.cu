@@ -263,7 +263,7 @@ struct mkb_sim {
     size_t rs = 8, hs = 8;              // sizeof(Real), sizeof(host element)
     int n_state = 0, i_vm = 0, n_inter = 0, n_field = 0, diff_mode = 0;
     u64 nx = 0, ny = 0, n = 0, stride = 0;
-    int block_x = 32, block_y = 1;
+    int block_x = 32, block_y = 1, cpt = 1, rpt = 1;
     u64 steps_per_call = 1000;
 
     // CUDA objects
@@ -829,6 +829,12 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     s->stride = (s->n + 31) / 32 * 32;
     s->block_x = c->block_x;
     s->block_y = c->block_y;
+    s->cpt = c->cells_per_thread > 1 ? c->cells_per_thread : 1;
+    s->rpt = c->rows_per_thread > 1 ? c->rows_per_thread : 1;
+    if (s->cpt > 1 && (c->nx % (u64)s->cpt) != 0) {
+        delete s;
+        return fail(MKB_ERR_INVALID, "nx must be a multiple of cells_per_thread");
+    }
     s->use_graphs = c->use_graphs != 0;
     s->tmin = c->tmin;
     s->tmax = c->tmax;
@@ -938,7 +944,7 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
         const u64 nyg = c->ny_global ? c->ny_global : s->ny;
         s->has_lo = c->iy_offset > 0;
         s->has_hi = c->iy_offset + s->ny < nyg;
-        s->nbx = (s->nx + s->block_x - 1) / s->block_x;
+        s->nbx = (s->nx + (u64)s->block_x * s->cpt - 1) / ((u64)s->block_x * s->cpt);
         if ((s->has_lo || s->has_hi) &&
             (s->diff_mode == MKB_DIFF_HOMOGENEOUS || s->diff_mode == MKB_DIFF_FIELD)) {
             // Exchange block: this GPU's ghost rows and arrival flags
@@ -958,8 +964,10 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     g.gx = c->gx;
     g.gy = c->gy;
     {
-        u64 bx = (s->nx + s->block_x - 1) / s->block_x;
-        u64 by = (s->ny + s->block_y - 1) / s->block_y;
+        const u64 cells_x = (u64)s->block_x * (u64)s->cpt;
+        u64 bx = (s->nx + cells_x - 1) / cells_x;
+        const u64 cells_y = (u64)s->block_y * (u64)s->rpt;
+        u64 by = (s->ny + cells_y - 1) / cells_y;
         // (column blocks, row blocks mod 32768, row blocks / 32768): the kernel
         // reads its block coordinates without an integer division
         const u64 gy = std::min<u64>(by, 32768);

@@ -297,6 +297,52 @@ __device__ __forceinline__ double mkb_exp(double x) {
 """
 
 
+_VECTOR_PRELUDE = r"""
+// N consecutive Reals as one 8/16-byte access (two for 32 bytes). The address
+// is aligned: planes start 128-byte aligned, nx and the thread's first cell
+// are multiples of N.
+template <int N>
+__device__ __forceinline__ void mkb_vload(Real (&d)[N], const Real* p, bool ok) {
+    if (!ok) {
+#pragma unroll
+        for (int c = 0; c < N; c++) d[c] = (Real)0;
+        return;
+    }
+    if constexpr (sizeof(Real) * N == 8) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        d[0] = t.x; d[1] = t.y;
+    } else if constexpr (sizeof(Real) == 4) {
+#pragma unroll
+        for (int c = 0; c < N; c += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(p + c);
+            d[c] = t.x; d[c + 1] = t.y; d[c + 2] = t.z; d[c + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < N; c += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + c);
+            d[c] = t.x; d[c + 1] = t.y;
+        }
+    }
+}
+template <int N>
+__device__ __forceinline__ void mkb_vstore(Real* p, const Real (&d)[N]) {
+    if constexpr (sizeof(Real) * N == 8) {
+        *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]);
+    } else if constexpr (sizeof(Real) == 4) {
+#pragma unroll
+        for (int c = 0; c < N; c += 4) {
+            *reinterpret_cast<float4*>(p + c) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < N; c += 2) {
+            *reinterpret_cast<double2*>(p + c) = make_double2(d[c], d[c + 1]);
+        }
+    }
+}
+"""
+
 # Output of scripts/gen_exp_coeffs.py (degree 11, c11 .. c2)
 _EXP_COEFFS = [
     '0x1.af632a0f7e2cep-26', '0x1.28b4101c77212p-22', '0x1.71ddf56d8deb5p-19',
@@ -334,9 +380,13 @@ def default_options(precision, n_state):
         # __fdividef: 2 ulp, inside the 2.5 ulp OpenCL allows its single-
         # precision division (the reference's arithmetic contract for fp32)
         return dict(min_blocks=None, fast_div=True, fast_exp=False,
-                    load_ahead=32)
+                    load_ahead=32,
+                    cells_per_thread=4 if n_state <= 4 else 1,
+                    rows_per_thread=4 if n_state <= 4 else 1)
     return dict(min_blocks=2 if n_state > 16 else None, fast_div=True,
-                fast_exp=True, load_ahead=32)
+                fast_exp=True, load_ahead=32,
+                cells_per_thread=2 if n_state <= 4 else 1,
+                rows_per_thread=4 if n_state <= 4 else 1)
 
 
 class KernelSource:
@@ -352,6 +402,8 @@ class KernelSource:
         self.diffusion_mode = diffusion_mode
         self.options = tuple(options)
         self.kernel_name = KERNEL_NAME
+        self.cells_per_thread = 1
+        self.rows_per_thread = 1
 
     def key(self):
         h = hashlib.sha256()
@@ -364,7 +416,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              diffusion_mode, paced_list, block, native_maths=False, fmad=True,
              max_registers=None, pow_multiply=True, fast_div=False,
              lazy_state=True, min_blocks=None, fast_exp=False,
-             const_pool=True, load_ahead=8, slab=False):
+             const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
+             rows_per_thread=1):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -386,6 +439,17 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         register allocation must allow.
     ``const_pool``
         Double-precision literals in a ``__constant__`` table.
+    ``cells_per_thread``
+        2 or 4: each thread owns that many x-adjacent cells, so every plane
+        access is one 8/16/32-byte vector load or store and the index / halo
+        bookkeeping is paid once per thread. For small models, where that
+        bookkeeping is a large share of the instructions (the stencil-only
+        kernel is otherwise instruction-, not HBM-bound). Needs
+        ``nx % cells_per_thread == 0``; not combined with ``slab`` or
+        connections.
+    ``rows_per_thread``
+        With ``cells_per_thread`` > 1: each thread also walks that many rows
+        (more bytes in flight per thread, fewer and fatter thread blocks).
     ``slab``
         Row-slab variant for multi-GPU grids: boundary row blocks run first,
         wait for the neighbouring GPU's ghost row (arrival flags), and push
@@ -408,6 +472,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     bx, by = block
     diffusion = diffusion_mode != DIFF_NONE
     slab = bool(slab) and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD)
+    cpt = int(cells_per_thread or 1)
+    if slab or diffusion_mode == DIFF_CONNECTIONS or cpt not in (2, 4, 8) \
+            or (sp and cpt == 2):
+        cpt = 1
 
     equations = model.solvable_order()
     del equations['*remaining*']
@@ -646,6 +714,235 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 var = eq.lhs.var()
                 if var not in fields and var not in folded:
                     consts.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+
+    # ------------------------------------------------------------------
+    # Vector path: several x-adjacent cells (and rows) per thread
+    # ------------------------------------------------------------------
+    if cpt > 1:
+        rpt = max(int(rows_per_thread or 1), 1)
+        o = []
+        q = o.append
+        q('// Generated by myokit_b200.kernelgen for sm_100a — do not edit.')
+        q('// Model: %s (%d x %d cells per thread)' % (model.name(), cpt, rpt))
+        q('#include "mkb_device_abi.h"')
+        q('typedef %s Real;' % real)
+        q('#define MKB_BX %d' % bx)
+        q('#define MKB_BY %d' % by)
+        q('#define MKB_CPT %d' % cpt)
+        q('#define MKB_RPT %d' % rpt)
+        q(_PRELUDE)
+        q(_VECTOR_PRELUDE)
+        if pooled and w._pool:
+            q('__constant__ double mkb_k[%d] = {' % len(w._pool))
+            for x in w._pool:
+                q('    %r,' % x)
+            q('};')
+        q('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
+        q('%s(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
+        q('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
+        q('{')
+        q('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
+        q('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+        q('    const unsigned long long stride = g.stride;')
+        q('    const unsigned int nby = (ny + MKB_BY * MKB_RPT - 1) / (MKB_BY * MKB_RPT);')
+        q('    const unsigned int byr = blockIdx.y + blockIdx.z * gridDim.y;')
+        q('    if (byr >= nby) return;')
+        q('    // This thread owns the patch of cells ix0 .. ix0 + MKB_CPT - 1 (nx is a')
+        q('    // multiple of MKB_CPT: all inside or all outside) by rows iy0 .. iy0 +')
+        q('    // MKB_RPT - 1. Neighbours inside the patch are in registers; only the')
+        q('    // rim of the patch is exchanged through shared memory.')
+        q('    const unsigned int ix0 = (blockIdx.x * MKB_BX + tx) * MKB_CPT;')
+        q('    const unsigned int iy0 = (byr * MKB_BY + ty) * MKB_RPT;')
+        q('    const bool in_x = ix0 < nx;')
+        q('    Real* const state = (Real*)g.state;')
+        q('    const Real time = (Real)sp->time;')
+        q('    const Real dt = (Real)sp->dt;')
+        q('    const Real pace_in = (Real)sp->pace;')
+        q('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
+        q('    (void)time; (void)pace_in; (void)store_aux; (void)v_in; (void)v_out;')
+        q('')
+        q('    // All vector loads of this thread first: they are in flight together')
+        if diffusion:
+            q('    Real vc[MKB_RPT][MKB_CPT];')
+        for var in states:
+            if var.index() != i_vm:
+                q('    Real S%d[MKB_RPT][MKB_CPT];' % var.index())
+        for k, var in enumerate(fields):
+            q('    Real F%d[MKB_RPT][MKB_CPT];' % k)
+        q('    #pragma unroll')
+        q('    for (int r = 0; r < MKB_RPT; r++) {')
+        q('        const unsigned int iy = iy0 + r;')
+        q('        const bool active = in_x && (iy < ny);')
+        q('        const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
+        if diffusion:
+            q('        mkb_vload<MKB_CPT>(vc[r], v_in + cid0, active);')
+        for var in states:
+            if var.index() != i_vm:
+                q('        mkb_vload<MKB_CPT>(S%d[r], state + %dull * stride + cid0, active);'
+                  % (var.index(), var.index()))
+        for k, var in enumerate(fields):
+            q('        mkb_vload<MKB_CPT>(F%d[r], (const Real*)g.field + %dull * stride + cid0, active);'
+              % (k, k))
+        q('    }')
+        if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+            q('    const unsigned int nyg = (unsigned int)g.ny_global;')
+            q('    // Rim exchange: first / last column of every row of the patch, first')
+            q('    // and last row of the patch; block-edge threads fetch the true halo.')
+            q('    __shared__ Real col_l[MKB_BY * MKB_RPT][MKB_BX + 2];   // [row][tx + 1]: first cell')
+            q('    __shared__ Real col_r[MKB_BY * MKB_RPT][MKB_BX + 2];   // [row][tx + 1]: last cell')
+            q('    __shared__ Real row_t[MKB_BY + 2][MKB_BX * MKB_CPT];   // [ty + 1]: first row')
+            q('    __shared__ Real row_b[MKB_BY + 2][MKB_BX * MKB_CPT];   // [ty + 1]: last row')
+            q('    #pragma unroll')
+            q('    for (int r = 0; r < MKB_RPT; r++) {')
+            q('        const unsigned int iy = iy0 + r;')
+            q('        const unsigned int tr = ty * MKB_RPT + r;')
+            q('        col_l[tr][tx + 1] = vc[r][0];')
+            q('        col_r[tr][tx + 1] = vc[r][MKB_CPT - 1];')
+            q('        if (in_x && iy < ny) {')
+            q('            const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
+            q('            // halo cells left and right of the block')
+            q('            if (tx == 0) col_r[tr][0] = (ix0 > 0) ? v_in[cid0 - 1] : vc[r][0];')
+            q('            if (tx == MKB_BX - 1 || ix0 + MKB_CPT >= nx)')
+            q('                col_l[tr][tx + 2] = (ix0 + MKB_CPT < nx) ? v_in[cid0 + MKB_CPT] : vc[r][MKB_CPT - 1];')
+            q('        }')
+            q('    }')
+            q('    #pragma unroll')
+            q('    for (int c = 0; c < MKB_CPT; c++) {')
+            q('        row_t[ty + 1][tx * MKB_CPT + c] = vc[0][c];')
+            q('        row_b[ty + 1][tx * MKB_CPT + c] = vc[MKB_RPT - 1][c];')
+            q('    }')
+            q('    if (in_x && iy0 < ny) {')
+            q('        if (ty == 0) {')
+            q('            // row above the block')
+            q('            Real vn[MKB_CPT];')
+            q('            mkb_vload<MKB_CPT>(vn, v_in + (unsigned long long)(iy0 - 1) * nx + ix0, iy0 > 0);')
+            q('            #pragma unroll')
+            q('            for (int c = 0; c < MKB_CPT; c++) row_b[0][tx * MKB_CPT + c] = vn[c];')
+            q('        }')
+            q('        if (ty == MKB_BY - 1) {')
+            q('            // row below the block')
+            q('            Real vn[MKB_CPT];')
+            q('            mkb_vload<MKB_CPT>(vn, v_in + (unsigned long long)(iy0 + MKB_RPT) * nx + ix0, iy0 + MKB_RPT < ny);')
+            q('            #pragma unroll')
+            q('            for (int c = 0; c < MKB_CPT; c++) row_t[MKB_BY + 1][tx * MKB_CPT + c] = vn[c];')
+            q('        }')
+            q('    }')
+            q('    __syncthreads();')
+            q('    if (!in_x || iy0 >= ny) return;')
+            q('    const bool at_x0 = (ix0 == 0), at_x1 = (ix0 + MKB_CPT == nx);')
+        else:
+            q('    if (!in_x || iy0 >= ny) return;')
+        if diffusion_mode == DIFF_HOMOGENEOUS:
+            q('    const Real gx = (Real)g.gx, gy = (Real)g.gy;')
+        if diffusion_mode == DIFF_FIELD:
+            q('    const Real* const gxf = (const Real*)g.gx_field;')
+            q('    const Real* const gyf = (const Real*)g.gy_field;')
+        if diffusion and not paced_list:
+            q('    // paced rectangle, relative to this patch (openclsim.cl:260-274)')
+            q('    const bool pacing_on = (pace_in != (Real)0);')
+            q('    const int pc0 = (int)g.pace_x0 - (int)ix0, pc1 = (int)g.pace_x1 - (int)ix0;')
+        q('')
+        q('    #pragma unroll')
+        q('    for (int r = 0; r < MKB_RPT; r++) {')
+        q('    const unsigned int iy = iy0 + r;')
+        q('    if (iy >= ny) break;')
+        q('    const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
+        for var in states:
+            q('    Real N%d[MKB_CPT];' % var.index())
+        if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+            q('    const unsigned int tr = ty * MKB_RPT + r;')
+            q('    const unsigned int iyg = iy + (unsigned int)g.iy_offset;')
+            q('    const bool at_y0 = (iyg == 0), at_y1 = (iyg == nyg - 1);')
+            if not paced_list:
+                q('    const bool row_paced = pacing_on && (int)iyg >= (int)g.pace_y0 && (int)iyg < (int)g.pace_y1;')
+        q('    #pragma unroll')
+        q('    for (int c = 0; c < MKB_CPT; c++) {')
+        q('    const unsigned int ix = ix0 + c;')
+        q('    const unsigned long long cid = cid0 + c;')
+        q('    (void)ix; (void)cid;')
+        if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+            q('    const Real vcc = vc[r][c];')
+            q('    // neighbours: registers inside the patch, shared memory on its rim')
+            q('    const Real vxm = (c > 0) ? vc[r][c > 0 ? c - 1 : 0] : col_r[tr][tx];')
+            q('    const Real vxp = (c < MKB_CPT - 1) ? vc[r][c < MKB_CPT - 1 ? c + 1 : 0] : col_l[tr][tx + 2];')
+            q('    const Real vym = (r > 0) ? vc[r > 0 ? r - 1 : 0][c] : row_b[ty][tx * MKB_CPT + c];')
+            q('    const Real vyp = (r < MKB_RPT - 1) ? vc[r < MKB_RPT - 1 ? r + 1 : 0][c] : row_t[ty + 2][tx * MKB_CPT + c];')
+            q('    Real idiff;')
+            if diffusion_mode == DIFF_HOMOGENEOUS:
+                q('    // openclsim.cl:401-434 (diff_step); nx >= MKB_CPT > 1 here. Only the')
+                q('    // first / last cell of a patch can sit on the grid edge.')
+                q('    if (c == 0 && at_x0) idiff = gx * (vcc - vxp);')
+                q('    else if (c == MKB_CPT - 1 && at_x1) idiff = gx * (vcc - vxm);')
+                q('    else idiff = gx * (2 * vcc - vxm - vxp);')
+                q('    if (nyg > 1) {')
+                q('        if (at_y0) idiff += gy * (vcc - vyp);')
+                q('        else if (at_y1) idiff += gy * (vcc - vym);')
+                q('        else idiff += gy * (2 * vcc - vym - vyp);')
+                q('    }')
+            else:
+                q('    // openclsim.cl:469-486 (diff_hetero)')
+                q('    idiff = 0.0;')
+                q('    if (!(c == 0 && at_x0)) { idiff += gxf[cid - iy - 1] * (vcc - vxm); }')
+                q('    if (!(c == MKB_CPT - 1 && at_x1)) { idiff += gxf[cid - iy] * (vcc - vxp); }')
+                q('    if (nyg > 1) {')
+                q('        if (!at_y0) idiff += gyf[(long long)cid - (long long)nx] * (vcc - vym);')
+                q('        if (!at_y1) idiff += gyf[cid] * (vcc - vyp);')
+                q('    }')
+            if paced_list:
+                q('    const Real pace = g.paced_mask[cid] ? pace_in : (Real)0;')
+            else:
+                q('    const Real pace = (row_paced && c >= pc0 && c < pc1) ? pace_in : (Real)0;')
+            q('    if (store_aux) ((Real*)g.idiff)[cid] = idiff;')
+        else:
+            q('    const Real pace = pace_in;')
+        q('    (void)pace;')
+        for k, var in enumerate(fields):
+            q('    const Real %s = F%d[r][c];' % (v(var), k))
+        for line in consts:
+            q(line)
+        for var in states:
+            if var.index() == i_vm:
+                q('    const Real %s = vcc;' % v(var))
+            else:
+                q('    const Real %s = S%d[r][c];' % (v(var), var.index()))
+        for name, eq in todo:
+            if name:
+                q('    // Component: %s' % name)
+            var = eq.lhs.var()
+            q('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+            if var in inter_index and not eq.lhs.is_derivative():
+                q('    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                  % (inter_index[var], v(eq.lhs)))
+        q('    // Update (openclsim.cl:358-364)')
+        for var in states:
+            if var in rl_states:
+                inf, tau = rl_states[var]
+                inf, tau, x = v(inf), v(tau), v(var)
+                arg = '-dt / %s' % tau
+                if fast_div and not sp and not native_maths:
+                    arg = 'mkb_div(-dt, %s)' % tau
+                rhs = '%s - (%s - %s) * %s(%s)' % (inf, inf, x, exp, arg)
+            else:
+                rhs = '%s + dt * %s' % (v(var), v(var.lhs()))
+            q('    N%d[c] = %s;' % (var.index(), rhs))
+        q('    }   // cells of this row')
+        for var in states:
+            if var.index() == i_vm:
+                q('    mkb_vstore<MKB_CPT>(v_out + cid0, N%d);' % var.index())
+            else:
+                q('    mkb_vstore<MKB_CPT>(state + %dull * stride + cid0, N%d);'
+                  % (var.index(), var.index()))
+        q('    }   // rows of this thread')
+        q('}')
+        q('')
+        options = ['--fmad=true' if fmad else '--fmad=false']
+        if max_registers:
+            options.append('--maxrregcount=%d' % int(max_registers))
+        ks = KernelSource('\n'.join(o), block, n_state, i_vm, len(inter_log),
+                          len(fields), diffusion_mode, options)
+        ks.cells_per_thread = cpt
+        ks.rows_per_thread = rpt
+        return ks
 
     # ------------------------------------------------------------------
     # Assembly

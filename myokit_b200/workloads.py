@@ -81,6 +81,47 @@ def c3_hetero(sim_class, nx=2048, ny=None, model=None, **kw):
     return s
 
 
+STENCIL_ONLY_MMT = """
+[[model]]
+name: stencil-only
+desc: V' = V - dt * i_diff; the fused kernel with the cell model removed
+membrane.V = -80
+
+[engine]
+time = 0 bind time
+pace = 0 bind pace
+
+[membrane]
+dot(V) = -(i_diff + engine.pace * stim)
+    label membrane_potential
+stim = -10
+i_diff = 0 bind diffusion_current
+"""
+
+
+def stencil_only(sim_class, nx, ny=None, precision=None, hetero=False, **kw):
+    """
+    The stencil-only variant SURVEY.md §8(d) asks for: same tile / halo code,
+    cell model replaced by ``V' = V - dt * i_diff``. Algorithmic bytes per
+    cell-step: 2 * sizeof(Real) (4 * sizeof(Real) with gx / gy fields).
+    """
+    ny = nx if ny is None else ny
+    if precision is None:
+        precision = myokit.SINGLE_PRECISION
+    m = myokit.parse_model(STENCIL_ONLY_MMT)
+    p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)
+    s = sim_class(m, p, ncells=(nx, ny), precision=precision, **kw)
+    if hetero:
+        rng = np.random.default_rng(99)
+        s.set_conductance_field(rng.uniform(0.5, 1.5, size=(ny, nx - 1)),
+                                rng.uniform(0.5, 1.5, size=(ny - 1, nx)))
+    else:
+        s.set_conductance(1.0, 0.5)
+    s.set_paced_cells(nx=5, ny=ny, x=0, y=0)
+    s.set_step_size(0.005)
+    return s
+
+
 # Algorithmic bytes per cell-step, SURVEY.md §8(d) / BASELINE.md §3:
 # B = (2 * n_state + n_field + n_gfield + 1) * sizeof(Real)
 def algorithmic_bytes(n_state, n_field, n_gfield, real_size):

@@ -31,6 +31,22 @@ if 'c4' in which:
     report('C4-proxy LR91 8192^2 fp32', workloads.c2_planar(S, 8192), 50, warmup=5)
     report('C4-proxy LR91 8192^2 fp32 fdiv', workloads.c2_planar(S, 8192), 50, warmup=5, fast_div=True)
     report('C4-proxy LR91 8192^2 fp32 mb4', workloads.c2_planar(S, 8192), 50, warmup=5, min_blocks=4)
+if 'stencil' in which:
+    for prec, name in ((myokit.SINGLE_PRECISION, 'fp32'), (myokit.DOUBLE_PRECISION, 'fp64')):
+        rs = 4 if name == 'fp32' else 8
+        for opts in (dict(block=(64, 4)), dict(block=(64, 4), rows_per_thread=2), dict(block=(64, 4), rows_per_thread=4), dict(block=(64, 2), rows_per_thread=8), dict(block=(32, 8), rows_per_thread=4)):
+            s = workloads.stencil_only(S, 8192, 4096, precision=prec)
+            s.set_kernel_options(**opts)
+            info = s.benchmark_steps(50, warmup=5)
+            ms = info['device_ms'] / info['steps']
+            gbs = 2 * rs * info['cells'] / ms / 1e6
+            print('stencil-only 8192^2 %s %-22s %8.4f ms/step  %7.1f GB/s  (%.1f%% of 6392.8)' % (
+                name, opts, ms, gbs, 100 * gbs / 6392.8), flush=True)
+    s = workloads.stencil_only(S, 8192, precision=myokit.SINGLE_PRECISION, hetero=True)
+    info = s.benchmark_steps(50, warmup=5)
+    ms = info['device_ms'] / info['steps']
+    gbs = 4 * 4 * info['cells'] / ms / 1e6
+    print('stencil-only 8192^2 fp32 hetero           %8.4f ms/step  %7.1f GB/s  (%.1f%% of 6392.8)' % (ms, gbs, 100 * gbs / 6392.8))
 if 'c5' in which:
     m = workloads.data_model('decker-2009.mmt')
     p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)

@@ -153,6 +153,17 @@ def test_every_kernel_variant_compiles_for_sm100a():
 
 def test_generated_source_follows_reference_arithmetic():
     s = variants()['1d_fp64']
+    # tiny models default to several cells per thread with vector accesses;
+    # any model can ask for it
+    s.set_kernel_options(cells_per_thread=2)
+    code = s.kernel_source().code
+    assert '#define MKB_CPT 2' in code
+    assert 'mkb_vload<MKB_CPT>(S1[r], state + 1ull * stride + cid0, active);' in code
+    assert 'N1[c] = V_m + dt * D_m;' in code
+    assert 'mkb_vstore<MKB_CPT>(v_out + cid0, N0);' in code
+    assert 'gx * (2 * vcc - vxm - vxp)' in code
+    # the one-cell-per-thread form
+    s.set_kernel_options(cells_per_thread=1)
     code = s.kernel_source().code
     # expression text comes from myokit's own CUDA writer; integer powers
     # become multiplication chains unless asked otherwise

@@ -412,6 +412,75 @@ def test_state_stays_on_device_between_runs():
     assert a.state() == make().state()
 
 
+@pytest.mark.parametrize('precision,cpt,rpt', [
+    (DP, 2, 1), (DP, 4, 2), (SP, 4, 1), (SP, 4, 4), (SP, 8, 2)])
+def test_vector_path_equals_scalar_path(precision, cpt, rpt):
+    # Several cells (and rows) per thread with vector loads/stores: same
+    # arithmetic per cell — homogeneous and heterogeneous stencils, fields,
+    # logged intermediaries, partial blocks. Compiled without FMA contraction
+    # the two code shapes must give the same bits (with contraction the
+    # compiler may fuse differently in the two shapes).
+    m, _ = example()
+    p = myokit.pacing.blocktrain(**PULSE)
+    nx, ny = 72, 11
+    rng = np.random.default_rng(3)
+    gx = rng.uniform(4, 12, size=(ny, nx - 1))
+    gy = rng.uniform(2, 8, size=(ny - 1, nx))
+    gna = rng.uniform(10, 16, size=(ny, nx))
+    logspec = ['engine.time', 'membrane.V', 'membrane.i_diff', 'ina.INa']
+    for hetero in (False, True):
+        res = []
+        for c in (1, cpt):
+            s = myokit_b200.SimulationCUDA(m, p, ncells=(nx, ny),
+                                           precision=precision)
+            s.set_kernel_options(cells_per_thread=c, rows_per_thread=rpt,
+                                 fmad=False)
+            assert s.kernel_source().cells_per_thread == c
+            if hetero:
+                s.set_conductance_field(gx, gy)
+                s.set_field('ina.gNa', gna)
+            else:
+                s.set_conductance(9, 4)
+            s.set_paced_cells(3, ny, 0, 0)
+            t, f = s.run_fields(6, logspec[1:], log_interval=0.5)
+            res.append((t, f, s.state_array()))
+        (t0, f0, s0), (t1, f1, s1) = res
+        assert f0['membrane.V'][-1].max() > 0
+        assert np.array_equal(t0, t1)
+        for k in f0:
+            assert np.array_equal(f0[k], f1[k]), (hetero, k)
+        assert np.array_equal(s0, s1)
+    # 1-d and uncoupled grids take the same path
+    for diffusion in (True, False):
+        res = []
+        for c in (1, cpt):
+            s = myokit_b200.SimulationCUDA(m, p, ncells=40 * cpt,
+                                           diffusion=diffusion,
+                                           precision=precision)
+            s.set_kernel_options(cells_per_thread=c, fmad=False)
+            d = s.run(4, log=['membrane.V'], log_interval=1)
+            res.append((dict((k, np.array(v)) for k, v in d.items()),
+                        s.state_array()))
+        for k in res[0][0]:
+            assert np.array_equal(res[0][0][k], res[1][0][k])
+        assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_stencil_only_model_vs_oracle():
+    # The stencil-only variant used for the HBM roofline measurement (tiny
+    # model, default vector path) against the oracle.
+    from myokit_b200 import workloads as wl
+    a = wl.stencil_only(myokit_b200.SimulationCUDA, 64, 20, precision=DP)
+    assert a.kernel_source().cells_per_thread == 2
+    b = wl.stencil_only(OracleSimulation, 64, 20, precision=DP)
+    d = a.run(4, log=['engine.time', 'membrane.V'], log_interval=0.5)
+    ol, ostate = b.run(4, log=['engine.time', 'membrane.V'], log_interval=0.5)
+    cl = dict((k, np.asarray(v)) for k, v in d.items())
+    assert cl['0.0.membrane.V'].max() > -79
+    assert max_abs_diff(cl, ol) <= 1e-9
+    assert np.max(np.abs(a.state_array() - ostate)) <= 1e-9
+
+
 def test_graph_replay_equals_single_launches():
     # Batches of 64 plain steps are replayed as CUDA graphs; logging steps and
     # remainders are single launches. Same kernels, same order: same bits.
