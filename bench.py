@@ -208,6 +208,17 @@ def run_reference(args, rank, world):
     print(json.dumps(out))
 
 
+FP64_INSTR_PER_CELL_STEP = 2523      # DFMA + DMUL + DADD + DSETP, ncu r01
+FP64_PEAK_GINSTR_S = 17105.3         # mkb_measure_peaks, r01
+
+
+def fp64_pipe(cells_per_launch, kernel_ms):
+    achieved = FP64_INSTR_PER_CELL_STEP * cells_per_launch / (kernel_ms * 1e-3) / 1e9
+    return {'achieved_ginstr_s': achieved, 'peak_ginstr_s': FP64_PEAK_GINSTR_S,
+            'frac': achieved / FP64_PEAK_GINSTR_S,
+            'instr_per_cell_step': FP64_INSTR_PER_CELL_STEP}
+
+
 def workload_config(args, cpu=False):
     n = args.cpu_grid if cpu else args.grid
     return {
@@ -347,8 +358,13 @@ def run_ours(args, rank, world):
             'kernel': 'mkb_cell_step',
             'algorithmic_bytes_per_cell_step': alg_bytes,
             'note': ('fused stencil + cell update; the cell update is FP64-'
-                     'pipe-bound, so the HBM fraction is not expected near 1 '
-                     '(DESIGN.md, kernel table)'),
+                     'pipe- and issue-bound, so the HBM fraction is not '
+                     'expected near 1 (DESIGN.md §4.1)'),
+            # The binding ceiling: FP64-pipe instructions per cell-step of
+            # this kernel (ncu, profiles/r01_opmix_c3.txt) against the FP64
+            # FMA issue rate measured by mkb_measure_peaks on this pool
+            # (profiles/r01_pipe_peaks.json).
+            'fp64_pipe': fp64_pipe(n * n / world, kernel_ms),
         },
         'cpu_baseline': cpu,
     }

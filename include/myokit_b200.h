@@ -232,6 +232,12 @@ int mkb_sim_halo_connect(mkb_sim* sim, const void* lower, const void* upper, int
  * current state to the neighbours again. mkb_sim_halo_connect includes it. */
 int mkb_sim_halo_seed(mkb_sim* sim);
 
+/* ---- roofline denominators ----
+ * Micro-benchmarks of the pipes the cell step is bound by. out6: fp64 FMA
+ * Ginstr/s (thread-level), fp32 FMA Ginstr/s, MUFU.EX2 Gop/s, device copy GB/s
+ * (read + write), SM clock MHz (driver attribute), SM count. */
+int mkb_measure_peaks(int device, double* out6);
+
 /* ---- pacing alone (unit tests; mirrors tests/ansic_event_based_pacing.c) ---- */
 int mkb_pacing_probe(double t0, int n_events, const double* events,
                      int n_times, const double* times,

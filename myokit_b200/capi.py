@@ -33,7 +33,7 @@ SYMBOLS = [
     'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
     'mkb_sim_reset_counters', 'mkb_sim_clean', 'mkb_sim_halo_info',
     'mkb_sim_halo_export', 'mkb_sim_halo_connect', 'mkb_sim_halo_seed',
-    'mkb_sim_rearm',
+    'mkb_sim_rearm', 'mkb_measure_peaks',
     'mkb_pacing_probe',
 ]
 
@@ -176,6 +176,19 @@ def jit_compile(source, options=()):
     data = ctypes.string_at(cubin.value, size.value)
     lib.mkb_free(cubin)
     return data, logtext
+
+
+def measure_peaks(device=0):
+    """Pipe and copy peaks measured on the device (see the C header)."""
+    out = (ctypes.c_double * 6)()
+    lib = library()
+    lib.mkb_measure_peaks.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    check(lib.mkb_measure_peaks(device, out))
+    return {
+        'fp64_fma_ginstr_s': out[0], 'fp32_fma_ginstr_s': out[1],
+        'mufu_ex2_gop_s': out[2], 'copy_gb_s': out[3],
+        'sm_clock_mhz': out[4], 'sm_count': int(out[5]),
+    }
 
 
 def device_count():

@@ -1525,3 +1525,103 @@ extern "C" int mkb_sim_halo_connect(mkb_sim* s, const void* lower, const void* u
 }
 
 extern "C" void mkb_sim_clean(mkb_sim* s) { sim_destroy(s); }
+
+// ---------------------------------------------------------------------------
+// Pipe micro-benchmarks: the denominators of the compute rooflines
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_peak_fma(T* out, int iters, T a, T b) {
+    // 8 independent chains per thread: enough ILP to saturate the pipe at
+    // full occupancy
+    T x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    T x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+            x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+__global__ void __launch_bounds__(256) k_peak_mufu(float* out, int iters, float a) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 0.1f, x2 = x0 + 0.2f, x3 = x0 + 0.3f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x0));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x1));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x2));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x3));
+        }
+        x0 *= a; x1 *= a; x2 *= a; x3 *= a;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3;
+}
+
+__global__ void __launch_bounds__(256) k_peak_copy(const float4* __restrict__ in,
+                                                   float4* __restrict__ out, u64 n) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    const u64 step = (u64)gridDim.x * blockDim.x;
+    for (; i + 3 * step < n; i += 4 * step) {
+        float4 a = in[i], b = in[i + step], c = in[i + 2 * step], d = in[i + 3 * step];
+        out[i] = a; out[i + step] = b; out[i + 2 * step] = c; out[i + 3 * step] = d;
+    }
+    for (; i < n; i += step) out[i] = in[i];
+}
+
+// Fills out[0..5]: fp64 FMA Ginstr/s (thread-level), fp32 FMA Ginstr/s, MUFU.EX2
+// Gop/s, copy GB/s (read + write), SM clock MHz seen by the driver, SM count.
+extern "C" int mkb_measure_peaks(int device, double* out6) {
+    if (!out6) return fail(MKB_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    const int blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    void* buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, (size_t)blocks * 256 * 8));
+    float ms = 0;
+    auto timed = [&](auto launch) -> double {
+        double best = 1e30;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            launch();
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        return best;
+    };
+    const int iters = 4096;
+    const double fma_per_thread = (double)iters * 64;
+    double t = timed([&] { k_peak_fma<double><<<blocks, 256>>>((double*)buf, iters, 1.0000001, 1e-9); });
+    out6[0] = fma_per_thread * blocks * 256 / (t * 1e-3) / 1e9;
+    t = timed([&] { k_peak_fma<float><<<blocks, 256>>>((float*)buf, iters, 1.0000001f, 1e-9f); });
+    out6[1] = fma_per_thread * blocks * 256 / (t * 1e-3) / 1e9;
+    t = timed([&] { k_peak_mufu<<<blocks, 256>>>((float*)buf, iters, 0.5f); });
+    out6[2] = (double)iters * 32 * blocks * 256 / (t * 1e-3) / 1e9;
+    cudaFree(buf);
+    const u64 nbytes = 2ull << 30;
+    void *a = nullptr, *b = nullptr;
+    CUDA_TRY(cudaMalloc(&a, nbytes));
+    CUDA_TRY(cudaMalloc(&b, nbytes));
+    CUDA_TRY(cudaMemset(a, 1, nbytes));
+    t = timed([&] { k_peak_copy<<<sms * 16, 256>>>((const float4*)a, (float4*)b, nbytes / 16); });
+    out6[3] = 2.0 * nbytes / (t * 1e-3) / 1e9;
+    cudaFree(a);
+    cudaFree(b);
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    out6[4] = khz / 1000.0;
+    out6[5] = sms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_TRY(cudaGetLastError());
+    return MKB_OK;
+}

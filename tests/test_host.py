@@ -446,3 +446,27 @@ def test_no_gpu_means_loud_failure_not_fallback():
                     text = f.read()
                 assert 'import oracle' not in text
                 assert 'from oracle' not in text
+
+
+def test_cuda_info_class(tmp_path, monkeypatch):
+    from myokit_b200 import CUDA
+    from myokit_b200 import cuda as cuda_mod
+    assert CUDA.supported() == HAS_GPU
+    assert isinstance(CUDA.info(formatted=True), str)
+    assert len(CUDA.available()) == capi.device_count()
+    monkeypatch.setattr(cuda_mod.CUDA, '_path',
+                        staticmethod(lambda: str(tmp_path / 'sel.ini')))
+    monkeypatch.delenv('MYOKIT_CUDA_DEVICE', raising=False)
+    assert CUDA.load_selection() == 0
+    CUDA.save_selection(3)
+    assert CUDA.load_selection() == 3
+    monkeypatch.setenv('MYOKIT_CUDA_DEVICE', '1')
+    assert CUDA.load_selection() == 1
+    monkeypatch.delenv('MYOKIT_CUDA_DEVICE')
+    CUDA.save_selection(None)
+    assert CUDA.load_selection() == 0
+    assert cuda_mod.bytesize(2048) == '2 KB'
+    assert cuda_mod.clockspeed(1.965e9) == '1.965 GHz'
+    if not HAS_GPU:
+        with pytest.raises(myokit_b200.NoCUDAError):
+            CUDA.current_info()
