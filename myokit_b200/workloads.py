@@ -122,6 +122,51 @@ def stencil_only(sim_class, nx, ny=None, precision=None, hetero=False, **kw):
     return s
 
 
+def fibre_mesh(nx=256, ny=128, nz=128, g_long=10.0, g_trans=2.0,
+               extra=0.01, seed=7):
+    """
+    Edge list of C5-ii: an ``nx * ny * nz`` lattice flattened
+    to 1-d cell ids (x fastest) with 6-neighbour edges, ``g_long`` along x and
+    ``g_trans`` across, plus ``extra`` (fraction of cells) random long-range
+    edges. Returns ``(n_cells, (i, j, g))`` with ``i < j``, no duplicates.
+    """
+    n = nx * ny * nz
+    ids = np.arange(n, dtype=np.int64).reshape(nz, ny, nx)
+    parts = []
+    for a, b, g in ((ids[:, :, :-1], ids[:, :, 1:], g_long),
+                    (ids[:, :-1, :], ids[:, 1:, :], g_trans),
+                    (ids[:-1, :, :], ids[1:, :, :], g_trans)):
+        parts.append((a.ravel(), b.ravel(), np.full(a.size, float(g))))
+    rng = np.random.default_rng(seed)
+    k = int(extra * n)
+    if k:
+        a = rng.integers(0, n, size=k)
+        b = rng.integers(0, n, size=k)
+        keep = np.abs(a - b) > nx * ny      # never a lattice neighbour
+        a, b = a[keep], b[keep]
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        _, first = np.unique(lo * n + hi, return_index=True)
+        parts.append((lo[first], hi[first], np.full(len(first), 0.5)))
+    i = np.concatenate([p[0] for p in parts])
+    j = np.concatenate([p[1] for p in parts])
+    g = np.concatenate([p[2] for p in parts])
+    return n, (i, j, g)
+
+
+def c5_mesh(sim_class, nx=256, ny=128, nz=128, precision=None, **kw):
+    """C5-ii: LR1991 on the fibre mesh through set_connections (one GPU)."""
+    if precision is None:
+        precision = myokit.SINGLE_PRECISION
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)
+    n, edges = fibre_mesh(nx, ny, nz)
+    s = sim_class(m, p, ncells=n, precision=precision, **kw)
+    s.set_connections(edges)
+    s.set_paced_cells(nx)       # the first row of the first plane
+    s.set_step_size(0.005)
+    return s
+
+
 # Algorithmic bytes per cell-step, SURVEY.md §8(d) / BASELINE.md §3:
 # B = (2 * n_state + n_field + n_gfield + 1) * sizeof(Real)
 def algorithmic_bytes(n_state, n_field, n_gfield, real_size):

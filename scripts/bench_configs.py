@@ -47,6 +47,11 @@ if 'stencil' in which:
     ms = info['device_ms'] / info['steps']
     gbs = 4 * 4 * info['cells'] / ms / 1e6
     print('stencil-only 8192^2 fp32 hetero           %8.4f ms/step  %7.1f GB/s  (%.1f%% of 6392.8)' % (ms, gbs, 100 * gbs / 6392.8))
+if 'mesh' in which:
+    t0 = time.time()
+    s = workloads.c5_mesh(S)
+    print('mesh built in %.1f s: %d cells, %d edges' % (time.time() - t0, s._nx, len(s._connections[0])))
+    report('C5-ii LR91 fp32 4.2M-node fibre mesh', s, 100, warmup=5)
 if 'c5' in which:
     m = workloads.data_model('decker-2009.mmt')
     p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)

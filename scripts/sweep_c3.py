@@ -9,17 +9,14 @@ grid = int(os.environ.get('SWEEP_GRID', '2048'))
 steps = int(os.environ.get('SWEEP_STEPS', '20'))
 variants = [
     ('default', dict()),
-    ('la64', dict(load_ahead=64)),
-    ('la1000', dict(load_ahead=1000)),
-    ('b128x2', dict(block=(128, 2))),
-    ('b32x8', dict(block=(32, 8))),
-    ('b256x1', dict(block=(256, 1))),
-    ('mb3', dict(min_blocks=3)),
-    ('b32x4 mb4', dict(block=(32, 4), min_blocks=4)),
+    ('b64x3 mb3', dict(block=(64, 3), min_blocks=3)),
+    ('b64x2 mb5', dict(block=(64, 2), min_blocks=5)),
     ('b64x2 mb4', dict(block=(64, 2), min_blocks=4)),
+    ('b64x2 mb6', dict(block=(64, 2), min_blocks=6)),
+    ('b64x3 mb3 la16', dict(block=(64, 3), min_blocks=3, load_ahead=16)),
+    ('b64x2 mb5 la16', dict(block=(64, 2), min_blocks=5, load_ahead=16)),
+    ('b64x5 mb1', dict(block=(64, 5), min_blocks=1)),
     ('b64x6 mb1', dict(block=(64, 6), min_blocks=1)),
-    ('nopool', dict(const_pool=False)),
-    ('libdevice exp', dict(fast_exp=False)),
 ]
 only = os.environ.get('SWEEP_ONLY')
 gpu = capi.device_count() > 0

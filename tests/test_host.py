@@ -302,6 +302,33 @@ def test_connections_validation():
         s2.set_connections([(0, 1, 1)])
 
 
+def test_connections_as_arrays():
+    m = br()
+    s = myokit_b200.SimulationCUDA(m, ncells=6)
+    i = np.array([0, 2, 5])
+    j = np.array([1, 1, 0])
+    g = np.array([1.0, 0.5, 2.0])
+    s.set_connections((i, j, g))
+    assert s.neighbors(1) == [0, 2] and s.neighbors(0) == [1, 5]
+    s.set_connections(np.stack([i, j, g], axis=1))
+    assert s.neighbors(5) == [0]
+    for bad_i, bad_j, bad_g, msg in (
+            ([0], [0], [1.0], 'Invalid connection'),
+            ([0], [6], [1.0], 'Invalid connection'),
+            ([-1], [2], [1.0], 'Invalid connection'),
+            ([0, 1], [1, 0], [1.0, 1.0], 'Duplicate connection'),
+            ([0], [1], [-1.0], 'Invalid conductance')):
+        with pytest.raises(ValueError, match=msg):
+            s.set_connections((np.array(bad_i), np.array(bad_j),
+                               np.array(bad_g)))
+    n, (ei, ej, eg) = workloads.fibre_mesh(8, 4, 3, extra=0.2)
+    lattice = 7 * 4 * 3 + 8 * 3 * 3 + 8 * 4 * 2
+    assert n == 96 and lattice <= len(ei) <= lattice + 19
+    assert np.all(ei < ej) and len(np.unique(ei * n + ej)) == len(ei)
+    big = myokit_b200.SimulationCUDA(m, ncells=n)
+    big.set_connections((ei, ej, eg))
+
+
 def test_diffusion_disabled_methods_raise():
     m = br()
     s = myokit_b200.SimulationCUDA(m, ncells=4, diffusion=False)
