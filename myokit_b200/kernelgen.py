@@ -179,7 +179,7 @@ class _ExpMixin:
 
     def _ex_exp(self, e):
         if self._fast_exp and not self._sp:
-            return self._ex_function(e, 'mkb_exp')
+            return self._ex_function(e, self._fast_exp)
         return super()._ex_exp(e)
 
 
@@ -260,8 +260,16 @@ __device__ __forceinline__ double mkb_div(double a, double b) {
     double q = a * r;
     const double d = fma(-b, q, a);
     const double q2 = fma(d, r, q);
-    // keep 0/inf/NaN results of a * r (d is NaN there)
-    return (d == d) ? q2 : q;
+    // Divisor 0 / inf / NaN (exponent field all zeros or all ones; tested on
+    // the integer pipe) or a non-finite dividend: the refinement produced
+    // NaNs, the plain product a * r is the IEEE answer.
+#if MKB_DIV_INT_CHECK
+    const unsigned int eb = ((unsigned int)__double2hiint(b) << 1) + 0x00200000u;
+    const unsigned int ea = ((unsigned int)__double2hiint(a) << 1) + 0x00200000u;
+    return (eb < 0x00400000u || ea < 0x00200000u) ? q : q2;
+#else
+    return (d == d) ? q2 : q;       // the same test on the FP64 pipe
+#endif
 }
 __device__ __forceinline__ float mkb_div(float a, float b) {
     return __fdividef(a, b);
@@ -279,7 +287,7 @@ __device__ __forceinline__ float mkb_div(float a, float b) {
 __constant__ double mkb_exp_c[14] = {
 @EXP_TABLE@
 };
-__device__ __forceinline__ double mkb_exp(double x) {
+__device__ __forceinline__ double mkb_exp_poly(double x) {
     double t = fma(x, mkb_exp_c[0], mkb_exp_c[1]);
     const int n = __double2loint(t);
     t -= mkb_exp_c[1];
@@ -293,6 +301,33 @@ __device__ __forceinline__ double mkb_exp(double x) {
     const int nc = min(max(n, -1021), 1024);
     const double y = __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
     return y;
+}
+
+// Table variant (option fast_exp = 'table', the default): exp(x) = 2^m T[j] e^r
+// with n = rint(64 x / ln2) = 64 m + j and |r| <= ln2 / 128, so e^r - 1 needs
+// only a degree-5 polynomial: 10 FP64-pipe instructions instead of 17, plus
+// one cached 8-byte table load. Max error 1.0 ulp (scripts/gen_exp_coeffs.py).
+// Same saturation behaviour as mkb_exp_poly.
+__device__ const double mkb_exp_t[64] = {
+@EXP_POW2@
+};
+__constant__ double mkb_expt_c[8] = {
+@EXP_TCOEF@
+};
+__device__ __forceinline__ double mkb_exp_tab(double x) {
+    double t = fma(x, mkb_expt_c[0], mkb_expt_c[1]);
+    const int n = __double2loint(t);
+    t -= mkb_expt_c[1];
+    double r = fma(t, mkb_expt_c[2], x);
+    r = fma(t, mkb_expt_c[3], r);
+    double p = fma(mkb_expt_c[4], r, mkb_expt_c[5]);
+    p = fma(p, r, mkb_expt_c[6]);
+    p = fma(p, r, mkb_expt_c[7]);
+    p = fma(r * r, p, r);
+    const int nc = min(max(n, -1021 * 64), 1024 * 64);
+    const double tj = __ldg(&mkb_exp_t[nc & 63]);
+    const double y = fma(tj, p, tj);
+    return __hiloint2double(__double2hiint(y) + ((nc >> 6) << 20), __double2loint(y));
 }
 """
 
@@ -350,6 +385,36 @@ _EXP_COEFFS = [
     '0x1.111111110f21ep-7', '0x1.555555554f0bap-5', '0x1.555555555555ap-3',
     '0x1.0000000000011p-1',
 ]
+# 2^(j/64), j = 0..63, correctly rounded (scripts/gen_exp_coeffs.py)
+_EXP_POW2 = [
+    '0x1.0000000000000p+0', '0x1.02c9a3e778061p+0', '0x1.059b0d3158574p+0', '0x1.0874518759bc8p+0',
+    '0x1.0b5586cf9890fp+0', '0x1.0e3ec32d3d1a2p+0', '0x1.11301d0125b51p+0', '0x1.1429aaea92de0p+0',
+    '0x1.172b83c7d517bp+0', '0x1.1a35beb6fcb75p+0', '0x1.1d4873168b9aap+0', '0x1.2063b88628cd6p+0',
+    '0x1.2387a6e756238p+0', '0x1.26b4565e27cddp+0', '0x1.29e9df51fdee1p+0', '0x1.2d285a6e4030bp+0',
+    '0x1.306fe0a31b715p+0', '0x1.33c08b26416ffp+0', '0x1.371a7373aa9cbp+0', '0x1.3a7db34e59ff7p+0',
+    '0x1.3dea64c123422p+0', '0x1.4160a21f72e2ap+0', '0x1.44e086061892dp+0', '0x1.486a2b5c13cd0p+0',
+    '0x1.4bfdad5362a27p+0', '0x1.4f9b2769d2ca7p+0', '0x1.5342b569d4f82p+0', '0x1.56f4736b527dap+0',
+    '0x1.5ab07dd485429p+0', '0x1.5e76f15ad2148p+0', '0x1.6247eb03a5585p+0', '0x1.6623882552225p+0',
+    '0x1.6a09e667f3bcdp+0', '0x1.6dfb23c651a2fp+0', '0x1.71f75e8ec5f74p+0', '0x1.75feb564267c9p+0',
+    '0x1.7a11473eb0187p+0', '0x1.7e2f336cf4e62p+0', '0x1.82589994cce13p+0', '0x1.868d99b4492edp+0',
+    '0x1.8ace5422aa0dbp+0', '0x1.8f1ae99157736p+0', '0x1.93737b0cdc5e5p+0', '0x1.97d829fde4e50p+0',
+    '0x1.9c49182a3f090p+0', '0x1.a0c667b5de565p+0', '0x1.a5503b23e255dp+0', '0x1.a9e6b5579fdbfp+0',
+    '0x1.ae89f995ad3adp+0', '0x1.b33a2b84f15fbp+0', '0x1.b7f76f2fb5e47p+0', '0x1.bcc1e904bc1d2p+0',
+    '0x1.c199bdd85529cp+0', '0x1.c67f12e57d14bp+0', '0x1.cb720dcef9069p+0', '0x1.d072d4a07897cp+0',
+    '0x1.d5818dcfba487p+0', '0x1.da9e603db3285p+0', '0x1.dfc97337b9b5fp+0', '0x1.e502ee78b3ff6p+0',
+    '0x1.ea4afa2a490dap+0', '0x1.efa1bee615a27p+0', '0x1.f50765b6e4540p+0', '0x1.fa7c1819e90d8p+0',
+]
+# Table variant: 64 / ln2, -ln2/64 (hi, lo), q3..q0 of (e^r - 1 - r) / r^2
+_EXP_TCOEF = [
+    ('0x1.71547652b82fep+6', '64 / ln2'),
+    ('0x1.8p+52', '1.5 * 2^52'),
+    ('-0x1.62e42fefa39efp-7', '-ln2 / 64, high part'),
+    ('-0x1.abc9e3b39803fp-62', '-ln2 / 64, low part'),
+    ('0x1.11111d90623e3p-7', 'q3'),
+    ('0x1.55556b342389bp-5', 'q2'),
+    ('0x1.5555555555255p-3', 'q1'),
+    ('0x1.ffffffffff57dp-2', 'q0'),
+]
 _EXP_TABLE = [
     ('0x1.71547652b82fep+0', 'log2(e)'),
     ('0x1.8p+52', '1.5 * 2^52: round-to-nearest-integer shift'),
@@ -358,6 +423,10 @@ _EXP_TABLE = [
 ] + [(c, 'c%d' % (11 - i)) for i, c in enumerate(_EXP_COEFFS)]
 _PRELUDE = _PRELUDE.replace('@EXP_TABLE@', '\n'.join(
     '    %r,  // %s' % (float.fromhex(h), name) for h, name in _EXP_TABLE))
+_PRELUDE = _PRELUDE.replace('@EXP_TCOEF@', '\n'.join(
+    '    %r,  // %s' % (float.fromhex(h), name) for h, name in _EXP_TCOEF))
+_PRELUDE = _PRELUDE.replace('@EXP_POW2@', '\n'.join(
+    '    %r,' % float.fromhex(h) for h in _EXP_POW2))
 
 
 def default_block(nx, ny, precision):
@@ -417,7 +486,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              max_registers=None, pow_multiply=True, fast_div=False,
              lazy_state=True, min_blocks=None, fast_exp=False,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
-             rows_per_thread=1):
+             rows_per_thread=1, div_int_check=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -462,7 +531,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     else:
         w = _Writer(precision)
         w._fast_div = bool(fast_div)
-        w._fast_exp = bool(fast_exp)
+        w._fast_exp = ({'table': 'mkb_exp_tab', 'poly': 'mkb_exp_poly'}.get(
+            fast_exp, 'mkb_exp_tab') if fast_exp else False)
         if const_pool and not sp:
             w.enable_pool()
     w._pow_multiply = bool(pow_multiply)
@@ -548,7 +618,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     vm = model.label('membrane_potential') if diffusion else None
     i_vm = vm.index() if vm is not None else -1
     real = 'float' if sp else 'double'
-    exp = 'expf' if sp else ('mkb_exp' if fast_exp else 'exp')
+    exp = 'expf' if sp else (w._fast_exp if fast_exp else 'exp')
     if native_maths and sp:
         exp = '__expf'
     states = list(model.states())
@@ -730,6 +800,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_BY %d' % by)
         q('#define MKB_CPT %d' % cpt)
         q('#define MKB_RPT %d' % rpt)
+        q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
         q(_PRELUDE)
         q(_VECTOR_PRELUDE)
         if pooled and w._pool:
@@ -955,6 +1026,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('typedef %s Real;' % real)
     p('#define MKB_BX %d' % bx)
     p('#define MKB_BY %d' % by)
+    p('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
     p(_PRELUDE)
     if pooled and w._pool:
         p('// Model constants (double precision), in order of first use')

@@ -84,3 +84,58 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+# ---------------------------------------------------------------------------
+# Table variant (mkb_exp in the shipped prelude): exp(x) = 2^m * T[j] * e^r,
+# n = rint(x * 64 / ln2) = 64 m + j, r = x - n ln2 / 64, |r| <= ln2 / 128,
+# e^r - 1 by a degree-5 polynomial: 10 FP64-pipe instructions instead of 17.
+# ---------------------------------------------------------------------------
+def table_variant():
+    N = 64
+    T = [rd(mp.mpf(2) ** (mp.mpf(j) / N)) for j in range(N)]
+    K = rd(N / mp.log(2))
+    C_HI = rd(mp.log(2) / N)
+    C_LO = rd(mp.log(2) / N - C_HI)
+    # q(r) ~ (e^r - 1 - r) / r^2 on |r| <= ln2/128, degree 3
+    a = mp.log(2) / (2 * N) * mp.mpf('1.0001')
+
+    def f(x):
+        if x == 0:
+            return mp.mpf(1) / 2
+        return (mp.exp(x) - 1 - x) / (x * x)
+    q = [rd(c) for c in cheb_coeffs(f, a, 3)]
+
+    def mkb_exp_t(x):
+        x = rd(x)
+        n = mp.nint(rd(x * K))
+        r = fma(n, -C_HI, x)
+        r = fma(n, -C_LO, r)
+        p = fma(q[3], r, q[2])
+        p = fma(p, r, q[1])
+        p = fma(p, r, q[0])
+        r2 = rd(r * r)
+        p = fma(r2, p, r)
+        j = int(n) % N
+        m = (int(n) - j) // N
+        y = fma(T[j], p, T[j])
+        return rd(y * mp.mpf(2) ** m)
+
+    print('table variant: K =', float(K).hex(), 'C_HI =', float(C_HI).hex(),
+          'C_LO =', float(C_LO).hex())
+    print('q0..q3 =', [float(c).hex() for c in q])
+    random.seed(2)
+    worst = 0
+    for i in range(20000):
+        x = random.uniform(-700, 700) if i % 2 else random.uniform(-5, 5)
+        got = mkb_exp_t(x)
+        want = mp.exp(rd(x))
+        ulp = mp.mpf(2) ** (mp.floor(mp.log(want, 2)) - 52)
+        worst = max(worst, abs(got - want) / ulp)
+    print('table variant, max error over 20000 random arguments: %.3f ulp'
+          % float(worst))
+    return T, K, C_HI, C_LO, q
+
+
+if __name__ == '__main__':
+    table_variant()

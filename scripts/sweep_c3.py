@@ -8,15 +8,10 @@ from myokit_b200 import workloads, capi
 grid = int(os.environ.get('SWEEP_GRID', '2048'))
 steps = int(os.environ.get('SWEEP_STEPS', '20'))
 variants = [
-    ('default', dict()),
-    ('b64x3 mb3', dict(block=(64, 3), min_blocks=3)),
-    ('b64x2 mb5', dict(block=(64, 2), min_blocks=5)),
-    ('b64x2 mb4', dict(block=(64, 2), min_blocks=4)),
-    ('b64x2 mb6', dict(block=(64, 2), min_blocks=6)),
-    ('b64x3 mb3 la16', dict(block=(64, 3), min_blocks=3, load_ahead=16)),
-    ('b64x2 mb5 la16', dict(block=(64, 2), min_blocks=5, load_ahead=16)),
-    ('b64x5 mb1', dict(block=(64, 5), min_blocks=1)),
-    ('b64x6 mb1', dict(block=(64, 6), min_blocks=1)),
+    ('exp table, div fp check', dict(fast_exp='table')),
+    ('exp table, div int check', dict(fast_exp='table', div_int_check=True)),
+    ('exp poly, div fp check', dict(fast_exp='poly')),
+    ('exp poly, div int check', dict(fast_exp='poly', div_int_check=True)),
 ]
 only = os.environ.get('SWEEP_ONLY')
 gpu = capi.device_count() > 0
