@@ -112,6 +112,9 @@ typedef struct mkb_sim_config {
     double gx, gy;
     const void* gx_field;       /* [ny][nx-1] */
     const void* gy_field;       /* [ny-1][nx], may be null when ny == 1 */
+    uint64_t n_ghost;           /* partitioned graphs: cells owned by other GPUs that
+                                   this partition's edges reach; an edge endpoint
+                                   conn_j >= nx names ghost cell conn_j - nx */
     uint64_t n_connections;     /* edges (i < j, g), openclsim.py:1405-1449 */
     const uint64_t* conn_i;
     const uint64_t* conn_j;
@@ -231,6 +234,27 @@ int mkb_sim_halo_connect(mkb_sim* sim, const void* lower, const void* upper, int
 /* After mkb_sim_rearm (and a barrier): delivers the boundary rows of the
  * current state to the neighbours again. mkb_sim_halo_connect includes it. */
 int mkb_sim_halo_seed(mkb_sim* sim);
+
+/* Partitioned connection graphs: a partition (contiguous cell ids, n_ghost > 0)
+ * owns an exchange block [ghost V: 3 x n_ghost][flags: one per rank]. Every
+ * step, after the step kernel, the owner of a cell pushes its new V into the
+ * ghost slots of the partitions that reference it and then raises its flag
+ * there; a partition's next step first waits for the flags of the ranks it
+ * imports from. Same handles and sequence as the row-slab calls above
+ * (mkb_sim_halo_export / this call instead of mkb_sim_halo_connect /
+ * mkb_sim_halo_seed after a re-arm). */
+typedef struct mkb_ghost_peer {
+    const void* handle;         /* peer's export: IPC handle, or pointer to its device pointer */
+    uint64_t peer_n_ghost;      /* the peer's n_ghost (layout of its block) */
+    uint32_t peer_n_flags;      /* the peer's flag count */
+    uint32_t flag_index;        /* which of the peer's flags this rank raises */
+    uint64_t n_export;          /* cells of this partition the peer needs */
+    const uint64_t* src_cell;   /* their local ids here */
+    const uint64_t* dst_slot;   /* their ghost slots there */
+} mkb_ghost_peer;
+int mkb_sim_ghost_connect(mkb_sim* sim, uint32_t n_flags, uint32_t n_peers,
+                          const mkb_ghost_peer* peers, int direct,
+                          uint32_t n_import, const uint32_t* import_flags);
 
 /* ---- roofline denominators ----
  * Micro-benchmarks of the pipes the cell step is bound by. out6: fp64 FMA

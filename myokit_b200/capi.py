@@ -33,7 +33,7 @@ SYMBOLS = [
     'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
     'mkb_sim_reset_counters', 'mkb_sim_clean', 'mkb_sim_halo_info',
     'mkb_sim_halo_export', 'mkb_sim_halo_connect', 'mkb_sim_halo_seed',
-    'mkb_sim_rearm', 'mkb_measure_peaks',
+    'mkb_sim_rearm', 'mkb_measure_peaks', 'mkb_sim_ghost_connect',
     'mkb_pacing_probe',
 ]
 
@@ -62,6 +62,7 @@ class SimConfig(ctypes.Structure):
         ('diffusion_mode', ctypes.c_int),
         ('gx', ctypes.c_double), ('gy', ctypes.c_double),
         ('gx_field', c_vp), ('gy_field', c_vp),
+        ('n_ghost', c_u64),
         ('n_connections', c_u64), ('conn_i', c_vp), ('conn_j', c_vp),
         ('conn_g', c_vp),
         ('pace_rect', ctypes.c_int),
@@ -85,6 +86,14 @@ class RunConfig(ctypes.Structure):
         ('n_events', ctypes.c_int), ('events', c_vp),
         ('n_log', c_u64), ('log_kind', c_vp), ('log_index', c_vp),
         ('steps_per_call', c_u64),
+    ]
+
+
+class GhostPeer(ctypes.Structure):
+    _fields_ = [
+        ('handle', c_vp), ('peer_n_ghost', c_u64),
+        ('peer_n_flags', ctypes.c_uint32), ('flag_index', ctypes.c_uint32),
+        ('n_export', c_u64), ('src_cell', c_vp), ('dst_slot', c_vp),
     ]
 
 
@@ -137,6 +146,9 @@ def library():
     lib.mkb_sim_halo_export.argtypes = [c_vp, c_vp, ctypes.POINTER(c_vp)]
     lib.mkb_sim_halo_connect.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int]
     lib.mkb_sim_halo_seed.argtypes = [c_vp]
+    lib.mkb_sim_ghost_connect.argtypes = [
+        c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(GhostPeer),
+        ctypes.c_int, ctypes.c_uint32, c_vp]
     lib.mkb_sim_rearm.argtypes = [c_vp, ctypes.POINTER(RunConfig)]
     lib.mkb_pacing_probe.argtypes = [
         ctypes.c_double, ctypes.c_int, c_vp, ctypes.c_int, c_vp, c_vp, c_vp]

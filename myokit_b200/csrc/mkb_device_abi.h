@@ -46,7 +46,12 @@ struct MkbGridArgs {
     /* connections as CSR over cells (deterministic gather) */
     const unsigned long long* csr_row;  /* [n+1] */
     const unsigned int* csr_col;        /* [nnz] */
-    const void* csr_g;                  /* Real[nnz], signed per CSR entry */
+    const void* csr_g;                  /* Real[nnz] */
+    /* Partitioned connection graphs (multi-GPU): CSR columns >= n are ghost
+     * cells owned by other GPUs; their V(t_step) sits in ghost[(step % 3) *
+     * n_ghost + (col - n)], pushed there by the owners (peer stores). */
+    const void* ghost;                  /* Real[3][n_ghost] or null */
+    unsigned long long n_ghost;
     /* Row-slab sharding (multi-GPU), all null on a single GPU.
      * halo_lo / halo_hi: THIS GPU's ghost rows, Real[3][nx] each (slot =
      *   step % 3): V(t_step) of global row iy_offset-1 / iy_offset+ny,

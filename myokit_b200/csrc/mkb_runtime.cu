@@ -132,6 +132,41 @@ __global__ void k_fill_u32(unsigned int* p, u64 n, unsigned int value) {
     if (i < n) p[i] = value;
 }
 
+// --- partitioned connection graphs ---------------------------------------
+// One thread waits until every listed flag has reached `step`.
+__global__ void k_wait_flags(const unsigned int* flags, const unsigned int* which, unsigned int n,
+                             unsigned int step, unsigned int* error) {
+    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
+        const volatile unsigned int* f = flags + which[k];
+        unsigned int spins = 0;
+        while (*f < step) {
+            __nanosleep(spins < 64 ? 20 : 200);
+            if (++spins > 50000000u) {
+                atomicExch(error, 1u);
+                break;
+            }
+        }
+    }
+    __threadfence();
+}
+
+// dst[slot[e]] = v[src[e]]: this partition's cells into a peer's ghost slots.
+template <typename TR>
+__global__ void k_push_ghosts(const TR* __restrict__ v, const u64* __restrict__ src,
+                              const u64* __restrict__ slot, u64 n, TR* dst) {
+    u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    for (; e < n; e += (u64)gridDim.x * blockDim.x) dst[slot[e]] = v[src[e]];
+}
+
+// Runs after the pushes (stream order = they have completed): raise this
+// rank's flag on every peer.
+__global__ void k_raise_flags(unsigned int* const* flags, unsigned int n, unsigned int value) {
+    __threadfence_system();
+    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
+        *((volatile unsigned int*)flags[k]) = value;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Library-level API
 // ---------------------------------------------------------------------------
@@ -343,6 +378,24 @@ struct mkb_sim {
     bool has_lo = false, has_hi = false;
     u64 step_index = 0;                 // steps taken in this run (1-based in the kernel)
 
+    // partitioned connection graphs: ghost cells (multi-GPU)
+    u64 n_ghost = 0;
+    unsigned int n_flags = 0;           // flags in this partition's block (one per rank)
+    struct GhostPeerRt {
+        void* base = nullptr;           // peer's exchange block as mapped here
+        bool ipc = false;
+        u64 peer_n_ghost = 0;
+        u64 n_export = 0;
+        u64* d_src = nullptr;           // local cells to send
+        u64* d_dst = nullptr;           // ghost slots on the peer
+        unsigned int* flag = nullptr;   // the flag this rank raises on the peer
+    };
+    std::vector<GhostPeerRt> gpeers;
+    unsigned int** d_peer_flags = nullptr;  // device array of the peers' flag pointers
+    unsigned int* d_import = nullptr;       // indices of own flags to wait for
+    unsigned int n_import = 0;
+    bool ghosts_connected = false;
+
     // counters
     u64 launches = 0, steps = 0;
     double device_ms = 0;
@@ -380,6 +433,13 @@ static void sim_destroy(mkb_sim* s) {
         cudaFree(gs.d_params);
         if (gs.done) cudaEventDestroy(gs.done);
     }
+    for (auto& gp : s->gpeers) {
+        cudaFree(gp.d_src);
+        cudaFree(gp.d_dst);
+        if (gp.base && gp.ipc) cudaIpcCloseMemHandle(gp.base);
+    }
+    cudaFree(s->d_peer_flags);
+    cudaFree(s->d_import);
     if (s->peer_lo_base && s->peer_lo_ipc) cudaIpcCloseMemHandle(s->peer_lo_base);
     if (s->peer_hi_base && s->peer_hi_ipc) cudaIpcCloseMemHandle(s->peer_hi_base);
     cudaFree(s->d_xchg);
@@ -549,13 +609,17 @@ static int sim_init_typed(mkb_sim* s, const mkb_sim_config* c) {
     if (s->diff_mode == MKB_DIFF_CONNECTIONS) {
         const u64 ne = c->n_connections;
         std::vector<u64> row(s->n + 1, 0);
+        // An endpoint j >= n is a ghost cell (owned by another partition): the
+        // edge then only contributes to the row of its local endpoint i.
+        const u64 ntot = s->n + c->n_ghost;
+        if (ntot > 0xffffffffull) return fail(MKB_ERR_INVALID, "too many cells for 32-bit CSR columns");
         for (u64 e = 0; e < ne; e++) {
             u64 i = c->conn_i[e], j = c->conn_j[e];
-            if (i >= s->n || j >= s->n || i == j) {
+            if (i >= s->n || j >= ntot || i == j) {
                 return fail(MKB_ERR_INVALID, "invalid connection %llu: (%llu, %llu)", e, i, j);
             }
             row[i + 1]++;
-            row[j + 1]++;
+            if (j < s->n) row[j + 1]++;
         }
         for (u64 i = 0; i < s->n; i++) row[i + 1] += row[i];
         std::vector<unsigned int> col(2 * ne + 1);
@@ -566,8 +630,10 @@ static int sim_init_typed(mkb_sim* s, const mkb_sim_config* c) {
             TR ge = host_double ? (TR)((const double*)c->conn_g)[e] : ((const TR*)c->conn_g)[e];
             col[fill[i]] = (unsigned int)j;
             g[fill[i]++] = ge;
-            col[fill[j]] = (unsigned int)i;
-            g[fill[j]++] = ge;
+            if (j < s->n) {
+                col[fill[j]] = (unsigned int)i;
+                g[fill[j]++] = ge;
+            }
         }
         CUDA_TRY(cudaMalloc(&s->d_csr_row, (s->n + 1) * sizeof(u64)));
         CUDA_TRY(cudaMalloc(&s->d_csr_col, (2 * ne + 1) * sizeof(unsigned int)));
@@ -591,6 +657,9 @@ static int preload_kernels(mkb_sim* s) {
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)s->kern));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_log_gather<TR>));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_fill_u32));
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_wait_flags));
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_raise_flags));
+    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_push_ghosts<TR>));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_soa_to_aos<TR, TR>));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_soa_to_aos<TR, double>));
     return MKB_OK;
@@ -955,6 +1024,19 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
             INIT_CUDA(cudaMemsetAsync(s->d_xchg, 0, s->xchg_bytes, s->stream));
             g.halo_error = (unsigned int*)(s->d_xchg + 2 * halo + 2 * flags);
         }
+        g.ghost = nullptr;
+        g.n_ghost = 0;
+        if (s->diff_mode == MKB_DIFF_CONNECTIONS && c->n_ghost > 0) {
+            // Exchange block: [ghost V: 3 x n_ghost][error][flags, sized at connect]
+            s->n_ghost = c->n_ghost;
+            const size_t ghost_bytes = (3 * s->n_ghost * s->rs + 255) / 256 * 256;
+            s->xchg_bytes = ghost_bytes + 256 + 4096 * sizeof(unsigned int);
+            INIT_CUDA(cudaMalloc(&s->d_xchg, s->xchg_bytes));
+            INIT_CUDA(cudaMemsetAsync(s->d_xchg, 0, s->xchg_bytes, s->stream));
+            g.ghost = s->d_xchg;
+            g.n_ghost = s->n_ghost;
+            g.halo_error = (unsigned int*)(s->d_xchg + ghost_bytes);
+        }
     }
     g.nx = s->nx;
     g.ny = s->ny;
@@ -1088,6 +1170,29 @@ static int finalize_rows(mkb_sim* s) {
     return MKB_OK;
 }
 
+static size_t ghost_flags_offset(u64 n_ghost, size_t rs) {
+    return (3 * n_ghost * rs + 255) / 256 * 256 + 256;
+}
+
+// Pushes V(t) of the exported cells into the peers' slot for `step` and raises
+// the flags to `step` (seeding uses step = 1 with the current V plane).
+template <typename TR>
+static int ghost_push(mkb_sim* s, const TR* v, unsigned int step) {
+    for (auto& gp : s->gpeers) {
+        if (!gp.n_export) continue;
+        TR* dst = (TR*)gp.base + (u64)(step % 3) * gp.peer_n_ghost;
+        k_push_ghosts<TR><<<grid_for(gp.n_export), 256, 0, s->stream>>>(v, gp.d_src, gp.d_dst,
+                                                                         gp.n_export, dst);
+        s->launches++;
+    }
+    if (!s->gpeers.empty()) {
+        k_raise_flags<<<1, 64, 0, s->stream>>>(s->d_peer_flags, (unsigned int)s->gpeers.size(), step);
+        s->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return MKB_OK;
+}
+
 // Builds (once per slot and entry parity) the graph
 //   [H2D: staged step parameters -> device] -> step kernel x kGraphSteps
 // by stream capture. Each node has its parameter pointer and its V planes
@@ -1202,7 +1307,7 @@ static int sim_step_typed(mkb_sim* s) {
         s->ring_chunk++;
 
         for (size_t i = 0; i < s->recs.size(); i++) {
-            if (s->use_graphs && i + kGraphSteps <= s->recs.size()) {
+            if (s->use_graphs && !s->ghosts_connected && i + kGraphSteps <= s->recs.size()) {
                 bool plain = true;
                 for (int j = 0; j < kGraphSteps && plain; j++) plain = !s->recs[i + j].logging;
                 if (plain) {
@@ -1264,6 +1369,13 @@ static int sim_step_typed(mkb_sim* s) {
                                              cudaMemcpyDeviceToDevice, s->stream));
                 }
             }
+            if (s->n_import) {
+                // ghost V(t) of this step must have arrived from every exporter
+                k_wait_flags<<<1, 64, 0, s->stream>>>(
+                    (const unsigned int*)(s->d_xchg + ghost_flags_offset(s->n_ghost, s->rs)),
+                    s->d_import, s->n_import, rec.p.step, s->grid.halo_error);
+                s->launches++;
+            }
             // fused diffusion + cell step: states -> t + dt (openclsim.c:1066-1096)
             const MkbStepParams* sp = dring + i;
             void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
@@ -1272,6 +1384,11 @@ static int sim_step_typed(mkb_sim* s) {
             s->launches++;
             s->steps++;
             s->parity ^= 1;
+            if (!s->gpeers.empty()) {
+                // V(t + dt) of the exported cells -> the peers' slot for the next step
+                int prc = ghost_push<TR>(s, v_out, rec.p.step + 1u);
+                if (prc) return prc;
+            }
             if (rec.logging) {
                 if (dev_row && s->n_post) {
                     // idiff(t), intermediaries(t) (openclsim.c:1110-1119)
@@ -1322,7 +1439,10 @@ static int sim_step_typed(mkb_sim* s) {
 
 extern "C" int mkb_sim_step(mkb_sim* s, double* engine_time, int* halted) {
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
-    if (s->d_xchg && ((s->has_lo && !s->peer_lo_base) || (s->has_hi && !s->peer_hi_base))) {
+    if (s->n_ghost > 0 && !s->ghosts_connected) {
+        return fail(MKB_ERR_STATE, "Graph partition not connected to its peers (mkb_sim_ghost_connect).");
+    }
+    if (s->d_xchg && !s->n_ghost && ((s->has_lo && !s->peer_lo_base) || (s->has_hi && !s->peer_hi_base))) {
         return fail(MKB_ERR_STATE, "Row slab not connected to its neighbours (mkb_sim_halo_connect).");
     }
     CUDA_TRY(cudaSetDevice(s->device));
@@ -1411,6 +1531,77 @@ extern "C" int mkb_sim_halo_export(mkb_sim* s, void* ipc_handle_64, void** devic
 template <typename TR>
 static int halo_seed_typed(mkb_sim* s);
 
+// --- partitioned connection graphs (kernels are defined with the helpers above) ---
+extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_peers,
+                                     const mkb_ghost_peer* peers, int direct, uint32_t n_import,
+                                     const uint32_t* import_flags) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (s->diff_mode != MKB_DIFF_CONNECTIONS) return fail(MKB_ERR_STATE, "not a connection graph");
+    if (s->step_index != 0 || s->ghosts_connected) return fail(MKB_ERR_STATE, "ghost_connect must be called once, before the first step");
+    if (n_flags > 4096) return fail(MKB_ERR_INVALID, "too many ranks");
+    if ((n_peers && !peers) || (n_import && !import_flags)) return fail(MKB_ERR_INVALID, "null argument");
+    if ((n_import > 0 || s->n_ghost > 0) && !s->d_xchg) return fail(MKB_ERR_STATE, "no exchange block");
+    CUDA_TRY(cudaSetDevice(s->device));
+    s->n_flags = n_flags;
+    std::vector<unsigned int*> flag_ptrs;
+    for (uint32_t k = 0; k < n_peers; k++) {
+        const mkb_ghost_peer& in = peers[k];
+        mkb_sim::GhostPeerRt gp;
+        if (!in.handle) return fail(MKB_ERR_INVALID, "missing peer handle");
+        if (direct) {
+            void* ptr = *(void* const*)in.handle;
+            cudaPointerAttributes attr;
+            CUDA_TRY(cudaPointerGetAttributes(&attr, ptr));
+            if (attr.device != s->device) {
+                int can = 0;
+                CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, attr.device));
+                if (!can) return fail(MKB_ERR_CUDA, "GPU %d cannot access GPU %d", s->device, attr.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+                cudaGetLastError();
+            }
+            gp.base = ptr;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, in.handle, 64);
+            CUDA_TRY(cudaIpcOpenMemHandle(&gp.base, h, cudaIpcMemLazyEnablePeerAccess));
+            gp.ipc = true;
+        }
+        gp.peer_n_ghost = in.peer_n_ghost;
+        gp.n_export = in.n_export;
+        if (in.flag_index >= in.peer_n_flags) return fail(MKB_ERR_INVALID, "flag index out of range");
+        gp.flag = (unsigned int*)((char*)gp.base + ghost_flags_offset(in.peer_n_ghost, s->rs)) + in.flag_index;
+        if (gp.n_export) {
+            for (u64 e = 0; e < gp.n_export; e++) {
+                if (in.src_cell[e] >= s->n || in.dst_slot[e] >= in.peer_n_ghost) {
+                    return fail(MKB_ERR_INVALID, "export entry out of range");
+                }
+            }
+            CUDA_TRY(cudaMalloc(&gp.d_src, gp.n_export * sizeof(u64)));
+            CUDA_TRY(cudaMalloc(&gp.d_dst, gp.n_export * sizeof(u64)));
+            CUDA_TRY(cudaMemcpy(gp.d_src, in.src_cell, gp.n_export * sizeof(u64), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(gp.d_dst, in.dst_slot, gp.n_export * sizeof(u64), cudaMemcpyHostToDevice));
+        }
+        s->gpeers.push_back(gp);
+        flag_ptrs.push_back(gp.flag);
+    }
+    if (!flag_ptrs.empty()) {
+        CUDA_TRY(cudaMalloc(&s->d_peer_flags, flag_ptrs.size() * sizeof(unsigned int*)));
+        CUDA_TRY(cudaMemcpy(s->d_peer_flags, flag_ptrs.data(), flag_ptrs.size() * sizeof(unsigned int*),
+                            cudaMemcpyHostToDevice));
+    }
+    s->n_import = n_import;
+    if (n_import) {
+        for (uint32_t k = 0; k < n_import; k++) {
+            if (import_flags[k] >= n_flags) return fail(MKB_ERR_INVALID, "import flag out of range");
+        }
+        CUDA_TRY(cudaMalloc(&s->d_import, n_import * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemcpy(s->d_import, import_flags, n_import * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    }
+    s->ghosts_connected = true;
+    return mkb_sim_halo_seed(s);
+}
+
 extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
     if (!r) return fail(MKB_ERR_INVALID, "null argument");
@@ -1419,8 +1610,9 @@ extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
     if (rc) return rc;
     if (s->d_xchg) {
         // Arrival flags restart from zero; the caller barriers, then reseeds
-        const size_t halo = 3 * s->nx * s->rs;
-        CUDA_TRY(cudaMemsetAsync(s->d_xchg + 2 * halo, 0, s->xchg_bytes - 2 * halo, s->stream));
+        const size_t keep = s->n_ghost ? (3 * s->n_ghost * s->rs + 255) / 256 * 256
+                                       : 2 * 3 * s->nx * s->rs;
+        CUDA_TRY(cudaMemsetAsync(s->d_xchg + keep, 0, s->xchg_bytes - keep, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     }
     return MKB_OK;
@@ -1428,6 +1620,20 @@ extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
 
 extern "C" int mkb_sim_halo_seed(mkb_sim* s) {
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (s->ghosts_connected) {
+        if (s->step_index != 0) return fail(MKB_ERR_STATE, "halo_seed must precede the first step");
+        CUDA_TRY(cudaSetDevice(s->device));
+        const u64 vm = (u64)std::max(s->i_vm, 0);
+        int rc;
+        if (s->precision == MKB_DOUBLE) {
+            rc = ghost_push<double>(s, plane_ptr<double>(s, s->parity ? s->plane_alt_v : vm), 1u);
+        } else {
+            rc = ghost_push<float>(s, plane_ptr<float>(s, s->parity ? s->plane_alt_v : vm), 1u);
+        }
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return MKB_OK;
+    }
     if (!s->d_xchg) return MKB_OK;
     if (s->step_index != 0) return fail(MKB_ERR_STATE, "halo_seed must precede the first step");
     if ((s->has_lo && !s->peer_lo_base) || (s->has_hi && !s->peer_hi_base)) {

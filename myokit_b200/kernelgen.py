@@ -486,7 +486,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              max_registers=None, pow_multiply=True, fast_div=False,
              lazy_state=True, min_blocks=None, fast_exp=False,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
-             rows_per_thread=1, div_int_check=False):
+             rows_per_thread=1, div_int_check=False, partitioned=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -519,6 +519,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     ``rows_per_thread``
         With ``cells_per_thread`` > 1: each thread also walks that many rows
         (more bytes in flight per thread, fewer and fatter thread blocks).
+    ``partitioned``
+        Connection graphs cut over several GPUs: CSR columns beyond the local
+        cells are ghost cells whose V is read from the ghost buffer the
+        owning GPUs push into.
     ``slab``
         Row-slab variant for multi-GPU grids: boundary row blocks run first,
         wait for the neighbouring GPU's ghost row (arrival flags), and push
@@ -1174,9 +1178,18 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    {')
         p('        const Real* const cg = (const Real*)g.csr_g;')
         p('        const unsigned long long e1 = g.csr_row[cid + 1];')
-        p('        for (unsigned long long e = g.csr_row[cid]; e < e1; e++) {')
-        p('            idiff += cg[e] * (vc - v_in[g.csr_col[e]]);')
-        p('        }')
+        if partitioned:
+            p('        // columns >= nx are ghost cells: V(t) pushed here by their owners')
+            p('        const Real* const ghost = (const Real*)g.ghost + (unsigned long long)(sp->step % 3u) * g.n_ghost;')
+            p('        for (unsigned long long e = g.csr_row[cid]; e < e1; e++) {')
+            p('            const unsigned int col = g.csr_col[e];')
+            p('            const Real vn = (col < nx) ? v_in[col] : __ldcg(ghost + (col - nx));')
+            p('            idiff += cg[e] * (vc - vn);')
+            p('        }')
+        else:
+            p('        for (unsigned long long e = g.csr_row[cid]; e < e1; e++) {')
+            p('            idiff += cg[e] * (vc - v_in[g.csr_col[e]]);')
+            p('        }')
         p('    }')
     else:
         p('    if (!active) return;')

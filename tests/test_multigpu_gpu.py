@@ -124,3 +124,42 @@ def test_uncoupled_population_shards_without_exchange():
         return comm.allgather(f['membrane.V'])
     out = multigpu.run_threads(3, target)
     assert np.array_equal(np.concatenate(out[0], axis=-1), f0['membrane.V'])
+
+
+@pytest.mark.parametrize('nparts,precision', [(2, DP), (3, DP), (4, SP)])
+def test_partitioned_connection_graph_equals_single_gpu(nparts, precision):
+    # set_connections graph cut into contiguous id blocks: ghost cells are
+    # pushed by their owners every step. Same per-cell summation order as on
+    # one GPU (edge-list order), so the same bits.
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(duration=2, offset=1, period=1000)
+    n, edges = workloads.fibre_mesh(12, 5, 4, extra=0.08, seed=3)
+
+    def make(device, comm):
+        s = myokit_b200.SimulationCUDA(m, p, ncells=n, precision=precision,
+                                       device=device, comm=comm)
+        s.set_connections(edges)
+        s.set_paced_cell_list([0, 1, 2, 12, 13, 60, 61])
+        return s
+    ref = make(0, None)
+    t0, f0 = ref.run_fields(8, ['membrane.V', 'membrane.i_diff'], 0.5)
+    V0 = f0['membrane.V']
+    assert V0[-1].max() > 0 and np.any((V0.min(axis=1) < -40) & (V0.max(axis=1) > -20))
+    devs = devices(nparts)
+
+    def target(comm):
+        s = make(devs[comm.rank], comm)
+        t, f = s.run_fields(8, ['membrane.V', 'membrane.i_diff'], 0.5)
+        # and a second run on the resident state (re-arm + re-seed)
+        t2, f2 = s.run_fields(2, ['membrane.V'], 0.5)
+        return (comm.allgather(f['membrane.V']),
+                comm.allgather(f['membrane.i_diff']),
+                comm.allgather(f2['membrane.V']),
+                comm.allgather(s.state_array()))
+    out = multigpu.run_threads(nparts, target)
+    t2, g2 = ref.run_fields(2, ['membrane.V'], 0.5)
+    V, I, V2, S = out[0]
+    assert np.array_equal(np.concatenate(V, axis=-1), f0['membrane.V'])
+    assert np.array_equal(np.concatenate(I, axis=-1), f0['membrane.i_diff'])
+    assert np.array_equal(np.concatenate(V2, axis=-1), g2['membrane.V'])
+    assert np.array_equal(np.concatenate(S), ref.state_array())

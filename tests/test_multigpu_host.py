@@ -70,11 +70,31 @@ WORKER = textwrap.dedent('''
     u = myokit_b200.SimulationCUDA(m, p, ncells=10, diffusion=False, comm=comm)
     assert u.local_shape() == ((0, 5, 0, 1), (5, 5, 0, 1))[comm.rank]
     assert 'g.flag_lo' not in u.kernel_source().code
+    # a coupled 1-d cable cannot be cut; a set_connections graph can
+    c = myokit_b200.SimulationCUDA(m, p, ncells=10, comm=comm, precision=myokit.DOUBLE_PRECISION)
     try:
-        myokit_b200.SimulationCUDA(m, p, ncells=10, comm=comm)
+        c.kernel_source()
         raise SystemExit('expected ValueError')
-    except ValueError:
-        pass
+    except ValueError as e:
+        assert 'cannot be sharded' in str(e)
+    edges = [(i, i + 1, 2.0 + i) for i in range(9)] + [(0, 7, 0.5), (2, 9, 0.25), (6, 1, 0.75)]
+    c.set_connections(edges)
+    assert 'g.ghost' in c.kernel_source().code
+    li, lj, lg, ghosts = c._partition_graph()
+    x0 = 5 * comm.rank
+    # every global edge touching this block appears once, local endpoint first
+    want = [(a, b, g) for (a, b, g) in [(min(a, b), max(a, b), g) for a, b, g in edges]
+            if x0 <= a < x0 + 5 or x0 <= b < x0 + 5]
+    assert len(li) == len(want)
+    expect_ghosts = sorted(set(v for a, b, g in want for v in (a, b) if not x0 <= v < x0 + 5))
+    assert list(ghosts) == expect_ghosts
+    for k, (a, b, gg) in enumerate(want):
+        loc, rem = (a, b) if x0 <= a < x0 + 5 else (b, a)
+        assert li[k] == loc - x0 and lg[k] == gg
+        if x0 <= rem < x0 + 5:
+            assert lj[k] == rem - x0
+        else:
+            assert lj[k] == 5 + expect_ghosts.index(rem)
 
     # gather_rows reassembles slabs
     loc = g[y0:y0 + sny][None]
