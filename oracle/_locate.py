@@ -15,10 +15,40 @@ import warnings
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+class _first_import_lock:
+    """
+    myokit creates ~/.config/myokit (bare os.makedirs) and writes myokit.ini
+    there on its first import. N ranks starting together on a fresh machine
+    race on both; one dies with FileExistsError. The directory is created
+    tolerantly here and the import itself is serialised with a file lock.
+    """
+    def __enter__(self):
+        self._f = None
+        try:
+            import fcntl
+            d = os.path.join(os.path.expanduser('~'), '.config', 'myokit')
+            os.makedirs(d, exist_ok=True)
+            self._f = open(os.path.join(d, '.import.lock'), 'w')
+            fcntl.flock(self._f, fcntl.LOCK_EX)
+        except Exception:
+            self._f = None
+        return self
+
+    def __exit__(self, *args):
+        if self._f is not None:
+            try:
+                import fcntl
+                fcntl.flock(self._f, fcntl.LOCK_UN)
+                self._f.close()
+            except Exception:
+                pass
+        return False
+
+
 def import_myokit():
     """Returns the ``myokit`` module, or raises ImportError."""
     try:
-        with warnings.catch_warnings():
+        with _first_import_lock(), warnings.catch_warnings():
             warnings.simplefilter('ignore')
             import myokit
         return myokit
@@ -28,7 +58,7 @@ def import_myokit():
         if os.path.isdir(os.path.join(path, 'myokit')):
             sys.path.insert(0, path)
             try:
-                with warnings.catch_warnings():
+                with _first_import_lock(), warnings.catch_warnings():
                     warnings.simplefilter('ignore')
                     import myokit
                 return myokit

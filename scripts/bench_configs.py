@@ -6,7 +6,26 @@ import numpy as np
 import myokit_b200, myokit
 from myokit_b200 import workloads
 
-S = myokit_b200.SimulationCUDA
+_S = myokit_b200.SimulationCUDA
+WORLD = int(os.environ.get('WORLD_SIZE', '1'))
+RANK = int(os.environ.get('RANK', '0'))
+COMM = None
+if WORLD > 1:
+    # one process per GPU under torchrun: shard every workload
+    import torch
+    import torch.distributed as dist
+    from myokit_b200 import multigpu
+    LOCAL = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(LOCAL)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', LOCAL))
+    COMM = multigpu.TorchComm()
+
+
+def S(*args, **kw):
+    if COMM is not None:
+        kw.setdefault('device', LOCAL)
+        kw.setdefault('comm', COMM)
+    return _S(*args, **kw)
 
 
 def report(name, s, steps, warmup=20, **opts):
@@ -14,8 +33,17 @@ def report(name, s, steps, warmup=20, **opts):
         s.set_kernel_options(**opts)
     info = s.benchmark_steps(steps, warmup=warmup)
     ms = info['device_ms'] / info['steps']
-    print('%-34s %9d cells  %8.4f ms/step  %.3e cell-steps/s  (%d launches)' % (
-        name, info['cells'], ms, info['cells'] / ms * 1e3, info['kernel_launches']), flush=True)
+    cells = info['cells']
+    if COMM is not None:
+        # whole job: all cells / slowest rank
+        got = COMM.allgather((ms, cells))
+        ms = max(g[0] for g in got)
+        cells = sum(g[1] for g in got)
+        if RANK != 0:
+            return
+        name = '[%d GPUs] %s' % (WORLD, name)
+    print('%-44s %9d cells  %8.4f ms/step  %.3e cell-steps/s  (%d launches/rank)' % (
+        name, cells, ms, cells / ms * 1e3, info['kernel_launches']), flush=True)
 
 
 which = sys.argv[1:] or ['c1', 'c2', 'c4', 'c5']
@@ -50,7 +78,8 @@ if 'stencil' in which:
 if 'mesh' in which:
     t0 = time.time()
     s = workloads.c5_mesh(S)
-    print('mesh built in %.1f s: %d cells, %d edges' % (time.time() - t0, s._nx, len(s._connections[0])))
+    if RANK == 0:
+        print('mesh built in %.1f s: %d cells, %d edges' % (time.time() - t0, s._nx, len(s._connections[0])))
     report('C5-ii LR91 fp32 4.2M-node fibre mesh', s, 100, warmup=5)
 if 'c5' in which:
     m = workloads.data_model('decker-2009.mmt')
