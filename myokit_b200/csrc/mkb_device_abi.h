@@ -59,6 +59,12 @@ struct MkbGridArgs {
      *   NVLink; flag_lo / flag_hi: unsigned[n column blocks], the last step
      *   whose row segment has landed (written by the neighbour after a
      *   system-scope fence).
+     *   Why three slots: GPU r at step n needs its neighbour's V(t_n), which
+     *   the neighbour writes during its step n-1 into slot n % 3. The
+     *   neighbour cannot start step n+1 before r has delivered V(t_{n+1})
+     *   (r's step n), so while r reads slot n % 3 the neighbour is writing
+     *   at most slot (n+1) % 3 or — one step ahead — (n+2) % 3: never the
+     *   slot being read.
      * peer_*: the same four arrays of the neighbouring GPUs, mapped into this
      *   process (cudaIpcOpenMemHandle or direct peer access): this GPU's
      *   first row goes to the lower neighbour's halo_hi, its last row to the
