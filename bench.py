@@ -234,7 +234,6 @@ def workload_config(args, cpu=False):
 
 
 def run_ours(args, rank, world):
-    import numpy as np
     import torch
     import myokit_b200
     from myokit_b200 import workloads, capi

@@ -1,5 +1,5 @@
 """Kernel-option sweep on the C3 workload: compile stats here, timings on a GPU."""
-import os, sys, time, re, json
+import os, sys, time, re
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
 import myokit_b200, myokit

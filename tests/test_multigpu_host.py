@@ -9,11 +9,7 @@ import subprocess
 import sys
 import textwrap
 
-import numpy as np
-
-import myokit_b200
 from myokit_b200 import multigpu
-import myokit
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

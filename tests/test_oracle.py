@@ -21,7 +21,6 @@ import numpy as np
 import pytest
 
 from oracle.oracle import OracleSimulation, pacing_probe, myokit
-from oracle import cgen  # noqa: F401
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 DP = myokit.DOUBLE_PRECISION

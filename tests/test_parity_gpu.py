@@ -19,7 +19,7 @@ from myokit_b200 import capi, workloads
 import myokit
 
 from oracle.oracle import OracleSimulation
-from util import run_pair, max_abs_diff, configure
+from util import run_pair, max_abs_diff
 
 pytestmark = pytest.mark.gpu
 
