@@ -259,17 +259,17 @@ __device__ __forceinline__ double mkb_div(double a, double b) {
     r = fma(r, e, r);
     double q = a * r;
     const double d = fma(-b, q, a);
-    const double q2 = fma(d, r, q);
-    // Divisor 0 / inf / NaN (exponent field all zeros or all ones; tested on
-    // the integer pipe) or a non-finite dividend: the refinement produced
-    // NaNs, the plain product a * r is the IEEE answer.
+    // Divisor 0 / inf / NaN or a non-finite dividend make the residual NaN;
+    // the plain product a * r is then already the IEEE answer (inf, 0, NaN).
 #if MKB_DIV_INT_CHECK
+    // the same test on the integer pipe (exponent field all zeros / ones)
     const unsigned int eb = ((unsigned int)__double2hiint(b) << 1) + 0x00200000u;
     const unsigned int ea = ((unsigned int)__double2hiint(a) << 1) + 0x00200000u;
-    return (eb < 0x00400000u || ea < 0x00200000u) ? q : q2;
+    if (!(eb < 0x00400000u || ea < 0x00200000u)) q = fma(d, r, q);
 #else
-    return (d == d) ? q2 : q;       // the same test on the FP64 pipe
+    if (d == d) q = fma(d, r, q);   // (ptxas turns this into DSETP + 2 FSEL)
 #endif
+    return q;
 }
 __device__ __forceinline__ float mkb_div(float a, float b) {
     return __fdividef(a, b);
