@@ -262,6 +262,16 @@ int mkb_sim_ghost_connect(mkb_sim* sim, uint32_t n_flags, uint32_t n_peers,
  * (read + write), SM clock MHz (driver attribute), SM count. */
 int mkb_measure_peaks(int device, double* out6);
 
+/* ---- the host schedule alone (unit tests, no GPU needed) ----
+ * Runs the step selection of the time loop (openclsim.c:1051-1178) without
+ * any device work: for each step its start time, size, pacing level and
+ * whether a log row is written. Arrays may be null. Returns 0 when the run
+ * ended within max_steps, 1 if it was cut off, < 0 on a pacing error. */
+int mkb_schedule_probe(double tmin, double tmax, double dt, double log_interval,
+                       int n_events, const double* events, uint64_t max_steps,
+                       double* times, double* dts, double* paces,
+                       unsigned char* logging, uint64_t* n_steps);
+
 /* ---- pacing alone (unit tests; mirrors tests/ansic_event_based_pacing.c) ---- */
 int mkb_pacing_probe(double t0, int n_events, const double* events,
                      int n_times, const double* times,

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'libmyokit_b200.so')
 _STAMP = LIB_PATH + '.stamp'
 
 SOURCES = ['mkb_runtime.cu']
-HEADERS = ['mkb_device_abi.h', 'mkb_pacing.hpp',
+HEADERS = ['mkb_device_abi.h', 'mkb_pacing.hpp', 'mkb_schedule.hpp',
            os.path.join('..', '..', 'include', 'myokit_b200.h')]
 
 

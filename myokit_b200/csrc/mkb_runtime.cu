@@ -34,6 +34,7 @@
 #include "../../include/myokit_b200.h"
 #include "mkb_device_abi.h"
 #include "mkb_pacing.hpp"
+#include "mkb_schedule.hpp"
 
 typedef unsigned long long u64;
 
@@ -253,6 +254,33 @@ extern "C" int mkb_jit_compile(const char* source, const char* options,
     return MKB_OK;
 }
 
+extern "C" int mkb_schedule_probe(double tmin, double tmax, double dt, double log_interval,
+                                  int n_events, const double* events, uint64_t max_steps,
+                                  double* times, double* dts, double* paces, unsigned char* logging,
+                                  uint64_t* n_steps) {
+    if (!n_steps) return fail(MKB_ERR_INVALID, "null argument");
+    mkb::StepScheduler sched;
+    int rc = sched.init(tmin, tmax, dt, log_interval, n_events, events);
+    u64 n = 0;
+    while (rc == 0 && !sched.finished() && n < max_steps) {
+        mkb::StepInfo info;
+        rc = sched.next(&info);
+        if (rc) break;
+        if (times) times[n] = info.time;
+        if (dts) dts[n] = info.dt;
+        if (paces) paces[n] = info.pace;
+        if (logging) logging[n] = info.logging ? 1 : 0;
+        n++;
+    }
+    *n_steps = n;
+    if (rc == mkb::PACING_SIMULTANEOUS_EVENT) {
+        return fail(MKB_ERR_SIMULTANEOUS,
+                    "E-Pacing error: Event scheduled or re-occuring at the same time as another event.");
+    }
+    if (rc) return fail(MKB_ERR_PACING, "E-Pacing error %d", rc);
+    return sched.finished() ? MKB_OK : 1;
+}
+
 extern "C" int mkb_pacing_probe(double t0, int n_events, const double* events, int n_times,
                                 const double* times, double* levels, double* next_times) {
     mkb::EventPacing p;
@@ -331,9 +359,8 @@ struct mkb_sim {
 
     // schedule (openclsim.c globals :84-211)
     double tmin = 0, tmax = 0, default_dt = 0, log_interval = 1;
-    double engine_time = 0, engine_pace = 0, tnext_pace = 0, tnext_log = 0;
-    u64 istep = 1, inext_log = 0;
-    mkb::EventPacing pacing;
+    double engine_time = 0;
+    mkb::StepScheduler sched;
     bool finished = false, halted = false;
 
     // logging
@@ -815,21 +842,15 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
     }
     CUDA_TRY(cudaStreamSynchronize(s->stream));     // tables copied from stack vectors
 
-    // Pacing: openclsim.c:488-496
-    int rc = s->pacing.init(r->tmin, r->n_events, r->events);
-    if (rc == 0) rc = s->pacing.advance(r->tmin);
+    // Pacing and schedule: openclsim.c:488-502, 1018-1022
+    int rc = s->sched.init(r->tmin, r->tmax, r->dt, r->log_interval, r->n_events, r->events);
     if (rc == mkb::PACING_SIMULTANEOUS_EVENT) {
         return fail(MKB_ERR_SIMULTANEOUS,
                     "E-Pacing error: Event scheduled or re-occuring at the same time as another event.");
     }
     if (rc) return fail(MKB_ERR_PACING, "E-Pacing error %d", rc);
-    s->tnext_pace = s->pacing.next_time();
-    s->engine_pace = s->pacing.level();
-    s->engine_time = r->tmin;               // openclsim.c:501
-    s->istep = 1;                           // openclsim.c:1018
-    s->inext_log = 0;
-    s->tnext_log = r->tmin;                 // openclsim.c:1021-1022
-    s->finished = !(r->tmax > r->tmin);
+    s->engine_time = r->tmin;
+    s->finished = s->sched.finished();
     s->halted = false;
     s->step_index = 0;
     s->issued = 0;
@@ -1235,7 +1256,6 @@ static int graph_get(mkb_sim* s, int slot, int parity, cudaGraphExec_t* out) {
 
 template <typename TR>
 static int sim_step_typed(mkb_sim* s) {
-    const double dt_min = 0;                    // openclsim.c:413
     u64 steps_left = s->steps_per_call;
     bool timing_started = false;
 
@@ -1244,45 +1264,26 @@ static int sim_step_typed(mkb_sim* s) {
         s->recs.clear();
         while (s->recs.size() < (size_t)kRingHalf && steps_left > 0) {
             StepRec rec;
-            // openclsim.c:1054
-            rec.logging = (s->engine_time >= s->tnext_log);
-            // openclsim.c:1057-1063
-            bool intermediary = false;
-            double dt = s->tmin + (double)s->istep * s->default_dt - s->engine_time;
-            double d = s->tmax - s->engine_time;
-            if (d > dt_min && d < dt) { dt = d; intermediary = true; }
-            d = s->tnext_pace - s->engine_time;
-            if (d > dt_min && d < dt) { dt = d; intermediary = true; }
-            d = s->tnext_log - s->engine_time;
-            if (d > dt_min && d < dt) { dt = d; intermediary = true; }
-            if (!intermediary) s->istep++;
-            rec.p.time = s->engine_time;
-            rec.p.dt = dt;
-            rec.p.pace = s->engine_pace;
-            rec.p.flags = (rec.logging && s->store_aux) ? MKB_FLAG_STORE_AUX : 0u;
-            rec.p.step = (unsigned int)(++s->step_index);
-            rec.log_time = (double)(TR)s->engine_time;
-            rec.log_pace = (double)(TR)s->engine_pace;
-            if (rec.logging) {
-                // openclsim.c:1134-1136
-                s->inext_log++;
-                s->tnext_log = s->tmin + (double)s->inext_log * s->log_interval;
-            }
-            // openclsim.c:1147-1155
-            s->engine_time += dt;
-            int prc = s->pacing.advance(s->engine_time);
+            mkb::StepInfo info;
+            int prc = s->sched.next(&info);
             if (prc == mkb::PACING_SIMULTANEOUS_EVENT) {
                 return fail(MKB_ERR_SIMULTANEOUS,
                             "E-Pacing error: Event scheduled or re-occuring at the same time as another "
                             "event.");
             }
             if (prc) return fail(MKB_ERR_PACING, "E-Pacing error %d", prc);
-            s->tnext_pace = s->pacing.next_time();
-            s->engine_pace = s->pacing.level();
+            rec.logging = info.logging;
+            rec.p.time = info.time;
+            rec.p.dt = info.dt;
+            rec.p.pace = info.pace;
+            rec.p.flags = (rec.logging && s->store_aux) ? MKB_FLAG_STORE_AUX : 0u;
+            rec.p.step = (unsigned int)(++s->step_index);
+            rec.log_time = (double)(TR)info.time;       // openclsim.c:936-943: logged as Real
+            rec.log_pace = (double)(TR)info.pace;
+            s->engine_time = s->sched.time();
             s->recs.push_back(rec);
             steps_left--;
-            // openclsim.c:1162
-            if (s->engine_time >= s->tmax) {
+            if (s->sched.finished()) {
                 s->finished = true;
                 break;
             }

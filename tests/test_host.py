@@ -111,6 +111,65 @@ def test_pacing_probe_matches_myokit_pacing_system():
         assert list(tnext) == want_n
 
 
+def schedule(tmin, tmax, dt, log_interval, events, max_steps=10 ** 6):
+    lib = capi.library()
+    ev = np.array(events, dtype=np.float64).ravel()
+    n_ev = len(ev) // 5
+    if n_ev == 0:
+        ev = np.zeros(5)
+    times = np.zeros(max_steps)
+    dts = np.zeros(max_steps)
+    paces = np.zeros(max_steps)
+    logging = np.zeros(max_steps, dtype=np.uint8)
+    n = ctypes.c_uint64(0)
+    rc = lib.mkb_schedule_probe(
+        tmin, tmax, dt, log_interval, n_ev, ev.ctypes.data, max_steps,
+        times.ctypes.data, dts.ctypes.data, paces.ctypes.data,
+        logging.ctypes.data, ctypes.byref(n))
+    assert rc == 0, lib.mkb_last_error()
+    n = n.value
+    return times[:n], dts[:n], paces[:n], logging[:n].astype(bool)
+
+
+def test_schedule_matches_the_oracle_loop():
+    # The runtime's step selection (mkb_schedule.hpp) against the oracle's
+    # independent restatement of openclsim.c:1051-1178, on the cases where
+    # the loop is subtle: sub-ulp intermediary steps, pacing events off the
+    # step grid, negative start times, log every step.
+    from oracle.oracle import OracleSimulation
+    m, _, _ = myokit.load('example')
+    cases = [
+        (0.0, 40.0, 0.005, 1.0, [(1, 10.0, 0.5, 0, 0)]),
+        (0.0, 30.0, 0.005, 0.1, [(1, 3.0, 2.0, 7.0, 0)]),     # 0.1 vs 0.005: micro-steps
+        (0.0, 20.0, 0.01, 0.3, [(2, 1.234, 0.777, 0, 0)]),     # event off the grid
+        (-3.0, 9.0, 0.005, 0.5, [(1, 0.0, 1.0, 4.0, 2)]),      # negative start, 2 repeats
+        (5.0, 6.5, 0.02, 1e-9, []),                             # log every step
+        (0.0, 10.0, 0.005, 2.5, [(1, 0.0, 0.5, 1.0, 0)]),      # event at t = 0
+    ]
+    for tmin, tmax, dt, li, events in cases:
+        t, dts, pace, logging = schedule(tmin, tmax, dt, li, events)
+        assert abs(t[-1] + dts[-1] - tmax) < 1e-9 or t[-1] + dts[-1] >= tmax
+        p = myokit.Protocol()
+        for level, start, dur, period, mult in events:
+            p.schedule(level, start, dur, period, mult)
+        o = OracleSimulation(m, p, ncells=1, precision=DP)
+        o.set_step_size(dt)
+        o.set_time(tmin)
+        lg, _ = o.run(tmax - tmin, log=['engine.time', 'engine.pace'],
+                      log_interval=li)
+        assert len(t) == o.last_steps, (tmin, tmax, dt, li)
+        assert np.array_equal(t[logging], lg['engine.time'])
+        assert np.array_equal(pace[logging], lg['engine.pace'])
+    # properties of the loop itself
+    t, dts, pace, logging = schedule(0.0, 1000.0, 0.005, 1.0,
+                                     [(1, 50.0, 0.5, 1000.0, 0)])
+    assert len(t) == 200000 and logging.sum() == 1000
+    assert np.all(dts > 0) and pace.max() == 1
+    t, dts, pace, logging = schedule(0.0, 100.0, 0.005, 0.1, [])
+    assert logging.sum() == 1000 and len(t) > 20000          # intermediary steps
+    assert dts.min() < 1e-12
+
+
 def test_pacing_probe_simultaneous_events():
     lib = capi.library()
     ev = np.array([1.0, 10, 1, 0, 0, 2.0, 10, 1, 0, 0])
