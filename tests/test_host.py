@@ -556,3 +556,22 @@ def test_cuda_info_class(tmp_path, monkeypatch):
     if not HAS_GPU:
         with pytest.raises(myokit_b200.NoCUDAError):
             CUDA.current_info()
+
+
+def test_export_kernel_compiles_with_nvcc(tmp_path):
+    import shutil
+    import subprocess
+    s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=16)
+    path = s.export_kernel(str(tmp_path))
+    assert os.path.isfile(path)
+    assert os.path.isfile(os.path.join(str(tmp_path), 'mkb_device_abi.h'))
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    with open(path) as f:
+        first = f.readline()
+    assert first.startswith('// Build: nvcc')
+    cmd = first[len('// Build: '):].split()
+    cmd[0] = nvcc
+    # nvcc spells the option --fmad like NVRTC does; -default-device is implied
+    r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.getsize(os.path.join(str(tmp_path), 'mkb_cell_step.cubin')) > 10000
