@@ -8,10 +8,9 @@ from myokit_b200 import workloads, capi
 grid = int(os.environ.get('SWEEP_GRID', '2048'))
 steps = int(os.environ.get('SWEEP_STEPS', '20'))
 variants = [
-    ('exp table, div fp check', dict(fast_exp='table')),
-    ('exp table, div int check', dict(fast_exp='table', div_int_check=True)),
-    ('exp poly, div fp check', dict(fast_exp='poly')),
-    ('exp poly, div int check', dict(fast_exp='poly', div_int_check=True)),
+    ('default (max L1)', dict()),
+    ('b64x8 mb1', dict(block=(64, 8), min_blocks=1)),
+    ('b128x4 mb1', dict(block=(128, 4), min_blocks=1)),
 ]
 only = os.environ.get('SWEEP_ONLY')
 gpu = capi.device_count() > 0
