@@ -1612,6 +1612,10 @@ extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
     CUDA_TRY(cudaSetDevice(s->device));
     int rc = arm_run(s, r);
     if (rc) return rc;
+    // counters describe one run
+    s->launches = 0;
+    s->steps = 0;
+    s->device_ms = 0;
     if (s->d_xchg) {
         // Arrival flags restart from zero; the caller barriers, then reseeds
         const size_t keep = s->n_ghost ? (3 * s->n_ghost * s->rs + 255) / 256 * 256
