@@ -52,6 +52,11 @@ struct MkbGridArgs {
      * n_ghost + (col - n)], pushed there by the owners (peer stores). */
     const void* ghost;                  /* Real[3][n_ghost] or null */
     unsigned long long n_ghost;
+    /* Every block waits until ghost_flags[ghost_import[k]] >= step for all k
+     * (one flag per exporting GPU, raised after its stores for `step`). */
+    const unsigned int* ghost_flags;
+    const unsigned int* ghost_import;   /* [n_ghost_import] */
+    unsigned long long n_ghost_import;
     /* Row-slab sharding (multi-GPU), all null on a single GPU.
      * halo_lo / halo_hi: THIS GPU's ghost rows, Real[3][nx] each (slot =
      *   step % 3): V(t_step) of global row iy_offset-1 / iy_offset+ny,

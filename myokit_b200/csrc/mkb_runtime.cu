@@ -134,38 +134,35 @@ __global__ void k_fill_u32(unsigned int* p, u64 n, unsigned int value) {
 }
 
 // --- partitioned connection graphs ---------------------------------------
-// One thread waits until every listed flag has reached `step`.
-__global__ void k_wait_flags(const unsigned int* flags, const unsigned int* which, unsigned int n,
-                             unsigned int step, unsigned int* error) {
-    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
-        const volatile unsigned int* f = flags + which[k];
-        unsigned int spins = 0;
-        while (*f < step) {
-            __nanosleep(spins < 64 ? 20 : 200);
-            if (++spins > 50000000u) {
-                atomicExch(error, 1u);
-                break;
-            }
-        }
-    }
-    __threadfence();
-}
-
-// dst[slot[e]] = v[src[e]]: this partition's cells into a peer's ghost slots.
+// One launch per step for all peers: entry e copies v[src[e]] into ghost slot
+// slot[e] of peer peer[e] (a store over NVLink), in that peer's plane for
+// `step`. The block that finishes last — every other block's stores are
+// behind a system-scope fence by then — raises this rank's flag on every
+// peer, so no second launch is needed to publish the step.
 template <typename TR>
 __global__ void k_push_ghosts(const TR* __restrict__ v, const u64* __restrict__ src,
-                              const u64* __restrict__ slot, u64 n, TR* dst) {
+                              const u64* __restrict__ slot, const unsigned int* __restrict__ peer,
+                              u64 n, void* const* peer_base, const u64* __restrict__ peer_n_ghost,
+                              unsigned int* const* flags, unsigned int n_peers, unsigned int step,
+                              unsigned int* done) {
+    __shared__ bool last;
+    const u64 plane = step % 3u;
     u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    for (; e < n; e += (u64)gridDim.x * blockDim.x) dst[slot[e]] = v[src[e]];
-}
-
-// Runs after the pushes (stream order = they have completed): raise this
-// rank's flag on every peer.
-__global__ void k_raise_flags(unsigned int* const* flags, unsigned int n, unsigned int value) {
-    __threadfence_system();
-    for (unsigned int k = threadIdx.x; k < n; k += blockDim.x) {
-        *((volatile unsigned int*)flags[k]) = value;
+    for (; e < n; e += (u64)gridDim.x * blockDim.x) {
+        const unsigned int p = peer[e];
+        TR* dst = (TR*)peer_base[p] + plane * peer_n_ghost[p];
+        dst[slot[e]] = v[src[e]];
     }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    for (unsigned int k = threadIdx.x; k < n_peers; k += blockDim.x) {
+        *((volatile unsigned int*)flags[k]) = step;
+    }
+    if (threadIdx.x == 0) *done = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -413,11 +410,17 @@ struct mkb_sim {
         bool ipc = false;
         u64 peer_n_ghost = 0;
         u64 n_export = 0;
-        u64* d_src = nullptr;           // local cells to send
-        u64* d_dst = nullptr;           // ghost slots on the peer
         unsigned int* flag = nullptr;   // the flag this rank raises on the peer
     };
     std::vector<GhostPeerRt> gpeers;
+    // all peers' export lists, concatenated (one push launch per step)
+    u64 n_export = 0;
+    u64* d_exp_src = nullptr;           // local cells to send
+    u64* d_exp_slot = nullptr;          // ghost slots on the receiving peer
+    unsigned int* d_exp_peer = nullptr; // which peer (index into gpeers)
+    void** d_peer_base = nullptr;       // device array: the peers' exchange blocks
+    u64* d_peer_n_ghost = nullptr;      // device array: ghost count of each peer
+    unsigned int* d_push_done = nullptr;// block counter of the push kernel
     unsigned int** d_peer_flags = nullptr;  // device array of the peers' flag pointers
     unsigned int* d_import = nullptr;       // indices of own flags to wait for
     unsigned int n_import = 0;
@@ -461,10 +464,14 @@ static void sim_destroy(mkb_sim* s) {
         if (gs.done) cudaEventDestroy(gs.done);
     }
     for (auto& gp : s->gpeers) {
-        cudaFree(gp.d_src);
-        cudaFree(gp.d_dst);
         if (gp.base && gp.ipc) cudaIpcCloseMemHandle(gp.base);
     }
+    cudaFree(s->d_exp_src);
+    cudaFree(s->d_exp_slot);
+    cudaFree(s->d_exp_peer);
+    cudaFree(s->d_peer_base);
+    cudaFree(s->d_peer_n_ghost);
+    cudaFree(s->d_push_done);
     cudaFree(s->d_peer_flags);
     cudaFree(s->d_import);
     if (s->peer_lo_base && s->peer_lo_ipc) cudaIpcCloseMemHandle(s->peer_lo_base);
@@ -684,8 +691,6 @@ static int preload_kernels(mkb_sim* s) {
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)s->kern));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_log_gather<TR>));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_fill_u32));
-    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_wait_flags));
-    CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_raise_flags));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_push_ghosts<TR>));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_soa_to_aos<TR, TR>));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_soa_to_aos<TR, double>));
@@ -1202,17 +1207,14 @@ static size_t ghost_flags_offset(u64 n_ghost, size_t rs) {
 // the flags to `step` (seeding uses step = 1 with the current V plane).
 template <typename TR>
 static int ghost_push(mkb_sim* s, const TR* v, unsigned int step) {
-    for (auto& gp : s->gpeers) {
-        if (!gp.n_export) continue;
-        TR* dst = (TR*)gp.base + (u64)(step % 3) * gp.peer_n_ghost;
-        k_push_ghosts<TR><<<grid_for(gp.n_export), 256, 0, s->stream>>>(v, gp.d_src, gp.d_dst,
-                                                                         gp.n_export, dst);
-        s->launches++;
-    }
-    if (!s->gpeers.empty()) {
-        k_raise_flags<<<1, 64, 0, s->stream>>>(s->d_peer_flags, (unsigned int)s->gpeers.size(), step);
-        s->launches++;
-    }
+    if (s->gpeers.empty()) return MKB_OK;
+    u64 blocks = (s->n_export + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_push_ghosts<TR><<<(unsigned int)blocks, 256, 0, s->stream>>>(
+        v, s->d_exp_src, s->d_exp_slot, s->d_exp_peer, s->n_export, s->d_peer_base,
+        s->d_peer_n_ghost, s->d_peer_flags, (unsigned int)s->gpeers.size(), step, s->d_push_done);
+    s->launches++;
     CUDA_TRY(cudaGetLastError());
     return MKB_OK;
 }
@@ -1372,13 +1374,6 @@ static int sim_step_typed(mkb_sim* s) {
                     CUDA_TRY(cudaMemcpyAsync(row + f.col, src, s->n * sizeof(TR),
                                              cudaMemcpyDeviceToDevice, s->stream));
                 }
-            }
-            if (s->n_import) {
-                // ghost V(t) of this step must have arrived from every exporter
-                k_wait_flags<<<1, 64, 0, s->stream>>>(
-                    (const unsigned int*)(s->d_xchg + ghost_flags_offset(s->n_ghost, s->rs)),
-                    s->d_import, s->n_import, rec.p.step, s->grid.halo_error);
-                s->launches++;
             }
             // fused diffusion + cell step: states -> t + dt (openclsim.c:1066-1096)
             const MkbStepParams* sp = dring + i;
@@ -1548,6 +1543,8 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
     CUDA_TRY(cudaSetDevice(s->device));
     s->n_flags = n_flags;
     std::vector<unsigned int*> flag_ptrs;
+    std::vector<u64> exp_src, exp_slot;
+    std::vector<unsigned int> exp_peer;
     for (uint32_t k = 0; k < n_peers; k++) {
         const mkb_ghost_peer& in = peers[k];
         mkb_sim::GhostPeerRt gp;
@@ -1575,24 +1572,42 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
         gp.n_export = in.n_export;
         if (in.flag_index >= in.peer_n_flags) return fail(MKB_ERR_INVALID, "flag index out of range");
         gp.flag = (unsigned int*)((char*)gp.base + ghost_flags_offset(in.peer_n_ghost, s->rs)) + in.flag_index;
-        if (gp.n_export) {
-            for (u64 e = 0; e < gp.n_export; e++) {
-                if (in.src_cell[e] >= s->n || in.dst_slot[e] >= in.peer_n_ghost) {
-                    return fail(MKB_ERR_INVALID, "export entry out of range");
-                }
+        for (u64 e = 0; e < gp.n_export; e++) {
+            if (in.src_cell[e] >= s->n || in.dst_slot[e] >= in.peer_n_ghost) {
+                return fail(MKB_ERR_INVALID, "export entry out of range");
             }
-            CUDA_TRY(cudaMalloc(&gp.d_src, gp.n_export * sizeof(u64)));
-            CUDA_TRY(cudaMalloc(&gp.d_dst, gp.n_export * sizeof(u64)));
-            CUDA_TRY(cudaMemcpy(gp.d_src, in.src_cell, gp.n_export * sizeof(u64), cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMemcpy(gp.d_dst, in.dst_slot, gp.n_export * sizeof(u64), cudaMemcpyHostToDevice));
+            exp_src.push_back(in.src_cell[e]);
+            exp_slot.push_back(in.dst_slot[e]);
+            exp_peer.push_back(k);
         }
         s->gpeers.push_back(gp);
         flag_ptrs.push_back(gp.flag);
     }
     if (!flag_ptrs.empty()) {
-        CUDA_TRY(cudaMalloc(&s->d_peer_flags, flag_ptrs.size() * sizeof(unsigned int*)));
-        CUDA_TRY(cudaMemcpy(s->d_peer_flags, flag_ptrs.data(), flag_ptrs.size() * sizeof(unsigned int*),
-                            cudaMemcpyHostToDevice));
+        std::vector<void*> bases;
+        std::vector<u64> counts;
+        for (auto& gp : s->gpeers) {
+            bases.push_back(gp.base);
+            counts.push_back(gp.peer_n_ghost);
+        }
+        const size_t np = flag_ptrs.size();
+        CUDA_TRY(cudaMalloc(&s->d_peer_flags, np * sizeof(unsigned int*)));
+        CUDA_TRY(cudaMemcpy(s->d_peer_flags, flag_ptrs.data(), np * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&s->d_peer_base, np * sizeof(void*)));
+        CUDA_TRY(cudaMemcpy(s->d_peer_base, bases.data(), np * sizeof(void*), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&s->d_peer_n_ghost, np * sizeof(u64)));
+        CUDA_TRY(cudaMemcpy(s->d_peer_n_ghost, counts.data(), np * sizeof(u64), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&s->d_push_done, sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(s->d_push_done, 0, sizeof(unsigned int)));
+        s->n_export = exp_src.size();
+        if (s->n_export) {
+            CUDA_TRY(cudaMalloc(&s->d_exp_src, s->n_export * sizeof(u64)));
+            CUDA_TRY(cudaMalloc(&s->d_exp_slot, s->n_export * sizeof(u64)));
+            CUDA_TRY(cudaMalloc(&s->d_exp_peer, s->n_export * sizeof(unsigned int)));
+            CUDA_TRY(cudaMemcpy(s->d_exp_src, exp_src.data(), s->n_export * sizeof(u64), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(s->d_exp_slot, exp_slot.data(), s->n_export * sizeof(u64), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(s->d_exp_peer, exp_peer.data(), s->n_export * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        }
     }
     s->n_import = n_import;
     if (n_import) {
@@ -1601,6 +1616,10 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
         }
         CUDA_TRY(cudaMalloc(&s->d_import, n_import * sizeof(unsigned int)));
         CUDA_TRY(cudaMemcpy(s->d_import, import_flags, n_import * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        // the step kernel itself waits for these flags (no separate launch)
+        s->grid.ghost_flags = (const unsigned int*)(s->d_xchg + ghost_flags_offset(s->n_ghost, s->rs));
+        s->grid.ghost_import = s->d_import;
+        s->grid.n_ghost_import = n_import;
     }
     s->ghosts_connected = true;
     return mkb_sim_halo_seed(s);

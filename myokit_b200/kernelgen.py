@@ -553,6 +553,15 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     if slab or diffusion_mode == DIFF_CONNECTIONS or cpt not in (2, 4, 8) \
             or (sp and cpt == 2):
         cpt = 1
+    if cpt > 1 and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+        # rim-exchange arrays of the register-patch path (static shared memory)
+        rpt_ = max(int(rows_per_thread or 1), 1)
+        smem = (2 * by * rpt_ * (bx + 2) + 2 * (by + 2) * bx * cpt) * (4 if sp else 8)
+        if smem > 48 * 1024:
+            raise ValueError(
+                'Tile too large: block %dx%d with cells_per_thread=%d,'
+                ' rows_per_thread=%d needs %d bytes of shared memory for its'
+                ' rim exchange (limit 49152).' % (bx, by, cpt, rpt_, smem))
 
     equations = model.solvable_order()
     del equations['*remaining*']
@@ -1079,6 +1088,17 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    }')
     else:
         p('    const unsigned int iy = byr * MKB_BY + ty;')
+    if partitioned:
+        p('    // Ghost cells: V(t) of this step must have arrived from every')
+        p('    // exporting GPU before any thread of this block gathers it.')
+        p('    if (g.n_ghost_import) {')
+        p('        const unsigned int nimp = (unsigned int)g.n_ghost_import;')
+        p('        for (unsigned int k = ty * MKB_BX + tx; k < nimp; k += MKB_BX * MKB_BY) {')
+        p('            mkb_wait_flag(g.ghost_flags + g.ghost_import[k], sp->step, g.halo_error);')
+        p('            __threadfence();')
+        p('        }')
+        p('        __syncthreads();')
+        p('    }')
     p('    const bool active = (ix < nx) && (iy < ny);')
     p('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
     p('    Real* const state = (Real*)g.state;')

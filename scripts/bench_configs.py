@@ -62,7 +62,7 @@ if 'c4' in which:
 if 'stencil' in which:
     for prec, name in ((myokit.SINGLE_PRECISION, 'fp32'), (myokit.DOUBLE_PRECISION, 'fp64')):
         rs = 4 if name == 'fp32' else 8
-        for opts in (dict(block=(64, 4)), dict(block=(64, 4), rows_per_thread=2), dict(block=(64, 4), rows_per_thread=4), dict(block=(64, 2), rows_per_thread=8), dict(block=(32, 8), rows_per_thread=4)):
+        for opts in (dict(), dict(block=(128, 2))):
             s = workloads.stencil_only(S, 8192, 4096, precision=prec)
             s.set_kernel_options(**opts)
             info = s.benchmark_steps(50, warmup=5)

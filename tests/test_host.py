@@ -575,3 +575,13 @@ def test_export_kernel_compiles_with_nvcc(tmp_path):
     r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert os.path.getsize(os.path.join(str(tmp_path), 'mkb_cell_step.cubin')) > 10000
+
+
+def test_oversized_tile_is_refused_before_the_compiler():
+    s = workloads.stencil_only(myokit_b200.SimulationCUDA, 512, 256,
+                               precision=myokit.DOUBLE_PRECISION)
+    s.set_kernel_options(block=(128, 2), cells_per_thread=2, rows_per_thread=8)
+    with pytest.raises(ValueError, match='shared memory'):
+        s.kernel_source()
+    s.set_kernel_options(block=(128, 2), cells_per_thread=2, rows_per_thread=4)
+    assert 'mkb_cell_step' in s.kernel_source().code

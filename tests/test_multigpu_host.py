@@ -104,7 +104,8 @@ WORKER = textwrap.dedent('''
         except capi.BackendError as e:
             assert 'no CPU fallback' in str(e)
     dist.barrier()
-    print('RANK_OK', comm.rank)
+    sys.stdout.write('RANK_OK_%%d%%s' %% (comm.rank, os.linesep))   # one write: ranks share the pipe
+    sys.stdout.flush()
 ''') % ROOT
 
 
@@ -119,7 +120,7 @@ def test_two_ranks_over_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, env=env,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert 'RANK_OK 0' in r.stdout and 'RANK_OK 1' in r.stdout
+    assert 'RANK_OK_0' in r.stdout and 'RANK_OK_1' in r.stdout
 
 
 def test_thread_comm_and_slab_rows():
