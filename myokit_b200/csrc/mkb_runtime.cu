@@ -153,9 +153,13 @@ __global__ void k_push_ghosts(const TR* __restrict__ v, const u64* __restrict__ 
         TR* dst = (TR*)peer_base[p] + plane * peer_n_ghost[p];
         dst[slot[e]] = v[src[e]];
     }
-    __threadfence_system();
+    // one system-scope fence per block, after the block has met: it is
+    // cumulative over the stores of every thread that reached the barrier
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(done, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = (atomicAdd(done, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (!last) return;
     __threadfence_system();

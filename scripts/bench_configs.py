@@ -90,3 +90,26 @@ if 'c5' in which:
     for var, base in (('ikr.Gbar', 0.0138542), ('ina.Gbar', 9.075), ('ik1.Gbar', 0.5)):
         s.set_field(var, base * (1 - rng.uniform(0, 1, n)))
     report('C5-i decker 1M uncoupled fp64 RL', s, 200, warmup=5)
+if 'meshtrace' in which:
+    # Where a partitioned-mesh step goes: kernel table from the CUPTI tracer
+    # (diagnostic only; numbers under a tracer are never bench values).
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    nz = 128 if WORLD > 1 else 128 // int(os.environ.get('MESH_SPLIT', '2'))
+    s = workloads.c5_mesh(S, nz=nz)
+    report('mesh nz=%d (untraced)' % nz, s, 100, warmup=5)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        s.benchmark_steps(50, warmup=0)
+        torch.cuda.synchronize()
+    if RANK == 0:
+        ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        ev.sort(key=lambda e: e.time_range.start)
+        by = {}
+        for e in ev:
+            by.setdefault(e.name[:60], []).append(e.time_range.end - e.time_range.start)
+        for k, v in by.items():
+            print('  %-60s n=%4d  mean %8.2f us' % (k, len(v), sum(v) / len(v)))
+        if ev:
+            span = ev[-1].time_range.end - ev[0].time_range.start
+            busy = sum(e.time_range.end - e.time_range.start for e in ev)
+            print('  span %.1f us, kernels %.1f us, gaps %.1f us' % (span, busy, span - busy))
