@@ -23,6 +23,7 @@
 #include <nvrtc.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -372,12 +373,21 @@ struct mkb_sim {
     };
     std::vector<FieldCopy> pre_fields, post_fields;
     u64 h_log_bytes = 0;                // capacity of h_log in bytes
+    std::vector<char*> h_log_retired;   // outgrown pinned matrices, freed at clean
+    u64 h_log_retired_bytes = 0;
     std::vector<int> time_cols, pace_cols;
     GatherEntry* d_tab_pre = nullptr;   // states at t (before the step kernel)
     GatherEntry* d_tab_post = nullptr;  // idiff / intermediaries at t (after it)
     u64 n_pre = 0, n_post = 0;
     bool logging_states = false, store_aux = false;
-    char* d_log = nullptr;              // device row ring
+    char* d_log = nullptr;              // device row ring (null: no device rows this run)
+    // Allocations behind d_log / d_tab_*: kept across re-armed runs, because
+    // cudaFree / cudaMalloc synchronise the device and were measured at up to
+    // several hundred ms between two runs of 20-200 ms.
+    char* d_log_store = nullptr;
+    u64 d_log_bytes = 0;
+    GatherEntry* d_tab_store[2] = {nullptr, nullptr};
+    u64 d_tab_cap[2] = {0, 0};
     u64 log_cap = 0, log_half = 0;      // rows in ring / per half
     u64 rows_written = 0, rows_flushed = 0, rows_final = 0;
     char* h_log = nullptr;              // pinned host matrix
@@ -455,9 +465,9 @@ static void sim_destroy(mkb_sim* s) {
     cudaFree(s->d_csr_col);
     cudaFree(s->d_csr_g);
     cudaFree(s->d_ring);
-    cudaFree(s->d_tab_pre);
-    cudaFree(s->d_tab_post);
-    cudaFree(s->d_log);
+    cudaFree(s->d_tab_store[0]);
+    cudaFree(s->d_tab_store[1]);
+    cudaFree(s->d_log_store);
     for (int i = 0; i < 2; i++) {
         mkb_sim::GraphSlot& gs = s->gslot[i];
         for (int p = 0; p < 2; p++) {
@@ -483,6 +493,7 @@ static void sim_destroy(mkb_sim* s) {
     cudaFree(s->d_xchg);
     if (s->h_ring) cudaFreeHost(s->h_ring);
     if (s->h_log) cudaFreeHost(s->h_log);
+    for (char* q : s->h_log_retired) cudaFreeHost(q);
     for (int i = 0; i < 2; i++) {
         if (s->ev_ring[i]) cudaEventDestroy(s->ev_ring[i]);
         if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
@@ -701,19 +712,35 @@ static int preload_kernels(mkb_sim* s) {
     return MKB_OK;
 }
 
+// MKB_DEBUG_TIMING=1: host wall-clock of the set-up phases on stderr.
+static bool debug_timing() {
+    static const bool on = getenv("MKB_DEBUG_TIMING") != nullptr;
+    return on;
+}
+static double wall_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define MKB_PHASE(label)                                                     \
+    do {                                                                     \
+        if (debug_timing()) {                                                \
+            const double t_ = wall_s();                                      \
+            fprintf(stderr, "[mkb] %-28s %9.3f ms\n", label, (t_ - t_phase) * 1e3); \
+            t_phase = t_;                                                    \
+        }                                                                    \
+    } while (0)
+
 // Prepares a run on the state that is resident on the device: log tables and
 // rings, pacing (openclsim.c:488-496), schedule (:501, :1018-1022). Used by
 // mkb_sim_init and mkb_sim_rearm.
 static int arm_run(mkb_sim* s, const mkb_run_config* r) {
     if (!(r->dt > 0)) return fail(MKB_ERR_INVALID, "Step size must be greater than zero.");
     if (r->tmax < r->tmin) return fail(MKB_ERR_INVALID, "Simulation time can't be negative.");
+    double t_phase = wall_s();
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->side));
+    MKB_PHASE("arm: stream sync");
 
-    // Drop the previous run's log
-    cudaFree(s->d_tab_pre);
-    cudaFree(s->d_tab_post);
-    cudaFree(s->d_log);
+    // Drop the previous run's log (its device allocations are reused)
     s->d_tab_pre = s->d_tab_post = nullptr;
     s->d_log = nullptr;
     // (the pinned host matrix is kept and reused when it is large enough)
@@ -830,15 +857,20 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
     }
     s->n_pre = pre.size();
     s->n_post = post.size();
-    if (s->n_pre) {
-        CUDA_TRY(cudaMalloc(&s->d_tab_pre, s->n_pre * sizeof(GatherEntry)));
-        CUDA_TRY(cudaMemcpyAsync(s->d_tab_pre, pre.data(), s->n_pre * sizeof(GatherEntry),
+    const std::vector<GatherEntry>* tabs[2] = {&pre, &post};
+    for (int k = 0; k < 2; k++) {
+        const u64 cnt = tabs[k]->size();
+        if (!cnt) continue;
+        if (cnt > s->d_tab_cap[k]) {
+            cudaFree(s->d_tab_store[k]);
+            s->d_tab_store[k] = nullptr;
+            s->d_tab_cap[k] = 0;
+            CUDA_TRY(cudaMalloc(&s->d_tab_store[k], cnt * sizeof(GatherEntry)));
+            s->d_tab_cap[k] = cnt;
+        }
+        CUDA_TRY(cudaMemcpyAsync(s->d_tab_store[k], tabs[k]->data(), cnt * sizeof(GatherEntry),
                                  cudaMemcpyHostToDevice, s->stream));
-    }
-    if (s->n_post) {
-        CUDA_TRY(cudaMalloc(&s->d_tab_post, s->n_post * sizeof(GatherEntry)));
-        CUDA_TRY(cudaMemcpyAsync(s->d_tab_post, post.data(), s->n_post * sizeof(GatherEntry),
-                                 cudaMemcpyHostToDevice, s->stream));
+        (k == 0 ? s->d_tab_pre : s->d_tab_post) = s->d_tab_store[k];
     }
     if (s->n_pre + s->n_post + s->pre_fields.size() + s->post_fields.size() > 0) {
         // Device row ring: two halves, ~64 MiB each at most
@@ -846,10 +878,19 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
         const u64 half = std::max<u64>(1, std::min<u64>(4096, (64ull << 20) / row_bytes));
         s->log_half = half;
         s->log_cap = 2 * half;
-        CUDA_TRY(cudaMalloc(&s->d_log, s->log_cap * row_bytes));
+        if (s->log_cap * row_bytes > s->d_log_bytes) {
+            cudaFree(s->d_log_store);
+            s->d_log_store = nullptr;
+            s->d_log_bytes = 0;
+            CUDA_TRY(cudaMalloc(&s->d_log_store, s->log_cap * row_bytes));
+            s->d_log_bytes = s->log_cap * row_bytes;
+        }
+        s->d_log = s->d_log_store;
         CUDA_TRY(cudaMemsetAsync(s->d_log, 0, s->log_cap * row_bytes, s->stream));
     }
+    MKB_PHASE("arm: tables + ring alloc");
     CUDA_TRY(cudaStreamSynchronize(s->stream));     // tables copied from stack vectors
+    MKB_PHASE("arm: sync after memset");
 
     // Pacing and schedule: openclsim.c:488-502, 1018-1022
     int rc = s->sched.init(r->tmin, r->tmax, r->dt, r->log_interval, r->n_events, r->events);
@@ -865,6 +906,7 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
     s->issued = 0;
     s->throttle_count = 0;
     s->ring_chunk = 0;
+    MKB_PHASE("arm: schedule init");
     return MKB_OK;
 }
 
@@ -1140,13 +1182,25 @@ static int ensure_host_rows(mkb_sim* s, u64 rows) {
     } else {
         want = std::max(rows, s->h_log_cap * 2);
     }
+    double t_phase = wall_s();
     CUDA_TRY(cudaStreamSynchronize(s->side));
     char* p = nullptr;
     CUDA_TRY(cudaHostAlloc(&p, want * row_bytes, cudaHostAllocDefault));
+    MKB_PHASE("log: pinned alloc");
     if (s->h_log) {
         if (s->h_log_cap) memcpy(p, s->h_log, s->rows_flushed * row_bytes);
-        cudaFreeHost(s->h_log);
+        // Unpinning is slow (measured: ~0.5 s for 100 MB) and synchronises the
+        // device: outgrown matrices are retired and freed with the simulation,
+        // unless they add up to more than 2 GiB.
+        s->h_log_retired.push_back(s->h_log);
+        s->h_log_retired_bytes += s->h_log_bytes;
+        if (s->h_log_retired_bytes > (2ull << 30)) {
+            for (char* q : s->h_log_retired) cudaFreeHost(q);
+            s->h_log_retired.clear();
+            s->h_log_retired_bytes = 0;
+        }
     }
+    MKB_PHASE("log: pinned copy + free");
     s->h_log = p;
     s->h_log_cap = want;
     s->h_log_bytes = want * row_bytes;
