@@ -539,7 +539,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     ``const_div``
         With ``fast_div``: ``x / c`` for a compile-time constant ``c`` becomes
         ``x * (1 / c)`` (within 1 ulp of the quotient). A third of the
-        divisions of a large model have constant divisors.
+        divisions of a large model have constant divisors. Likewise the
+        Rush-Larsen exponent ``-dt / tau`` with ``tau = c / X`` becomes
+        ``-dt * X / c``.
     ``partitioned``
         Connection graphs cut over several GPUs: CSR columns beyond the local
         cells are ghost cells whose V is read from the ghost buffer the
@@ -691,6 +693,17 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             arg = '-dt / %s' % tau
             if fast_div and not sp and not native_maths:
                 arg = 'mkb_div(-dt, %s)' % tau
+                trhs = rl_states[var][1].rhs()
+                if (w.const_value is not None
+                        and isinstance(trhs, myokit.Divide)):
+                    # tau = c / X: -dt / tau = -dt * X * (1 / c), no division
+                    # (X is the expression tau was computed from: the
+                    # compiler reuses its value)
+                    c = w.const_value(trhs[0])
+                    if c is not None and c != 0 and 1e-290 < abs(c) < 1e290:
+                        arg = '(-dt * (%s))' % w.ex(trhs[1])
+                        if c != 1.0:
+                            arg = '(%s * %s)' % (arg, w.ex(myokit.Number(1.0 / c)))
             rhs = '%s - (%s - %s) * %s(%s)' % (inf, inf, x, exp, arg)
         else:
             rhs = '%s + dt * %s' % (v(var), v(var.lhs()))

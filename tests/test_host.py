@@ -236,7 +236,12 @@ def test_generated_source_follows_reference_arithmetic():
     assert 'state[1ull * stride + cid] = V_m + dt * D_m;' in code
     # Rush-Larsen update, openclsim.cl:362
     code = variants()['2d_hetero_rl_field'].kernel_source().code
-    assert re.search(r'= V_\w+ - \(V_\w+ - V_\w+\) \* mkb_exp_poly\(mkb_div\(-dt, V_\w+\)\);', code)
+    # (tau = 1 / X: the exponent -dt / tau is written -dt * X)
+    assert re.search(r'= V_\w+ - \(V_\w+ - V_\w+\) \* mkb_exp_poly\(\(-dt \* \(V_\w+ \+ V_\w+\)\)\);', code)
+    s = variants()['2d_hetero_rl_field']
+    s.set_kernel_options(const_div=False)
+    assert re.search(r'= V_\w+ - \(V_\w+ - V_\w+\) \* mkb_exp_poly\(mkb_div\(-dt, V_\w+\)\);',
+                     s.kernel_source().code)
     s = variants()['2d_hetero_rl_field']
     s.set_kernel_options(fast_div=False, fast_exp=False)
     assert re.search(r'= V_\w+ - \(V_\w+ - V_\w+\) \* exp\(-dt / V_\w+\);',
