@@ -208,7 +208,7 @@ def run_reference(args, rank, world):
     print(json.dumps(out))
 
 
-FP64_INSTR_PER_CELL_STEP = 2523      # DFMA + DMUL + DADD + DSETP, ncu r01
+FP64_INSTR_PER_CELL_STEP = 2255      # DFMA + DMUL + DADD + DSETP per cell-step, profiles/r01_opmix_c3.txt
 FP64_PEAK_GINSTR_S = 17105.3         # mkb_measure_peaks, r01
 
 
@@ -366,7 +366,7 @@ def run_ours(args, rank, world):
             'frac': achieved / peak,
             # dram__bytes_read + dram__bytes_write of one launch, from the
             # ncu --set full capture of this workload (profiles/r01_summary.md)
-            'traffic': 3.424e9 if (n == 2048 and world == 1) else None,
+            'traffic': 3.412e9 if (n == 2048 and world == 1) else None,
             'peak_source': peaks_src + ' (MEASURED_PEAKS.json hbm_gbs)',
             'kernel': 'mkb_cell_step',
             'algorithmic_bytes_per_cell_step': alg_bytes,
