@@ -26,6 +26,7 @@ cross-implementation tolerances of
 ``myokit/tests/test_simulation_opencl_vs_sim1d.py:118-136``.
 """
 import ctypes
+import time
 import hashlib
 import io
 import os
@@ -175,6 +176,7 @@ class OracleSimulation:
         self._state = np.tile(np.array(
             self._model.initial_values(True), dtype=np.float64), self._n)
         self.last_steps = 0
+        self.last_run_seconds = 0.0     # wall clock of the native run call
         self.last_halted = False
 
     # -- setters (subset of openclsim.py:1286-1715) --------------------------
@@ -417,6 +419,7 @@ class OracleSimulation:
         def ptr(a, t):
             return a.ctypes.data_as(ctypes.POINTER(t))
 
+        t_call = time.perf_counter()
         rc = lib.oracle_run(
             ctypes.c_size_t(self._nx), ctypes.c_size_t(self._ny),
             ctypes.c_int(mode),
@@ -435,6 +438,7 @@ class OracleSimulation:
             ctypes.byref(n_rows), ctypes.byref(n_steps),
             ctypes.byref(halted), ctypes.byref(tfinal),
             ctypes.c_int(nthreads))
+        self.last_run_seconds = time.perf_counter() - t_call
         if rc < 0:
             raise RuntimeError('Oracle pacing error %d' % rc)
         if rc > 0:
