@@ -237,6 +237,29 @@ __device__ __forceinline__ Real mkb_powi(Real x) {
     }
 }
 
+// Thread / block coordinates read again where they are needed (volatile: the
+// compiler may not reuse an earlier read), so that they do not occupy
+// registers across the whole cell model between the tile load at the top of a
+// slab kernel and its flag publication at the bottom (option slab_lean).
+struct MkbSlabPos {
+    unsigned int tx, ty, bxb, byb, nby;
+};
+template <int BY>
+__device__ __forceinline__ MkbSlabPos mkb_slab_pos(unsigned int ny) {
+    unsigned int by, bz, gy;
+    MkbSlabPos p;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(p.tx));
+    asm volatile("mov.u32 %0, %%tid.y;" : "=r"(p.ty));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(p.bxb));
+    asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
+    asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
+    asm volatile("mov.u32 %0, %%nctaid.y;" : "=r"(gy));
+    p.nby = (ny + BY - 1) / BY;
+    const unsigned int byr = by + bz * gy;
+    p.byb = (byr == 0) ? 0 : ((byr == 1) ? p.nby - 1 : byr - 1);
+    return p;
+}
+
 // Ghost-row arrival: spin (with back-off) until the neighbouring GPU has
 // delivered the row for `step`; gives up after ~10 s and raises halo_error so
 // a stalled neighbour surfaces as an error instead of a hung GPU.
@@ -503,7 +526,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              lazy_state=True, min_blocks=None, fast_exp=False,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
              rows_per_thread=1, div_int_check=False, partitioned=False,
-             const_div=True):
+             const_div=True, slab_lean=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -546,6 +569,15 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         Connection graphs cut over several GPUs: CSR columns beyond the local
         cells are ghost cells whose V is read from the ghost buffer the
         owning GPUs push into.
+    ``slab_lean``
+        With ``slab``: threads outside the grid leave before the cell model
+        (as in the single-GPU kernel) instead of skipping it inside a
+        conditional region, and the flag publication at the end re-reads its
+        block coordinates and the step number. ptxas then allocates the slab
+        kernel like the plain one (decker-2009 fp64: 96 bytes of spills per
+        thread instead of 348). The closing ``__syncthreads()`` is reached by
+        all non-exited threads only, which is what the barrier waits for on
+        sm_70 and later. Off by default until measured on a multi-GPU box.
     ``slab``
         Row-slab variant for multi-GPU grids: boundary row blocks run first,
         wait for the neighbouring GPU's ghost row (arrival flags), and push
@@ -1209,7 +1241,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('        }')
         p('    }')
         p('    __syncthreads();')
-        if slab:
+        if slab and not slab_lean:
             p('    if (active) {')
         else:
             p('    if (!active) return;')
@@ -1284,7 +1316,24 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('')
     for line in body:
         p(line)
-    if slab:
+    if slab and slab_lean:
+        p('    // Publish the boundary rows: data first, then (after a system-scope')
+        p('    // fence by every writer and a barrier of the threads still here)')
+        p('    // the arrival flag. Coordinates and step are read again.')
+        p('    const MkbSlabPos q = mkb_slab_pos<MKB_BY>((unsigned int)g.ny);')
+        p('    const bool send_lo = (q.byb == 0) && g.peer_lo_halo_hi;')
+        p('    const bool send_hi = (q.byb == q.nby - 1) && g.peer_hi_halo_lo;')
+        p('    if (send_lo || send_hi) {')
+        p('        __threadfence_system();')
+        p('        __syncthreads();')
+        p('        // (thread (0, 0) owns the block\'s lowest cell: it is in the grid)')
+        p('        if (q.tx == 0 && q.ty == 0) {')
+        p('            const unsigned int next = *(const volatile unsigned int*)&sp->step + 1u;')
+        p('            if (send_lo) *((volatile unsigned int*)g.peer_lo_flag_hi + q.bxb) = next;')
+        p('            if (send_hi) *((volatile unsigned int*)g.peer_hi_flag_lo + q.bxb) = next;')
+        p('        }')
+        p('    }')
+    elif slab:
         p('    }   // active')
         p('    // Publish the boundary rows: data first, then (after a system-scope')
         p('    // fence by every writer and a CTA barrier) the arrival flag.')

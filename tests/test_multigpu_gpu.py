@@ -163,3 +163,29 @@ def test_partitioned_connection_graph_equals_single_gpu(nparts, precision):
     assert np.array_equal(np.concatenate(I, axis=-1), f0['membrane.i_diff'])
     assert np.array_equal(np.concatenate(V2, axis=-1), g2['membrane.V'])
     assert np.array_equal(np.concatenate(S), ref.state_array())
+
+
+@pytest.mark.skipif(
+    not __import__('os').environ.get('MKB_TEST_EXPERIMENTAL'),
+    reason='slab_lean is off by default until measured on a GPU box;'
+           ' set MKB_TEST_EXPERIMENTAL=1 to run')
+@pytest.mark.parametrize('nslab', [2, 3])
+def test_lean_slab_kernel_equals_single_gpu(nslab):
+    # grid sizes that leave threads outside the grid in every block row/column
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(duration=2, offset=1, period=1000)
+    nx, ny = 70, 26
+
+    def make(device, comm):
+        s = myokit_b200.SimulationCUDA(m, p, ncells=(nx, ny), precision=DP,
+                                       device=device, comm=comm)
+        s.set_conductance(9, 6)
+        s.set_paced_cells(4, 7, 0, 9)
+        s.set_kernel_options(slab_lean=True)
+        return s
+    ref = make(0, None)
+    t0, f0 = ref.run_fields(6, ['membrane.V'], 0.5)
+    out = sharded(make, nslab, 6, ['membrane.V'], 0.5)
+    for t, f, state, info in out:
+        assert np.array_equal(f['membrane.V'], f0['membrane.V'])
+        assert np.array_equal(state, ref.state_array())

@@ -142,3 +142,33 @@ def test_thread_comm_and_slab_rows():
         assert False
     except KeyError:
         pass
+
+
+def test_slab_kernel_variants_compile():
+    """Both forms of the row-slab kernel build for sm_100a (NVRTC, no GPU)."""
+    import myokit
+    import myokit_b200
+    from myokit_b200 import capi
+
+    m, p, _ = myokit.load('example')
+    out = {}
+
+    def work(comm):
+        for lean in (False, True):
+            s = myokit_b200.SimulationCUDA(
+                m, p, ncells=(70, 9), precision=myokit.DOUBLE_PRECISION,
+                comm=comm)
+            s.set_kernel_options(slab_lean=lean)
+            if comm.rank == 0:
+                out[lean] = s.kernel_source()
+    multigpu.run_threads(2, work)
+    plain, lean = out[False].code, out[True].code
+    # default form: inactive threads skip the cell model inside a region
+    assert '    if (active) {\n' in plain and 'mkb_slab_pos<MKB_BY>(' not in plain
+    # lean form: they leave, and the publication re-reads its coordinates
+    assert '    if (!active) return;\n' in lean
+    assert 'const MkbSlabPos q = mkb_slab_pos<MKB_BY>((unsigned int)g.ny);' in lean
+    for src in (out[False], out[True]):
+        assert 'peer_lo_flag_hi' in src.code
+        cubin, log = capi.jit_compile(src.code, src.options)
+        assert len(cubin) > 10000
