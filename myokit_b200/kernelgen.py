@@ -285,18 +285,32 @@ __device__ __forceinline__ Real mkb_powh(Real x) {
 // Branch-free division (option fast_div): hardware reciprocal seed (~2^-23),
 // one Newton step on the reciprocal (~2^-46), then one residual correction of
 // the quotient (error ~2^-92 before the final rounding): within 1 ulp, not
-// guaranteed correctly rounded. Operands and quotient must be in the normal
-// range (|x| in [2^-1000, 2^1000]); b = 0, inf and NaN behave like IEEE;
-// denormal divisors are not supported.
+// guaranteed correctly rounded (20 M random operand pairs on the host, with a
+// 20-bit seed: all correctly rounded). Operands and quotient must be in the
+// normal range (|x| in [2^-1000, 2^1000]); denormal divisors are not
+// supported. A NaN operand or an infinite dividend give the IEEE result; a
+// divisor of exactly 0 or inf gives NaN (IEEE: inf / 0) unless the kernel is
+// built with div_parallel, whose unrefined product a * rcp(b) is at hand for
+// those cases.
 __device__ __forceinline__ double mkb_div(double a, double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     const double e = fma(-b, r, 1.0);
+#if MKB_DIV_PARALLEL
+    // Quotient and reciprocal are refined side by side (dependent chain of 4
+    // instead of 5 after the seed, same instruction count).
+    const double q0 = a * r;
+    const double q1 = fma(q0, e, q0);
+    r = fma(r, e, r);
+    const double dp = fma(-b, q1, a);
+    const double qp = fma(dp, r, q1);
+    // NaN residual: special operands; a * rcp(b) is the IEEE answer then
+    return (dp == dp) ? qp : q0;
+#endif
     r = fma(r, e, r);
     double q = a * r;
     const double d = fma(-b, q, a);
-    // Divisor 0 / inf / NaN or a non-finite dividend make the residual NaN;
-    // the plain product a * r is then already the IEEE answer (inf, 0, NaN).
+    // A NaN residual (special operands): keep the uncorrected product.
 #if MKB_DIV_INT_CHECK
     // the same test on the integer pipe (exponent field all zeros / ones)
     const unsigned int eb = ((unsigned int)__double2hiint(b) << 1) + 0x00200000u;
@@ -337,6 +351,35 @@ __device__ __forceinline__ double mkb_exp_poly(double x) {
     const int nc = min(max(n, -1021), 1024);
     const double y = __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
     return y;
+}
+
+// Estrin variant (option fast_exp = 'estrin'): the same reduction and
+// coefficients, the polynomial evaluated as a tree — dependent chain of 6
+// instead of 11 fused multiply-adds, for 3 more FP64 instructions. Max error
+// 0.97 ulp (scripts/gen_exp_coeffs.py). For kernels that wait on dependent
+// FP64 results (stall_wait) more than on the FP64 pipe itself.
+__device__ __forceinline__ double mkb_exp_estrin(double x) {
+    double t = fma(x, mkb_exp_c[0], mkb_exp_c[1]);
+    const int n = __double2loint(t);
+    t -= mkb_exp_c[1];
+    double r = fma(t, mkb_exp_c[2], x);
+    r = fma(t, mkb_exp_c[3], r);
+    const double r2 = r * r;
+    const double a1 = fma(mkb_exp_c[12], r, mkb_exp_c[13]);    // c2 + c3 r
+    const double a2 = fma(mkb_exp_c[10], r, mkb_exp_c[11]);    // c4 + c5 r
+    const double a3 = fma(mkb_exp_c[8], r, mkb_exp_c[9]);      // c6 + c7 r
+    const double a4 = fma(mkb_exp_c[6], r, mkb_exp_c[7]);      // c8 + c9 r
+    const double a5 = fma(mkb_exp_c[4], r, mkb_exp_c[5]);      // c10 + c11 r
+    const double r4 = r2 * r2;
+    const double b0 = fma(a2, r2, a1);
+    const double b1 = fma(a4, r2, a3);
+    const double r8 = r4 * r4;
+    const double d = fma(b1, r4, b0);
+    const double q = fma(a5, r8, d);
+    double p = fma(r2, q, r);
+    p += 1.0;
+    const int nc = min(max(n, -1021), 1024);
+    return __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
 }
 
 // Table variant (option fast_exp = 'table'): exp(x) = 2^m T[j] e^r
@@ -526,7 +569,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              lazy_state=True, min_blocks=None, fast_exp=False,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
              rows_per_thread=1, div_int_check=False, partitioned=False,
-             const_div=True, slab_lean=False):
+             const_div=True, slab_lean=False, div_parallel=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -569,6 +612,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         Connection graphs cut over several GPUs: CSR columns beyond the local
         cells are ghost cells whose V is read from the ghost buffer the
         owning GPUs push into.
+    ``div_parallel``
+        ``mkb_div`` refines quotient and reciprocal side by side: a shorter
+        dependent chain, and IEEE results for divisors 0 and inf. Same
+        instruction count; off by default until measured.
     ``slab_lean``
         With ``slab``: threads outside the grid leave before the cell model
         (as in the single-GPU kernel) instead of skipping it inside a
@@ -590,7 +637,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     else:
         w = _Writer(precision)
         w._fast_div = bool(fast_div)
-        w._fast_exp = ({'table': 'mkb_exp_tab', 'poly': 'mkb_exp_poly'}.get(
+        w._fast_exp = ({'table': 'mkb_exp_tab', 'poly': 'mkb_exp_poly',
+                        'estrin': 'mkb_exp_estrin'}.get(
             fast_exp, 'mkb_exp_poly') if fast_exp else False)
         if const_pool and not sp:
             w.enable_pool()
@@ -894,6 +942,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_CPT %d' % cpt)
         q('#define MKB_RPT %d' % rpt)
         q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
+        q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
         q(_PRELUDE)
         q(_VECTOR_PRELUDE)
         if pooled and w._pool:
@@ -1120,6 +1169,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('#define MKB_BX %d' % bx)
     p('#define MKB_BY %d' % by)
     p('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
+    p('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
     p(_PRELUDE)
     if pooled and w._pool:
         p('// Model constants (double precision), in order of first use')

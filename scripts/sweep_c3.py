@@ -8,9 +8,12 @@ from myokit_b200 import workloads, capi
 grid = int(os.environ.get('SWEEP_GRID', '2048'))
 steps = int(os.environ.get('SWEEP_STEPS', '20'))
 variants = [
-    ('default (max L1)', dict()),
-    ('b64x8 mb1', dict(block=(64, 8), min_blocks=1)),
-    ('b128x4 mb1', dict(block=(128, 4), min_blocks=1)),
+    ('default', dict()),
+    # prepared in round 1 without GPU time left to measure them:
+    ('div_parallel', dict(div_parallel=True)),
+    ('exp estrin', dict(fast_exp='estrin')),
+    ('estrin + div_parallel', dict(fast_exp='estrin', div_parallel=True)),
+    ('const_div off', dict(const_div=False)),
 ]
 only = os.environ.get('SWEEP_ONLY')
 gpu = capi.device_count() > 0

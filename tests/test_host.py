@@ -590,3 +590,18 @@ def test_oversized_tile_is_refused_before_the_compiler():
         s.kernel_source()
     s.set_kernel_options(block=(128, 2), cells_per_thread=2, rows_per_thread=4)
     assert 'mkb_cell_step' in s.kernel_source().code
+
+
+def test_opt_in_arithmetic_variants_generate_and_build():
+    # prepared, off by default: Estrin-scheme exp and side-by-side division
+    s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=16)
+    base = s.kernel_source().code
+    assert '#define MKB_DIV_PARALLEL 0' in base
+    assert 'mkb_exp_poly(' in base[base.index('extern "C" __global__'):]
+    s.set_kernel_options(fast_exp='estrin', div_parallel=True)
+    src = s.kernel_source()
+    body = src.code[src.code.index('extern "C" __global__'):]
+    assert '#define MKB_DIV_PARALLEL 1' in src.code
+    assert 'mkb_exp_estrin(' in body and 'mkb_exp_poly(' not in body
+    cubin, log = capi.jit_compile(src.code, src.options)
+    assert len(cubin) > 10000
