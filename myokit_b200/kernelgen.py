@@ -220,6 +220,13 @@ class _NativeWriter(_PowMixin, _NativeCudaExpressionWriter):
 
 
 _PRELUDE = r"""
+// The two pieces of inline PTX go through macros so that a host build of this
+// source (tests/cuda_shim, test infrastructure) can supply its own.
+#ifndef MKB_ASM_RCP64
+#define MKB_ASM_RCP64(r, b) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b))
+#define MKB_ASM_SREG(v, name) asm volatile("mov.u32 %0, %%" name ";" : "=r"(v))
+#endif
+
 // x^k for a compile-time integer k: square-and-multiply, fixed order.
 template <int N>
 __device__ __forceinline__ Real mkb_powi(Real x) {
@@ -248,12 +255,12 @@ template <int BY>
 __device__ __forceinline__ MkbSlabPos mkb_slab_pos(unsigned int ny) {
     unsigned int by, bz, gy;
     MkbSlabPos p;
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(p.tx));
-    asm volatile("mov.u32 %0, %%tid.y;" : "=r"(p.ty));
-    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(p.bxb));
-    asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
-    asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
-    asm volatile("mov.u32 %0, %%nctaid.y;" : "=r"(gy));
+    MKB_ASM_SREG(p.tx, "tid.x");
+    MKB_ASM_SREG(p.ty, "tid.y");
+    MKB_ASM_SREG(p.bxb, "ctaid.x");
+    MKB_ASM_SREG(by, "ctaid.y");
+    MKB_ASM_SREG(bz, "ctaid.z");
+    MKB_ASM_SREG(gy, "nctaid.y");
     p.nby = (ny + BY - 1) / BY;
     const unsigned int byr = by + bz * gy;
     p.byb = (byr == 0) ? 0 : ((byr == 1) ? p.nby - 1 : byr - 1);
@@ -294,7 +301,7 @@ __device__ __forceinline__ Real mkb_powh(Real x) {
 // those cases.
 __device__ __forceinline__ double mkb_div(double a, double b) {
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    MKB_ASM_RCP64(r, b);
     const double e = fma(-b, r, 1.0);
 #if MKB_DIV_PARALLEL
     // Quotient and reciprocal are refined side by side (dependent chain of 4

@@ -1,0 +1,149 @@
+"""
+Host execution of generated kernels — TEST INFRASTRUCTURE ONLY.
+
+``run_on_host(sim, duration, ...)`` takes a configured ``SimulationCUDA``
+(never run, no GPU needed), compiles the CUDA source its next run would JIT
+(``sim.kernel_source()``) as host C++ behind ``mkb_cuda_shim.h`` and steps it
+with the library's own schedule (``mkb_schedule_probe``). The product never
+imports this package.
+"""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+from myokit_b200 import capi, kernelgen
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_BUILD = os.path.join(_HERE, '_build')
+_CSRC = os.path.join(_ROOT, 'myokit_b200', 'csrc')
+
+
+def _compile(code, contract):
+    os.makedirs(_BUILD, exist_ok=True)
+    with open(os.path.join(_HERE, 'runner.cpp'), 'rb') as f:
+        runner = f.read()
+    with open(os.path.join(_HERE, 'mkb_cuda_shim.h'), 'rb') as f:
+        shim = f.read()
+    key = hashlib.sha1(code.encode('utf-8') + runner + shim
+                       + (b'c' if contract else b'n')).hexdigest()[:20]
+    so = os.path.join(_BUILD, 'k_%s.so' % key)
+    if not os.path.isfile(so):
+        cu = os.path.join(_BUILD, 'k_%s.cu.h' % key)
+        with open(cu, 'w') as f:
+            f.write(code)
+        tmp = so + '.tmp%d' % os.getpid()
+        cmd = ['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-mfma',
+               '-ffp-contract=' + ('fast' if contract else 'off'),
+               '-Wno-unknown-pragmas', '-Wno-unused-variable',
+               '-DMKB_KERNEL_FILE="%s"' % cu, '-I' + _CSRC, '-I' + _HERE,
+               os.path.join(_HERE, 'runner.cpp'), '-o', tmp]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('host build of the generated kernel failed:\n'
+                               + r.stderr[-4000:])
+        os.replace(tmp, so)
+    return ctypes.CDLL(so)
+
+
+def schedule(sim, duration, log_interval):
+    """The library's step list for a run: (times, dts, paces, logging)."""
+    lib = capi.library()
+    events, n_events = sim._events()
+    tmin = sim.time()
+    cap = int(duration / sim.step_size()) * 2 + 64
+    times = np.zeros(cap)
+    dts = np.zeros(cap)
+    paces = np.zeros(cap)
+    logging = np.zeros(cap, dtype=np.uint8)
+    n = ctypes.c_uint64(0)
+    rc = lib.mkb_schedule_probe(
+        ctypes.c_double(tmin), ctypes.c_double(tmin + duration),
+        ctypes.c_double(sim.step_size()), ctypes.c_double(log_interval),
+        ctypes.c_int(n_events), events.ctypes.data_as(ctypes.c_void_p),
+        ctypes.c_uint64(cap), times.ctypes.data_as(ctypes.c_void_p),
+        dts.ctypes.data_as(ctypes.c_void_p), paces.ctypes.data_as(ctypes.c_void_p),
+        logging.ctypes.data_as(ctypes.c_void_p), ctypes.byref(n))
+    assert rc == 0, rc
+    k = int(n.value)
+    return times[:k], dts[:k], paces[:k], logging[:k]
+
+
+def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None):
+    """
+    Runs ``duration`` on the host. Returns a dict: ``time`` (nt,), ``V``
+    (nt, ncells) — V(t) at the logged steps —, ``idiff`` (nt, ncells),
+    ``inter`` (nt, n_inter, ncells), ``state`` (ncells, n_state), ``steps``.
+    ``contract``: let g++ contract a*b+c like nvcc's --fmad (default: what
+    the kernel source was generated for).
+    """
+    inter_vars = [sim._model.get(q) for q in inter_log]
+    src = sim.kernel_source(inter_vars)
+    if contract is None:
+        contract = '--fmad=true' in src.options
+    lib = _compile(src.code, contract)
+    nx, ny = sim._nx, sim._ny
+    n = nx * ny
+    times, dts, paces, logging = schedule(sim, duration, log_interval)
+    rows = int(logging.sum())
+
+    state = np.ascontiguousarray(sim._state, dtype=np.float64).copy()
+    assert state.size == n * src.n_state
+    fields = [np.asarray(f, dtype=np.float64).ravel() for f in sim._fields.values()]
+    field_aos = (np.ascontiguousarray(np.vstack(fields).T).ravel()
+                 if fields else np.zeros(1))
+    mode = src.diffusion_mode
+    gxf = gyf = None
+    if mode == kernelgen.DIFF_FIELD:
+        gxf = np.ascontiguousarray(sim._gx_field, dtype=np.float64).ravel()
+        if sim._gy_field is not None:
+            gyf = np.ascontiguousarray(sim._gy_field, dtype=np.float64).ravel()
+    ci = cj = cg = None
+    n_conn = 0
+    if mode == kernelgen.DIFF_CONNECTIONS:
+        a, b, g = sim._connections
+        ci = np.ascontiguousarray(a, dtype=np.uint64)
+        cj = np.ascontiguousarray(b, dtype=np.uint64)
+        cg = np.ascontiguousarray(g, dtype=np.float64)
+        n_conn = len(ci)
+    px0 = px1 = py0 = py1 = 0
+    mask = None
+    if sim._diffusion_enabled:
+        if type(sim._paced_cells) == tuple:
+            pnx, pny, px, py = sim._paced_cells
+            px0, px1, py0, py1 = px, px + pnx, py, py + pny
+        else:
+            mask = np.zeros(n, dtype=np.uint8)
+            mask[np.array(sim._paced_cells, dtype=np.int64)] = 1
+
+    def ptr(a):
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    log_v = np.zeros((rows, n))
+    log_idiff = np.zeros((rows, n))
+    log_inter = np.zeros((rows, max(src.n_inter, 1), n))
+    lib.shim_run.restype = ctypes.c_int
+    rc = lib.shim_run(
+        ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(src.n_state),
+        ctypes.c_int(src.i_vm), ctypes.c_int(src.n_inter),
+        ctypes.c_int(src.n_field), ctypes.c_int(mode),
+        ctypes.c_double(sim._gx or 0), ctypes.c_double(sim._gy or 0),
+        ptr(gxf), ptr(gyf),
+        ctypes.c_longlong(px0), ctypes.c_longlong(px1),
+        ctypes.c_longlong(py0), ctypes.c_longlong(py1), ptr(mask),
+        ctypes.c_ulonglong(n_conn), ptr(ci), ptr(cj), ptr(cg),
+        ctypes.c_int(len(times)), ptr(times), ptr(dts), ptr(paces),
+        ptr(logging), ptr(state), ptr(field_aos), ptr(log_v), ptr(log_idiff),
+        ptr(log_inter),
+        ctypes.c_int(src.block[0]), ctypes.c_int(src.block[1]),
+        ctypes.c_int(src.cells_per_thread), ctypes.c_int(src.rows_per_thread))
+    assert rc == 0
+    return {
+        'time': times[logging.astype(bool)], 'V': log_v, 'idiff': log_idiff,
+        'inter': log_inter[:, :src.n_inter], 'steps': len(times),
+        'state': state.reshape(n, src.n_state),
+        'real_size': lib.shim_real_size(),
+    }
