@@ -1273,7 +1273,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    // entries hold the cell\'s own V and are never used: the edge')
         p('    // formulas below drop those terms exactly as openclsim.cl does.')
         p('    __shared__ Real tile[MKB_BY + 2][MKB_BX + 2];')
-        p('    tile[ty + 1][tx + 1] = vc;')
+        p('    // (only cells of the grid: the slot of a thread beyond the last row or')
+        p('    // column is the halo slot of its neighbour, written below)')
+        p('    if (active) tile[ty + 1][tx + 1] = vc;')
         p('    if (active) {')
         p('        if (tx == 0) tile[ty + 1][0] = (ix > 0) ? v_in[cid - 1] : vc;')
         p('        if (tx == MKB_BX - 1 || ix == nx - 1)')

@@ -72,7 +72,8 @@ def schedule(sim, duration, log_interval):
     return times[:k], dts[:k], paces[:k], logging[:k]
 
 
-def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None):
+def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None,
+                reverse=False):
     """
     Runs ``duration`` on the host. Returns a dict: ``time`` (nt,), ``V``
     (nt, ncells) — V(t) at the logged steps —, ``idiff`` (nt, ncells),
@@ -85,6 +86,7 @@ def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None):
     if contract is None:
         contract = '--fmad=true' in src.options
     lib = _compile(src.code, contract)
+    lib.shim_set_thread_order(1 if reverse else 0)
     nx, ny = sim._nx, sim._ny
     n = nx * ny
     times, dts, paces, logging = schedule(sim, duration, log_interval)
@@ -146,4 +148,83 @@ def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None):
         'inter': log_inter[:, :src.n_inter], 'steps': len(times),
         'state': state.reshape(n, src.n_state),
         'real_size': lib.shim_real_size(),
+    }
+
+
+def run_slabs_on_host(make, n_slabs, duration, log_interval=1.0, options=None,
+                      reverse=False):
+    """
+    Row-slab kernels on the host: ``make(comm=None)`` builds the simulation;
+    the slab variant of its kernel is what a rank of an ``n_slabs``-GPU run
+    compiles. All slabs run in this process, step by step (see runner.cpp).
+    Returns the same dict as :func:`run_on_host` for the whole grid plus
+    ``halo_error``.
+    """
+    from myokit_b200 import multigpu
+    options = options or {}
+    whole = make(None)
+    whole.set_kernel_options(**options)
+    box = {}
+
+    def work(comm):
+        s = make(comm)
+        s.set_kernel_options(**options)
+        if comm.rank == 0:
+            box['src'] = s.kernel_source()
+    multigpu.run_threads(n_slabs, work)
+    src = box['src']
+    assert 'peer_lo_halo_hi' in src.code      # the slab variant
+    contract = '--fmad=true' in src.options
+    lib = _compile(src.code, contract)
+    lib.shim_set_thread_order(1 if reverse else 0)
+    nx, ny = whole._nx, whole._ny
+    n = nx * ny
+    rows = multigpu.slab_rows(ny, n_slabs)
+    row0 = np.array([r[0] for r in rows], dtype=np.int32)
+    row1 = np.array([r[1] for r in rows], dtype=np.int32)
+    times, dts, paces, logging = schedule(whole, duration, log_interval)
+    nrows = int(logging.sum())
+    state = np.ascontiguousarray(whole._state, dtype=np.float64).copy()
+    fields = [np.asarray(f, dtype=np.float64).ravel() for f in whole._fields.values()]
+    field_aos = (np.ascontiguousarray(np.vstack(fields).T).ravel()
+                 if fields else np.zeros(1))
+    gxf = gyf = None
+    if src.diffusion_mode == kernelgen.DIFF_FIELD:
+        gxf = np.ascontiguousarray(whole._gx_field, dtype=np.float64).ravel()
+        gyf = np.ascontiguousarray(whole._gy_field, dtype=np.float64).ravel()
+    px0 = px1 = py0 = py1 = 0
+    mask = None
+    if type(whole._paced_cells) == tuple:
+        pnx, pny, px, py = whole._paced_cells
+        px0, px1, py0, py1 = px, px + pnx, py, py + pny
+    else:
+        mask = np.zeros(n, dtype=np.uint8)
+        mask[np.array(whole._paced_cells, dtype=np.int64)] = 1
+
+    def ptr(a):
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    log_v = np.zeros((nrows, n))
+    log_idiff = np.zeros((nrows, n))
+    err = ctypes.c_uint(0)
+    lib.shim_run_slabs.restype = ctypes.c_int
+    rc = lib.shim_run_slabs(
+        ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(n_slabs),
+        ptr(row0), ptr(row1),
+        ctypes.c_int(src.n_state), ctypes.c_int(src.i_vm),
+        ctypes.c_int(src.n_inter), ctypes.c_int(src.n_field),
+        ctypes.c_int(src.diffusion_mode),
+        ctypes.c_double(whole._gx or 0), ctypes.c_double(whole._gy or 0),
+        ptr(gxf), ptr(gyf),
+        ctypes.c_longlong(px0), ctypes.c_longlong(px1),
+        ctypes.c_longlong(py0), ctypes.c_longlong(py1), ptr(mask),
+        ctypes.c_int(len(times)), ptr(times), ptr(dts), ptr(paces),
+        ptr(logging), ptr(state), ptr(field_aos), ptr(log_v), ptr(log_idiff),
+        ctypes.c_int(src.block[0]), ctypes.c_int(src.block[1]),
+        ctypes.byref(err))
+    assert rc == 0
+    return {
+        'time': times[logging.astype(bool)], 'V': log_v, 'idiff': log_idiff,
+        'steps': len(times), 'state': state.reshape(n, src.n_state),
+        'halo_error': int(err.value),
     }

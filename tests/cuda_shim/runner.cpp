@@ -27,6 +27,7 @@ struct Fiber {
 ucontext_t g_sched;
 Fiber* g_cur = nullptr;
 int g_or_acc = 0, g_or_res = 0;
+int g_reverse = 0;
 
 struct Launch {
     MkbGridArgs g;
@@ -74,7 +75,10 @@ void run_block(std::vector<Fiber>& fibers, std::vector<char>& stacks, unsigned i
     g_or_acc = g_or_res = 0;
     for (;;) {
         bool alive = false;
-        for (unsigned int t = 0; t < nthreads; t++) {
+        for (unsigned int k = 0; k < nthreads; k++) {
+            // thread order within a barrier phase is not defined on the GPU:
+            // tests run both directions and require identical results
+            const unsigned int t = g_reverse ? nthreads - 1 - k : k;
             Fiber& f = fibers[t];
             if (f.done || f.waiting) continue;
             threadIdx.x = f.tx;
@@ -95,6 +99,7 @@ void run_block(std::vector<Fiber>& fibers, std::vector<char>& stacks, unsigned i
 }   // namespace
 
 extern "C" int shim_real_size(void) { return (int)sizeof(Real); }
+extern "C" void shim_set_thread_order(int reverse) { g_reverse = reverse; }
 
 extern "C" int shim_run(
     int nx, int ny, int n_state, int i_vm, int n_inter, int n_field, int diffusion_mode,
@@ -228,5 +233,191 @@ extern "C" int shim_run(
     for (size_t c = 0; c < n; c++) {
         for (int k = 0; k < n_state; k++) state_aos[c * n_state + k] = (double)state[(size_t)k * stride + c];
     }
+    return 0;
+}
+
+
+/*
+ * Row slabs: the grid cut into `n_slabs` row ranges, every slab with its own
+ * planes and exchange block ([halo_lo 3 x nx][halo_hi 3 x nx][flags lo][flags
+ * hi][error], as mkb_runtime.cu lays it out), neighbours connected by plain
+ * pointers. Slabs take each step one after the other: a slab's wait for its
+ * neighbour's row of step n is satisfied by the neighbour's step n - 1, which
+ * has already run — the same protocol as on the GPUs, minus the concurrency.
+ */
+namespace {
+
+struct Slab {
+    size_t iy0, ny, n, stride;
+    std::vector<Real> state, v_alt, idiff, inter, field, gxf, gyf;
+    std::vector<unsigned char> mask;
+    std::vector<char> xchg;
+    MkbGridArgs g;
+};
+
+}   // namespace
+
+extern "C" int shim_run_slabs(
+    int nx, int ny, int n_slabs, const int* row0, const int* row1,
+    int n_state, int i_vm, int n_inter, int n_field, int diffusion_mode,
+    double gx, double gy, const double* gx_field, const double* gy_field,
+    long long px0, long long px1, long long py0, long long py1, const unsigned char* paced_mask,
+    int n_steps, const double* st_time, const double* st_dt, const double* st_pace,
+    const unsigned char* st_log,
+    double* state_aos, const double* field_aos, double* log_v, double* log_idiff,
+    int block_x, int block_y, unsigned int* halo_error_out)
+{
+    const size_t ntot = (size_t)nx * ny;
+    const size_t nbx = ((size_t)nx + block_x - 1) / block_x;
+    const size_t halo = 3 * (size_t)nx * sizeof(Real);
+    const size_t flags = nbx * sizeof(unsigned int);
+    std::vector<Slab> slabs(n_slabs);
+    for (int r = 0; r < n_slabs; r++) {
+        Slab& s = slabs[r];
+        s.iy0 = row0[r];
+        s.ny = row1[r] - row0[r];
+        s.n = s.ny * nx;
+        s.stride = (s.n + 31) / 32 * 32;
+        s.state.assign((size_t)n_state * s.stride, (Real)0);
+        s.v_alt.assign(s.stride, (Real)0);
+        s.idiff.assign(s.stride, (Real)0);
+        s.inter.assign((size_t)(n_inter > 0 ? n_inter : 1) * s.stride, (Real)0);
+        s.field.assign((size_t)(n_field > 0 ? n_field : 1) * s.stride, (Real)0);
+        const size_t c0 = s.iy0 * nx;
+        for (size_t c = 0; c < s.n; c++) {
+            for (int k = 0; k < n_state; k++) s.state[(size_t)k * s.stride + c] = (Real)state_aos[(c0 + c) * n_state + k];
+            for (int k = 0; k < n_field; k++) s.field[(size_t)k * s.stride + c] = (Real)field_aos[(c0 + c) * n_field + k];
+        }
+        if (gx_field) {
+            const size_t ngx = s.ny * (nx > 1 ? nx - 1 : 0);
+            s.gxf.assign(ngx + 1, (Real)0);
+            for (size_t k = 0; k < ngx; k++) s.gxf[k] = (Real)gx_field[s.iy0 * (nx - 1) + k];
+        }
+        if (gy_field) {
+            // local row q <- global gy row iy0 - 1 + q; rows that do not exist stay zero
+            s.gyf.assign((s.ny + 1) * nx, (Real)0);
+            for (size_t q = 0; q <= s.ny; q++) {
+                const long long j = (long long)s.iy0 - 1 + (long long)q;
+                if (j < 0 || j > (long long)ny - 2) continue;
+                for (int x = 0; x < nx; x++) s.gyf[q * nx + x] = (Real)gy_field[(size_t)j * nx + x];
+            }
+        }
+        if (paced_mask) s.mask.assign(paced_mask + c0, paced_mask + c0 + s.n);
+        s.xchg.assign(2 * halo + 2 * flags + 64, 0);
+    }
+    for (int r = 0; r < n_slabs; r++) {
+        Slab& s = slabs[r];
+        MkbGridArgs& g = s.g;
+        memset(&g, 0, sizeof(g));
+        g.state = s.state.data();
+        g.idiff = s.idiff.data();
+        g.inter = s.inter.data();
+        g.field = s.field.data();
+        g.gx_field = gx_field ? s.gxf.data() : nullptr;
+        g.gy_field = gy_field ? s.gyf.data() + nx : nullptr;
+        g.paced_mask = paced_mask ? s.mask.data() : nullptr;
+        g.nx = nx;
+        g.ny = s.ny;
+        g.stride = s.stride;
+        g.iy_offset = s.iy0;
+        g.ny_global = ny;
+        g.gx = gx;
+        g.gy = gy;
+        g.pace_x0 = px0; g.pace_x1 = px1; g.pace_y0 = py0; g.pace_y1 = py1;
+        char* b = s.xchg.data();
+        const bool has_lo = r > 0, has_hi = r + 1 < n_slabs;
+        g.halo_lo = has_lo ? b : nullptr;
+        g.halo_hi = has_hi ? b + halo : nullptr;
+        g.flag_lo = (const unsigned int*)(b + 2 * halo);
+        g.flag_hi = (const unsigned int*)(b + 2 * halo + flags);
+        g.halo_error = (unsigned int*)(b + 2 * halo + 2 * flags);
+        if (has_lo) {
+            char* pb = slabs[r - 1].xchg.data();
+            g.peer_lo_halo_hi = pb + halo;
+            g.peer_lo_flag_hi = (unsigned int*)(pb + 2 * halo + flags);
+        }
+        if (has_hi) {
+            char* pb = slabs[r + 1].xchg.data();
+            g.peer_hi_halo_lo = pb;
+            g.peer_hi_flag_lo = (unsigned int*)(pb + 2 * halo);
+        }
+    }
+    // seed: V(t0) of the boundary rows into the neighbours' slot of step 1
+    for (int r = 0; r < n_slabs; r++) {
+        Slab& s = slabs[r];
+        const Real* v = s.state.data() + (size_t)i_vm * s.stride;
+        if (s.g.peer_lo_halo_hi) {
+            memcpy((Real*)s.g.peer_lo_halo_hi + 1 * (size_t)nx, v, nx * sizeof(Real));
+            for (size_t k = 0; k < nbx; k++) s.g.peer_lo_flag_hi[k] = 1u;
+        }
+        if (s.g.peer_hi_halo_lo) {
+            memcpy((Real*)s.g.peer_hi_halo_lo + 1 * (size_t)nx, v + (s.ny - 1) * nx, nx * sizeof(Real));
+            for (size_t k = 0; k < nbx; k++) s.g.peer_hi_flag_lo[k] = 1u;
+        }
+    }
+
+    if (getenv("SHIM_DEBUG")) {
+        for (int r = 0; r < n_slabs; r++) {
+            Slab& s = slabs[r];
+            fprintf(stderr, "slab %d iy0 %zu ny %zu halo_lo %p halo_hi %p peer_lo_halo_hi %p peer_hi_halo_lo %p\n", r, s.iy0, s.ny,
+                    s.g.halo_lo, s.g.halo_hi, s.g.peer_lo_halo_hi, s.g.peer_hi_halo_lo);
+            if (s.g.halo_hi) for (int x = 0; x < nx; x++) fprintf(stderr, " %g", (double)((const Real*)s.g.halo_hi)[nx + x]);
+            fprintf(stderr, "\n");
+        }
+    }
+    blockDim.x = block_x; blockDim.y = block_y; blockDim.z = 1;
+    std::vector<Fiber> fibers((size_t)block_x * block_y);
+    std::vector<char> stacks((size_t)block_x * block_y * kStack);
+    int parity = 0;
+    size_t row_out = 0;
+    for (int st = 0; st < n_steps; st++) {
+        MkbStepParams sp;
+        sp.time = st_time[st];
+        sp.dt = st_dt[st];
+        sp.pace = st_pace[st];
+        sp.flags = st_log[st] ? MKB_FLAG_STORE_AUX : 0u;
+        sp.step = (unsigned int)(st + 1);
+        for (int r = 0; r < n_slabs; r++) {
+            Slab& s = slabs[r];
+            Real* v_main = s.state.data() + (size_t)i_vm * s.stride;
+            const Real* v_in = parity ? s.v_alt.data() : v_main;
+            Real* v_out = parity ? v_main : s.v_alt.data();
+            if (st_log[st] && log_v) {
+                for (size_t c = 0; c < s.n; c++) log_v[row_out * ntot + s.iy0 * nx + c] = (double)v_in[c];
+            }
+            const unsigned long long by_blocks = (s.ny + block_y - 1) / block_y;
+            gridDim.x = (unsigned int)nbx;
+            gridDim.y = (unsigned int)(by_blocks < 32768 ? by_blocks : 32768);
+            gridDim.z = (unsigned int)((by_blocks + gridDim.y - 1) / gridDim.y);
+            g_launch.g = s.g;
+            g_launch.sp = &sp;
+            g_launch.v_in = v_in;
+            g_launch.v_out = v_out;
+            for (unsigned int bz = 0; bz < gridDim.z; bz++) {
+                for (unsigned int by = 0; by < gridDim.y; by++) {
+                    for (unsigned int bx = 0; bx < gridDim.x; bx++) {
+                        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                        run_block(fibers, stacks, (unsigned int)block_x, (unsigned int)block_y);
+                    }
+                }
+            }
+            if (st_log[st] && log_idiff) {
+                for (size_t c = 0; c < s.n; c++) log_idiff[row_out * ntot + s.iy0 * nx + c] = (double)s.idiff[c];
+            }
+        }
+        if (st_log[st]) row_out++;
+        parity ^= 1;
+    }
+    unsigned int err = 0;
+    for (int r = 0; r < n_slabs; r++) {
+        Slab& s = slabs[r];
+        if (parity) memcpy(s.state.data() + (size_t)i_vm * s.stride, s.v_alt.data(), s.n * sizeof(Real));
+        const size_t c0 = s.iy0 * nx;
+        for (size_t c = 0; c < s.n; c++) {
+            for (int k = 0; k < n_state; k++) state_aos[(c0 + c) * n_state + k] = (double)s.state[(size_t)k * s.stride + c];
+        }
+        err |= *s.g.halo_error;
+    }
+    if (halo_error_out) *halo_error_out = err;
     return 0;
 }

@@ -186,3 +186,57 @@ def test_lr91_fp32_default_options():
     assert got['real_size'] == 4
     # fp32 with fast division / FMA contraction: close, not identical
     assert np.abs(got['V'] - want['membrane.V']).max() <= 5e-2
+
+
+# ---------------------------------------------------------------------------
+# Thread order: nothing may depend on the order in which the threads of a block
+# reach a barrier. The shim can run them first-to-last or last-to-first.
+# (Found this way: threads beyond the last row used to write their — unused —
+# centre value into the tile slot that holds the halo of the row below them;
+# harmless on one GPU, a write-write race with the ghost row in a row slab
+# whose height is not a multiple of the block height.)
+# ---------------------------------------------------------------------------
+def test_results_do_not_depend_on_thread_order():
+    def make(cls):
+        return lr91_2d(cls, nx=10, ny=7)
+    runs = []
+    for reverse in (False, True):
+        a = make(myokit_b200.SimulationCUDA)
+        a.set_kernel_options(**dict(EXACT, block=(8, 4)))
+        runs.append(cuda_shim.run_on_host(a, 3.0, log_interval=0.5, reverse=reverse))
+    assert np.array_equal(runs[0]['V'], runs[1]['V'])
+    assert np.array_equal(runs[0]['state'], runs[1]['state'])
+
+    def make(cls):
+        return lr91_2d(cls, nx=20, ny=11)
+    runs = []
+    for reverse in (False, True):
+        a = make(myokit_b200.SimulationCUDA)
+        a.set_kernel_options(**dict(EXACT, block=(4, 2), cells_per_thread=2,
+                                    rows_per_thread=4))
+        runs.append(cuda_shim.run_on_host(a, 3.0, log_interval=0.5, reverse=reverse))
+    assert runs[0]['V'].max() > 0
+    assert np.array_equal(runs[0]['V'], runs[1]['V'])
+    assert np.array_equal(runs[0]['state'], runs[1]['state'])
+
+
+@pytest.mark.parametrize('lean', [False, True], ids=['slab', 'slab_lean'])
+@pytest.mark.parametrize('nslab', [2, 3])
+def test_row_slab_kernels_equal_the_whole_grid(nslab, lean):
+    # 11 rows: slab heights 5/6 or 3/4/4 under 4-row thread blocks, so every
+    # slab has a partial last block row; conductance fields cross the cuts
+    def make(comm):
+        kw = {} if comm is None else dict(comm=comm)
+        return workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=12, ny=11, **kw)
+    opts = dict(EXACT, block=(8, 4))
+    whole = make(None)
+    whole.set_kernel_options(**opts)
+    one = cuda_shim.run_on_host(whole, 3.0, log_interval=0.5)
+    assert one['V'].max() > 0
+    for reverse in (False, True):
+        out = cuda_shim.run_slabs_on_host(make, nslab, 3.0, 0.5,
+                                          dict(opts, slab_lean=lean), reverse=reverse)
+        assert out['halo_error'] == 0
+        assert np.array_equal(out['V'], one['V'])
+        assert np.array_equal(out['idiff'], one['idiff'])
+        assert np.array_equal(out['state'], one['state'])
