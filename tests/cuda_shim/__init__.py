@@ -228,3 +228,143 @@ def run_slabs_on_host(make, n_slabs, duration, log_interval=1.0, options=None,
         'steps': len(times), 'state': state.reshape(n, src.n_state),
         'halo_error': int(err.value),
     }
+
+
+def run_parts_on_host(make, n_parts, duration, log_interval=1.0, options=None,
+                      reverse=False):
+    """
+    Partitioned ``set_connections`` graphs on the host: ``make(comm)`` builds
+    the simulation on every rank of an ``n_parts`` job; the partitions (the
+    product's own ``_partition_graph``) are stepped in lockstep in this
+    process, the exported V pushed into the other partitions' ghost planes
+    between steps like ``k_push_ghosts`` does. Returns ``time``, ``V``
+    (nt, ncells, global cell order), ``idiff``, ``state``, ``halo_error``.
+    """
+    from myokit_b200 import multigpu
+    options = options or {}
+    ranks = [None] * n_parts
+
+    def work(comm):
+        s = make(comm)
+        s.set_kernel_options(**options)
+        src = s.kernel_source()
+        ci, cj, cg, ghost_ids = s._partition_graph()
+        ranks[comm.rank] = dict(
+            sim=s, src=src, x0=s._sx0, n=s._snx, ci=ci, cj=cj, cg=cg,
+            ghost_ids=ghost_ids, state=np.array(s._state, dtype=np.float64),
+            fields=[np.asarray(s._local_slice(f), dtype=np.float64).ravel()
+                    for f in s._fields.values()])
+    multigpu.run_threads(n_parts, work)
+    src = ranks[0]['src']
+    assert 'g.ghost' in src.code            # the partitioned variant
+    lib = _compile(src.code, '--fmad=true' in src.options)
+    lib.shim_set_thread_order(1 if reverse else 0)
+    lib.shim_part_create.restype = ctypes.c_void_p
+    lib.shim_part_ghost.restype = ctypes.c_void_p
+    lib.shim_part_flags.restype = ctypes.c_void_p
+    lib.shim_part_error.restype = ctypes.c_uint
+    real = np.float32 if lib.shim_real_size() == 4 else np.float64
+    whole = ranks[0]['sim']
+    ntot = whole._nx
+    times, dts, paces, logging = schedule(whole, duration, log_interval)
+
+    def ptr(a):
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    keep = []
+    for r, d in enumerate(ranks):
+        s = d['sim']
+        # ranks that own ghost cells of this partition raise a flag here
+        imp = [q for q, e in enumerate(ranks) if q != r and len(d['ghost_ids'])
+               and np.any((d['ghost_ids'] >= e['x0']) & (d['ghost_ids'] < e['x0'] + e['n']))]
+        imp = np.array(imp, dtype=np.uint32)
+        px0 = px1 = 0
+        mask = None
+        if type(s._paced_cells) == tuple:
+            pnx, pny, px, py = s._paced_cells
+            px0, px1 = px - d['x0'], px - d['x0'] + pnx
+        else:
+            mask = np.zeros(d['n'], dtype=np.uint8)
+            pc = np.array(s._paced_cells, dtype=np.int64)
+            pc = pc[(pc >= d['x0']) & (pc < d['x0'] + d['n'])] - d['x0']
+            mask[pc] = 1
+        field_aos = (np.ascontiguousarray(np.vstack(d['fields']).T).ravel()
+                     if d['fields'] else np.zeros(1))
+        ci = np.ascontiguousarray(d['ci'], dtype=np.uint64)
+        cj = np.ascontiguousarray(d['cj'], dtype=np.uint64)
+        cg = np.ascontiguousarray(d['cg'], dtype=np.float64)
+        keep += [imp, mask, field_aos, ci, cj, cg]
+        h = lib.shim_part_create(
+            ctypes.c_ulonglong(d['n']), ctypes.c_int(src.n_state),
+            ctypes.c_int(src.i_vm), ctypes.c_int(src.n_inter),
+            ctypes.c_int(src.n_field), ctypes.c_ulonglong(len(ci)),
+            ptr(ci), ptr(cj), ptr(cg),
+            ctypes.c_ulonglong(len(d['ghost_ids'])), ctypes.c_int(n_parts),
+            ctypes.c_int(len(imp)), ptr(imp) if len(imp) else None,
+            ctypes.c_longlong(px0), ctypes.c_longlong(px1), ptr(mask),
+            ptr(d['state']), ptr(field_aos), ctypes.c_int(src.block[0]))
+        d['h'] = ctypes.c_void_p(h)
+        ng = max(len(d['ghost_ids']), 1)
+        d['ghost'] = np.ctypeslib.as_array(
+            ctypes.cast(lib.shim_part_ghost(d['h']), ctypes.POINTER(
+                ctypes.c_float if real is np.float32 else ctypes.c_double)),
+            shape=(3, ng))
+        d['flags'] = np.ctypeslib.as_array(
+            ctypes.cast(lib.shim_part_flags(d['h']), ctypes.POINTER(ctypes.c_uint)),
+            shape=(n_parts,))
+        d['v'] = np.zeros(d['n'])
+    # export lists: cells of partition r that are ghost cells of partition q
+    for r, d in enumerate(ranks):
+        d['exports'] = []
+        for q, e in enumerate(ranks):
+            if q == r:
+                continue
+            ids = e['ghost_ids']
+            sel = np.nonzero((ids >= d['x0']) & (ids < d['x0'] + d['n']))[0]
+            if len(sel):
+                d['exports'].append((q, ids[sel] - d['x0'], sel))
+
+    def push(r, step):
+        d = ranks[r]
+        lib.shim_part_v(d['h'], ptr(d['v']))
+        for q, src_cells, slots in d['exports']:
+            ranks[q]['ghost'][step % 3, slots] = d['v'][src_cells]
+        for q, e in enumerate(ranks):
+            if q != r and any(x[0] == q for x in d['exports']):
+                e['flags'][r] = step
+
+    for r in range(n_parts):
+        push(r, 1)                          # seed: V(t0) for step 1
+    nrows = int(logging.sum())
+    log_v = np.zeros((nrows, ntot))
+    log_idiff = np.zeros((nrows, ntot))
+    row = 0
+    tmp = None
+    for k in range(len(times)):
+        step = k + 1
+        for r, d in enumerate(ranks):
+            if logging[k]:
+                lib.shim_part_v(d['h'], ptr(d['v']))
+                log_v[row, d['x0']:d['x0'] + d['n']] = d['v']
+            lib.shim_part_step(d['h'], ctypes.c_double(times[k]),
+                               ctypes.c_double(dts[k]), ctypes.c_double(paces[k]),
+                               ctypes.c_int(int(logging[k])), ctypes.c_uint(step))
+            if logging[k]:
+                tmp = np.zeros(d['n'])
+                lib.shim_part_idiff(d['h'], ptr(tmp))
+                log_idiff[row, d['x0']:d['x0'] + d['n']] = tmp
+            push(r, step + 1)
+        if logging[k]:
+            row += 1
+    err = 0
+    state = np.zeros((ntot, src.n_state))
+    for d in ranks:
+        err |= lib.shim_part_error(d['h'])
+        out = np.zeros(d['n'] * src.n_state)
+        d.pop('ghost')
+        d.pop('flags')
+        lib.shim_part_finish(d['h'], ptr(out))
+        state[d['x0']:d['x0'] + d['n']] = out.reshape(d['n'], src.n_state)
+    del keep
+    return {'time': times[logging.astype(bool)], 'V': log_v, 'idiff': log_idiff,
+            'state': state, 'halo_error': int(err), 'steps': len(times)}

@@ -421,3 +421,151 @@ extern "C" int shim_run_slabs(
     if (halo_error_out) *halo_error_out = err;
     return 0;
 }
+
+
+/*
+ * Partitioned connection graphs: one handle per partition, stepped from Python
+ * in lockstep (the push of the exported V into the other partitions' ghost
+ * planes and the flag updates are done by the caller between steps, as
+ * k_push_ghosts does on the GPU).
+ */
+namespace {
+
+struct Part {
+    size_t n, n_ghost, stride;
+    int n_state, i_vm, block_x;
+    std::vector<Real> state, v_alt, idiff, inter, field, ghost, cg;
+    std::vector<unsigned long long> row;
+    std::vector<unsigned int> col, flags, import;
+    std::vector<unsigned char> mask;
+    unsigned int error = 0;
+    int parity = 0;
+    MkbGridArgs g;
+};
+
+}   // namespace
+
+extern "C" void* shim_part_create(
+    unsigned long long n, int n_state, int i_vm, int n_inter, int n_field,
+    unsigned long long n_conn, const unsigned long long* ci, const unsigned long long* cj, const double* cgd,
+    unsigned long long n_ghost, int n_ranks, int n_import, const unsigned int* import_ranks,
+    long long px0, long long px1, const unsigned char* paced_mask,
+    const double* state_aos, const double* field_aos, int block_x)
+{
+    Part* p = new Part();
+    p->n = n;
+    p->n_ghost = n_ghost;
+    p->stride = (n + 31) / 32 * 32;
+    p->n_state = n_state;
+    p->i_vm = i_vm;
+    p->block_x = block_x;
+    p->state.assign((size_t)n_state * p->stride, (Real)0);
+    p->v_alt.assign(p->stride, (Real)0);
+    p->idiff.assign(p->stride, (Real)0);
+    p->inter.assign((size_t)(n_inter > 0 ? n_inter : 1) * p->stride, (Real)0);
+    p->field.assign((size_t)(n_field > 0 ? n_field : 1) * p->stride, (Real)0);
+    for (size_t c = 0; c < n; c++) {
+        for (int k = 0; k < n_state; k++) p->state[(size_t)k * p->stride + c] = (Real)state_aos[c * n_state + k];
+        for (int k = 0; k < n_field; k++) p->field[(size_t)k * p->stride + c] = (Real)field_aos[c * n_field + k];
+    }
+    // CSR as mkb_runtime.cu builds it: per-cell order = edge-list order; an
+    // endpoint >= n is a ghost cell and only contributes to its local end
+    p->row.assign(n + 1, 0);
+    for (unsigned long long e = 0; e < n_conn; e++) {
+        p->row[ci[e] + 1]++;
+        if (cj[e] < n) p->row[cj[e] + 1]++;
+    }
+    for (size_t i = 0; i < n; i++) p->row[i + 1] += p->row[i];
+    p->col.assign(2 * n_conn + 1, 0);
+    p->cg.assign(2 * n_conn + 1, (Real)0);
+    std::vector<unsigned long long> fill(p->row.begin(), p->row.end() - 1);
+    for (unsigned long long e = 0; e < n_conn; e++) {
+        const unsigned long long i = ci[e], j = cj[e];
+        p->col[fill[i]] = (unsigned int)j;
+        p->cg[fill[i]++] = (Real)cgd[e];
+        if (j < n) {
+            p->col[fill[j]] = (unsigned int)i;
+            p->cg[fill[j]++] = (Real)cgd[e];
+        }
+    }
+    p->ghost.assign(3 * (n_ghost ? n_ghost : 1), (Real)0);
+    p->flags.assign(n_ranks > 0 ? n_ranks : 1, 0u);
+    p->import.assign(import_ranks, import_ranks + n_import);
+    if (paced_mask) p->mask.assign(paced_mask, paced_mask + n);
+    MkbGridArgs& g = p->g;
+    memset(&g, 0, sizeof(g));
+    g.state = p->state.data();
+    g.idiff = p->idiff.data();
+    g.inter = p->inter.data();
+    g.field = p->field.data();
+    g.paced_mask = paced_mask ? p->mask.data() : nullptr;
+    g.csr_row = p->row.data();
+    g.csr_col = p->col.data();
+    g.csr_g = p->cg.data();
+    g.ghost = n_ghost ? p->ghost.data() : nullptr;
+    g.n_ghost = n_ghost;
+    g.ghost_flags = p->flags.data();
+    g.ghost_import = p->import.data();
+    g.n_ghost_import = (unsigned long long)n_import;
+    g.halo_error = &p->error;
+    g.nx = n;
+    g.ny = 1;
+    g.stride = p->stride;
+    g.iy_offset = 0;
+    g.ny_global = 1;
+    g.pace_x0 = px0; g.pace_x1 = px1; g.pace_y0 = 0; g.pace_y1 = 1;
+    return p;
+}
+
+extern "C" void* shim_part_ghost(void* h) { return ((Part*)h)->ghost.data(); }
+extern "C" void* shim_part_flags(void* h) { return ((Part*)h)->flags.data(); }
+extern "C" unsigned int shim_part_error(void* h) { return ((Part*)h)->error; }
+
+// V(t) of the partition's cells: what the next step will read
+extern "C" void shim_part_v(void* h, double* out) {
+    Part* p = (Part*)h;
+    const Real* v = p->parity ? p->v_alt.data() : p->state.data() + (size_t)p->i_vm * p->stride;
+    for (size_t c = 0; c < p->n; c++) out[c] = (double)v[c];
+}
+extern "C" void shim_part_idiff(void* h, double* out) {
+    Part* p = (Part*)h;
+    for (size_t c = 0; c < p->n; c++) out[c] = (double)p->idiff[c];
+}
+
+extern "C" void shim_part_step(void* h, double time, double dt, double pace, int logging, unsigned int step) {
+    Part* p = (Part*)h;
+    MkbStepParams sp;
+    sp.time = time;
+    sp.dt = dt;
+    sp.pace = pace;
+    sp.flags = logging ? MKB_FLAG_STORE_AUX : 0u;
+    sp.step = step;
+    Real* v_main = p->state.data() + (size_t)p->i_vm * p->stride;
+    g_launch.g = p->g;
+    g_launch.sp = &sp;
+    g_launch.v_in = p->parity ? p->v_alt.data() : v_main;
+    g_launch.v_out = p->parity ? v_main : p->v_alt.data();
+    blockDim.x = p->block_x; blockDim.y = 1; blockDim.z = 1;
+    gridDim.x = (unsigned int)((p->n + p->block_x - 1) / p->block_x);
+    gridDim.y = gridDim.z = 1;
+    static std::vector<Fiber> fibers;
+    static std::vector<char> stacks;
+    if (fibers.size() < (size_t)p->block_x) {
+        fibers.resize(p->block_x);
+        stacks.resize((size_t)p->block_x * kStack);
+    }
+    for (unsigned int bx = 0; bx < gridDim.x; bx++) {
+        blockIdx.x = bx; blockIdx.y = 0; blockIdx.z = 0;
+        run_block(fibers, stacks, (unsigned int)p->block_x, 1);
+    }
+    p->parity ^= 1;
+}
+
+extern "C" void shim_part_finish(void* h, double* state_aos) {
+    Part* p = (Part*)h;
+    if (p->parity) memcpy(p->state.data() + (size_t)p->i_vm * p->stride, p->v_alt.data(), p->n * sizeof(Real));
+    for (size_t c = 0; c < p->n; c++) {
+        for (int k = 0; k < p->n_state; k++) state_aos[c * p->n_state + k] = (double)p->state[(size_t)k * p->stride + c];
+    }
+    delete p;
+}

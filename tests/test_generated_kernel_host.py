@@ -240,3 +240,31 @@ def test_row_slab_kernels_equal_the_whole_grid(nslab, lean):
         assert np.array_equal(out['V'], one['V'])
         assert np.array_equal(out['idiff'], one['idiff'])
         assert np.array_equal(out['state'], one['state'])
+
+
+@pytest.mark.parametrize('nparts', [2, 3])
+def test_partitioned_graph_kernels_equal_the_whole_graph(nparts):
+    # a small fibre mesh with long-range edges, cut into contiguous id blocks
+    # by the product's own _partition_graph; ghost planes and flags on the host
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)
+    n, edges = workloads.fibre_mesh(6, 4, 5, extra=0.1, seed=3)
+
+    def make(comm):
+        kw = {} if comm is None else dict(comm=comm)
+        s = myokit_b200.SimulationCUDA(m, p, ncells=n, precision=DP, **kw)
+        s.set_connections(edges)
+        s.set_paced_cells(12)
+        return s
+    opts = dict(EXACT, block=(16, 1))
+    whole = make(None)
+    whole.set_kernel_options(**opts)
+    one = cuda_shim.run_on_host(whole, 5.0, log_interval=0.5)
+    assert one['V'].max() > 0
+    for reverse in (False, True):
+        out = cuda_shim.run_parts_on_host(make, nparts, 5.0, 0.5, opts,
+                                          reverse=reverse)
+        assert out['halo_error'] == 0
+        assert np.array_equal(out['V'], one['V'])
+        assert np.array_equal(out['idiff'], one['idiff'])
+        assert np.array_equal(out['state'], one['state'])
