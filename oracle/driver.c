@@ -473,3 +473,105 @@ done:
     free(gxf); free(gyf); free(cg); free(snap_state);
     return rc;
 }
+
+/* -------------------------------------------------------------------------
+ * Step-wise entry points for coupled runs (oracle/fiber_tissue.py): the
+ * fibre-tissue simulation (myokit/_sim/fiber_tissue.c:1001-1155) steps two
+ * grids with two models and one pacing system, so its loop lives in Python
+ * and calls the pieces of one model's library. Arrays are `Real`.
+ * ------------------------------------------------------------------------- */
+
+/* diff_step for every cell: fiber_tissue.c:1031-1032 (openclsim.cl:384-435) */
+void oracle_k_diff(size_t nx, size_t ny, double gx_in, double gy_in,
+                   const Real* state, Real* idiff)
+{
+    const Real gx = (Real)gx_in, gy = (Real)gy_in;
+    long ic;
+    for (ic = 0; ic < (long)(nx * ny); ic++) {
+        const size_t ix = (size_t)ic % nx, iy = (size_t)ic / nx;
+#ifdef ORACLE_REF_KERNEL
+        cl_set_gid(ix, iy);
+        diff_step(nx, ny, gx, gy, state, idiff);
+#else
+        diff_step_cell(ix, iy, nx, ny, gx, gy, (Real*)state, idiff);
+#endif
+    }
+}
+
+/* diff_step_fiber_tissue: fiber_tissue.c:1033 (openclsim.cl:601-628). Called
+ * on the FIBRE model's library; nst / ivt describe the tissue's state vector. */
+void oracle_k_junction(size_t nfx, size_t nfy, size_t ntx, size_t ctx, size_t cty,
+                       size_t nst, int ivt, double gft_in,
+                       const Real* state_f, const Real* state_t,
+                       Real* idiff_f, Real* idiff_t)
+{
+    const Real gft = (Real)gft_in;
+    size_t cid;
+#if defined(ORACLE_REF_KERNEL) && defined(ORACLE_REF_FT)
+    for (cid = 0; cid < nfy; cid++) {
+        cl_set_gid(cid, 0);
+        diff_step_fiber_tissue(nfx, nfy, ntx, ctx, cty, N_STATE, nst, I_VM, ivt, gft,
+                               state_f, state_t, idiff_f, idiff_t);
+    }
+#else
+    for (cid = 0; cid < nfy; cid++) {
+        const size_t iff = (nfx - 1) + cid * nfx;
+        const size_t ift = ctx + (cty + cid) * ntx;
+        const Real i = gft * (state_f[iff * N_STATE + I_VM] - state_t[ift * nst + ivt]);
+        idiff_f[iff] += i;
+        idiff_t[ift] -= i;
+    }
+#endif
+}
+
+/* cell_step for every cell: fiber_tissue.c:1055-1062 */
+void oracle_k_cells(size_t nx, size_t ny, double time_in, double dt_in, double pace_in,
+                    const unsigned char* paced, Real* state, const Real* idiff,
+                    Real* inter_log, const Real* field_data)
+{
+    const Real arg_time = (Real)time_in, arg_dt = (Real)dt_in, arg_pace = (Real)pace_in;
+    long ic;
+    for (ic = 0; ic < (long)(nx * ny); ic++) {
+#ifdef ORACLE_REF_KERNEL
+        cl_set_gid((size_t)ic % nx, (size_t)ic / nx);
+        cell_step(nx, ny, arg_time, arg_dt, arg_pace, state, idiff, inter_log, field_data);
+        (void)paced;
+#else
+        cell_step((size_t)ic, arg_time, arg_dt, paced[ic] ? arg_pace : 0, state,
+                  (Real*)idiff, inter_log, field_data);
+#endif
+    }
+}
+
+/* The pacing system as an object: fiber_tissue.c:473-481, 1135-1139 */
+void* oracle_pacing_new(double t0, int n_events, const double* events, int* rc_out)
+{
+    OPacing* p = (OPacing*)calloc(1, sizeof(OPacing));
+    int rc = o_pacing_init(p, t0, n_events, events);
+    if (!rc) rc = o_pacing_advance(p, t0);
+    *rc_out = rc;
+    return p;
+}
+
+int oracle_pacing_advance(void* h, double t, double* level, double* tnext)
+{
+    OPacing* p = (OPacing*)h;
+    int rc = o_pacing_advance(p, t);
+    *level = p->level;
+    *tnext = p->tnext;
+    return rc;
+}
+
+void oracle_pacing_state(void* h, double* level, double* tnext)
+{
+    OPacing* p = (OPacing*)h;
+    *level = p->level;
+    *tnext = p->tnext;
+}
+
+void oracle_pacing_free(void* h)
+{
+    OPacing* p = (OPacing*)h;
+    if (p) free(p->ev);
+    free(p);
+}

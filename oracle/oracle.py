@@ -100,7 +100,7 @@ def _compile(header_text, tag, ref_kernel, openmp, contract, opt):
 
 def render_reference_kernel(model, precision, bound_variables, inter_log,
                             diffusion, fields, paced_cells, rl_states,
-                            connections, heterogeneous):
+                            connections, heterogeneous, fiber_tissue=False):
     """
     Renders the REFERENCE's ``openclsim.cl`` with the reference's own template
     engine, argument dict as in ``myokit/_sim/openclsim.py:1060-1073``.
@@ -118,7 +118,7 @@ def render_reference_kernel(model, precision, bound_variables, inter_log,
         'rl_states': rl_states,
         'connections': connections,
         'heterogeneous': heterogeneous,
-        'fiber_tissue': False,
+        'fiber_tissue': bool(fiber_tissue),
     }
     e = myokit.pype.TemplateEngine()
     s = io.StringIO()
@@ -129,6 +129,8 @@ def render_reference_kernel(model, precision, bound_variables, inter_log,
     post = ['#define N_STATE n_state', '#define N_INTER n_inter',
             '#define N_FIELD n_field']
     post.append('#define I_VM i_vm' if diffusion else '#define I_VM 0')
+    if fiber_tissue:
+        post.append('#define ORACLE_REF_FT 1')
     if not (diffusion and connections):
         post.append('#define diff_arb_reset(a, b) ((void)0)')
         post.append('#define diff_arb_step(a, b, c, d, e, f) ((void)0)')
