@@ -91,6 +91,18 @@ struct MkbGridArgs {
     double gx, gy;                  /* homogeneous conductances */
     long long pace_x0, pace_x1;     /* paced rectangle [x0,x1) x [y0,y1) */
     long long pace_y0, pace_y1;
+    /* Junction with a second grid stepped in lockstep (fibre-tissue,
+     * myokit/_sim/openclsim.cl:601-628). Cells (jx, jy0 + k), k < jn, of this
+     * grid are coupled with conductance jg to element joff + k * jstride of the
+     * other grid's V(t) plane: junction_v0 when this grid reads its first V
+     * plane, junction_v1 when it reads its second (both grids swap planes
+     * every step). Kernels generated with junction='fiber' add
+     * jg * (V - Vother) to idiff, junction='tissue' subtract jg * (Vother - V).
+     * All zero / null on ordinary simulations. */
+    const void* junction_v0;
+    const void* junction_v1;
+    double jg;
+    unsigned long long jx, jy0, jn, joff, jstride;
 };
 
 #endif

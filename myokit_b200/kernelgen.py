@@ -576,7 +576,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              lazy_state=True, min_blocks=None, fast_exp=False,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
              rows_per_thread=1, div_int_check=False, partitioned=False,
-             const_div=True, slab_lean=False, div_parallel=False):
+             const_div=True, slab_lean=False, div_parallel=False,
+             junction=None):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -619,6 +620,12 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         Connection graphs cut over several GPUs: CSR columns beyond the local
         cells are ghost cells whose V is read from the ghost buffer the
         owning GPUs push into.
+    ``junction``
+        ``'fiber'`` or ``'tissue'``: the kernel of one of two grids stepped in
+        lockstep (``FiberTissueSimulationCUDA``); cells on the junction add
+        the current to / from the other grid's cell to ``idiff`` after their
+        own stencil, as ``diff_step_fiber_tissue`` does
+        (``openclsim.cl:601-628``). Homogeneous 2-d grids, one cell per thread.
     ``div_parallel``
         ``mkb_div`` refines quotient and reciprocal side by side: a shorter
         dependent chain, and IEEE results for divisors 0 and inf. Same
@@ -658,7 +665,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     slab = bool(slab) and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD)
     cpt = int(cells_per_thread or 1)
     if slab or diffusion_mode == DIFF_CONNECTIONS or cpt not in (2, 4, 8) \
-            or (sp and cpt == 2):
+            or (sp and cpt == 2) or junction:
         cpt = 1
     if cpt > 1 and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
         # rim-exchange arrays of the register-patch path (static shared memory)
@@ -669,6 +676,12 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 'Tile too large: block %dx%d with cells_per_thread=%d,'
                 ' rows_per_thread=%d needs %d bytes of shared memory for its'
                 ' rim exchange (limit 49152).' % (bx, by, cpt, rpt_, smem))
+
+    if junction not in (None, 'fiber', 'tissue'):
+        raise ValueError('junction must be None, "fiber" or "tissue".')
+    if junction and (diffusion_mode != DIFF_HOMOGENEOUS or slab or cpt > 1):
+        raise ValueError('A junction needs a homogeneous grid kernel with one'
+                         ' cell per thread.')
 
     equations = model.solvable_order()
     del equations['*remaining*']
@@ -1322,6 +1335,18 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('        else if (iyg == nyg - 1) idiff += gy * (vc - vym);')
             p('        else idiff += gy * (2 * vc - vym - vyp);')
             p('    }')
+            if junction:
+                p('    // openclsim.cl:617-627 (diff_step_fiber_tissue), this grid\'s side')
+                p('    if (g.junction_v0 && ix == (unsigned int)g.jx && iy >= (unsigned int)g.jy0')
+                p('            && iy < (unsigned int)(g.jy0 + g.jn)) {')
+                p('        const Real* const other = (const Real*)((v_in == (const Real*)g.state + %dull * stride)' % i_vm)
+                p('            ? g.junction_v0 : g.junction_v1);')
+                p('        const Real vo = other[g.joff + (unsigned long long)(iy - (unsigned int)g.jy0) * g.jstride];')
+                if junction == 'fiber':
+                    p('        idiff += (Real)g.jg * (vc - vo);')
+                else:
+                    p('        idiff -= (Real)g.jg * (vo - vc);')
+                p('    }')
         else:
             p('    // openclsim.cl:469-486 (diff_hetero)')
             p('    idiff = 0.0;')

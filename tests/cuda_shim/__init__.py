@@ -368,3 +368,78 @@ def run_parts_on_host(make, n_parts, duration, log_interval=1.0, options=None,
     del keep
     return {'time': times[logging.astype(bool)], 'V': log_v, 'idiff': log_idiff,
             'state': state, 'halo_error': int(err), 'steps': len(times)}
+
+
+def run_pair_on_host(fiber, tissue, g_fiber_tissue, cty, duration,
+                     log_interval=1.0, reverse=False):
+    """
+    Two homogeneous 2-d grids stepped in lockstep on the host, coupled through
+    ``MkbGridArgs::junction_*``: ``fiber`` and ``tissue`` are configured
+    ``SimulationCUDA`` objects whose kernels were generated with
+    ``junction='fiber'`` / ``'tissue'``. The last fibre column is tied to
+    tissue cells ``(0, cty + y)``. Returns ``time`` and, per part, ``V``,
+    ``idiff`` (nt, ny, nx) and ``state``.
+    """
+    parts = []
+    for sim in (fiber, tissue):
+        src = sim.kernel_source()
+        assert 'g.junction_v0' in src.code
+        lib = _compile(src.code, '--fmad=true' in src.options)
+        lib.shim_set_thread_order(1 if reverse else 0)
+        lib.shim_grid_create.restype = ctypes.c_void_p
+        lib.shim_grid_vplane.restype = ctypes.c_void_p
+        nx, ny = sim._nx, sim._ny
+        pnx, pny, px, py = sim._paced_cells
+        state = np.ascontiguousarray(sim._state, dtype=np.float64)
+        h = ctypes.c_void_p(lib.shim_grid_create(
+            ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(src.n_state),
+            ctypes.c_int(src.i_vm), ctypes.c_int(src.n_inter), ctypes.c_int(0),
+            ctypes.c_double(sim._gx), ctypes.c_double(sim._gy),
+            ctypes.c_longlong(px), ctypes.c_longlong(px + pnx),
+            ctypes.c_longlong(py), ctypes.c_longlong(py + pny), None,
+            state.ctypes.data_as(ctypes.c_void_p),
+            np.zeros(1).ctypes.data_as(ctypes.c_void_p),
+            ctypes.c_int(src.block[0]), ctypes.c_int(src.block[1])))
+        parts.append(dict(sim=sim, src=src, lib=lib, h=h, nx=nx, ny=ny,
+                          n=nx * ny))
+    f, t = parts
+    for me, other, jx, jy0, joff, jstride in (
+            (f, t, f['nx'] - 1, 0, 0 + cty * t['nx'], t['nx']),
+            (t, f, 0, cty, f['nx'] - 1, f['nx'])):
+        v0 = other['lib'].shim_grid_vplane(other['h'], 0)
+        v1 = other['lib'].shim_grid_vplane(other['h'], 1)
+        me['lib'].shim_grid_set_junction(
+            me['h'], ctypes.c_void_p(v0), ctypes.c_void_p(v1),
+            ctypes.c_double(g_fiber_tissue), ctypes.c_ulonglong(jx),
+            ctypes.c_ulonglong(jy0), ctypes.c_ulonglong(f['ny']),
+            ctypes.c_ulonglong(joff), ctypes.c_ulonglong(jstride))
+    times, dts, paces, logging = schedule(fiber, duration, log_interval)
+    rows = {0: [], 1: []}
+    for k in range(len(times)):
+        for i, p in enumerate(parts):
+            if logging[k]:
+                v = np.zeros(p['n'])
+                p['lib'].shim_grid_v(p['h'], v.ctypes.data_as(ctypes.c_void_p))
+                rows[i].append([v])
+        # both kernels of a step read V(t) of both grids and write V(t + dt)
+        for i, p in enumerate(parts):
+            p['lib'].shim_grid_step(
+                p['h'], ctypes.c_double(times[k]), ctypes.c_double(dts[k]),
+                ctypes.c_double(paces[k]), ctypes.c_int(int(logging[k])),
+                ctypes.c_uint(k + 1))
+            if logging[k]:
+                d = np.zeros(p['n'])
+                p['lib'].shim_grid_idiff(p['h'], d.ctypes.data_as(ctypes.c_void_p))
+                rows[i][-1].append(d)
+    out = {'time': times[logging.astype(bool)], 'steps': len(times)}
+    for i, name in enumerate(('fiber', 'tissue')):
+        p = parts[i]
+        nt = len(rows[i])
+        state = np.zeros(p['n'] * p['src'].n_state)
+        p['lib'].shim_grid_finish(p['h'], state.ctypes.data_as(ctypes.c_void_p))
+        out[name] = {
+            'V': np.array([r[0] for r in rows[i]]).reshape(nt, p['ny'], p['nx']),
+            'idiff': np.array([r[1] for r in rows[i]]).reshape(nt, p['ny'], p['nx']),
+            'state': state,
+        }
+    return out

@@ -569,3 +569,125 @@ extern "C" void shim_part_finish(void* h, double* state_aos) {
     }
     delete p;
 }
+
+
+/*
+ * One homogeneous grid as a handle, stepped from Python: two of them (two
+ * kernels, two libraries) coupled through MkbGridArgs::junction_* make the
+ * fibre-tissue pair.
+ */
+namespace {
+
+struct Grid {
+    size_t nx, ny, n, stride;
+    int n_state, i_vm, n_inter, block_x, block_y;
+    std::vector<Real> state, v_alt, idiff, inter, field;
+    std::vector<unsigned char> mask;
+    int parity = 0;
+    MkbGridArgs g;
+};
+
+}   // namespace
+
+extern "C" void* shim_grid_create(
+    int nx, int ny, int n_state, int i_vm, int n_inter, int n_field, double gx, double gy,
+    long long px0, long long px1, long long py0, long long py1, const unsigned char* paced_mask,
+    const double* state_aos, const double* field_aos, int block_x, int block_y)
+{
+    Grid* p = new Grid();
+    p->nx = nx; p->ny = ny; p->n = (size_t)nx * ny;
+    p->stride = (p->n + 31) / 32 * 32;
+    p->n_state = n_state; p->i_vm = i_vm; p->n_inter = n_inter;
+    p->block_x = block_x; p->block_y = block_y;
+    p->state.assign((size_t)n_state * p->stride, (Real)0);
+    p->v_alt.assign(p->stride, (Real)0);
+    p->idiff.assign(p->stride, (Real)0);
+    p->inter.assign((size_t)(n_inter > 0 ? n_inter : 1) * p->stride, (Real)0);
+    p->field.assign((size_t)(n_field > 0 ? n_field : 1) * p->stride, (Real)0);
+    for (size_t c = 0; c < p->n; c++) {
+        for (int k = 0; k < n_state; k++) p->state[(size_t)k * p->stride + c] = (Real)state_aos[c * n_state + k];
+        for (int k = 0; k < n_field; k++) p->field[(size_t)k * p->stride + c] = (Real)field_aos[c * n_field + k];
+    }
+    if (paced_mask) p->mask.assign(paced_mask, paced_mask + p->n);
+    MkbGridArgs& g = p->g;
+    memset(&g, 0, sizeof(g));
+    g.state = p->state.data();
+    g.idiff = p->idiff.data();
+    g.inter = p->inter.data();
+    g.field = p->field.data();
+    g.paced_mask = paced_mask ? p->mask.data() : nullptr;
+    g.nx = nx; g.ny = ny; g.stride = p->stride;
+    g.iy_offset = 0; g.ny_global = ny;
+    g.gx = gx; g.gy = gy;
+    g.pace_x0 = px0; g.pace_x1 = px1; g.pace_y0 = py0; g.pace_y1 = py1;
+    return p;
+}
+
+extern "C" void* shim_grid_vplane(void* h, int which) {
+    Grid* p = (Grid*)h;
+    return which ? p->v_alt.data() : p->state.data() + (size_t)p->i_vm * p->stride;
+}
+
+extern "C" void shim_grid_set_junction(void* h, const void* v0, const void* v1, double jg,
+                                       unsigned long long jx, unsigned long long jy0, unsigned long long jn,
+                                       unsigned long long joff, unsigned long long jstride) {
+    Grid* p = (Grid*)h;
+    p->g.junction_v0 = v0;
+    p->g.junction_v1 = v1;
+    p->g.jg = jg;
+    p->g.jx = jx; p->g.jy0 = jy0; p->g.jn = jn; p->g.joff = joff; p->g.jstride = jstride;
+}
+
+extern "C" void shim_grid_step(void* h, double time, double dt, double pace, int logging, unsigned int step) {
+    Grid* p = (Grid*)h;
+    MkbStepParams sp;
+    sp.time = time; sp.dt = dt; sp.pace = pace;
+    sp.flags = logging ? MKB_FLAG_STORE_AUX : 0u;
+    sp.step = step;
+    Real* v_main = p->state.data() + (size_t)p->i_vm * p->stride;
+    g_launch.g = p->g;
+    g_launch.sp = &sp;
+    g_launch.v_in = p->parity ? p->v_alt.data() : v_main;
+    g_launch.v_out = p->parity ? v_main : p->v_alt.data();
+    blockDim.x = p->block_x; blockDim.y = p->block_y; blockDim.z = 1;
+    gridDim.x = (unsigned int)((p->nx + p->block_x - 1) / p->block_x);
+    gridDim.y = (unsigned int)((p->ny + p->block_y - 1) / p->block_y);
+    gridDim.z = 1;
+    static std::vector<Fiber> fibers;
+    static std::vector<char> stacks;
+    const size_t nthreads = (size_t)p->block_x * p->block_y;
+    if (fibers.size() < nthreads) {
+        fibers.resize(nthreads);
+        stacks.resize(nthreads * kStack);
+    }
+    for (unsigned int by = 0; by < gridDim.y; by++) {
+        for (unsigned int bx = 0; bx < gridDim.x; bx++) {
+            blockIdx.x = bx; blockIdx.y = by; blockIdx.z = 0;
+            run_block(fibers, stacks, (unsigned int)p->block_x, (unsigned int)p->block_y);
+        }
+    }
+    p->parity ^= 1;
+}
+
+// V(t) as the next step will read it / idiff and logged intermediaries of the last logged step
+extern "C" void shim_grid_v(void* h, double* out) {
+    Grid* p = (Grid*)h;
+    const Real* v = p->parity ? p->v_alt.data() : p->state.data() + (size_t)p->i_vm * p->stride;
+    for (size_t c = 0; c < p->n; c++) out[c] = (double)v[c];
+}
+extern "C" void shim_grid_idiff(void* h, double* out) {
+    Grid* p = (Grid*)h;
+    for (size_t c = 0; c < p->n; c++) out[c] = (double)p->idiff[c];
+}
+extern "C" void shim_grid_inter(void* h, int k, double* out) {
+    Grid* p = (Grid*)h;
+    for (size_t c = 0; c < p->n; c++) out[c] = (double)p->inter[(size_t)k * p->stride + c];
+}
+extern "C" void shim_grid_finish(void* h, double* state_aos) {
+    Grid* p = (Grid*)h;
+    if (p->parity) memcpy(p->state.data() + (size_t)p->i_vm * p->stride, p->v_alt.data(), p->n * sizeof(Real));
+    for (size_t c = 0; c < p->n; c++) {
+        for (int k = 0; k < p->n_state; k++) state_aos[c * p->n_state + k] = (double)p->state[(size_t)k * p->stride + c];
+    }
+    delete p;
+}

@@ -268,3 +268,61 @@ def test_partitioned_graph_kernels_equal_the_whole_graph(nparts):
         assert np.array_equal(out['V'], one['V'])
         assert np.array_equal(out['idiff'], one['idiff'])
         assert np.array_equal(out['state'], one['state'])
+
+
+# ---------------------------------------------------------------------------
+# Fibre-tissue junction: two kernels, two models, stepped
+# in lockstep, against oracle/fiber_tissue.py (itself pinned against the
+# reference's rendered kernels in tests/test_oracle_fiber_tissue.py).
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('options,exact', [(EXACT, True), ({}, False)],
+                         ids=['exact', 'default'])
+def test_fiber_tissue_junction_kernels(options, exact):
+    import os
+    from oracle.fiber_tissue import OracleFiberTissue
+    data = os.path.join(os.path.dirname(myokit.__file__), 'tests', 'data')
+    mf = myokit.load_model(os.path.join(data, 'dn-1985-normalised.mmt'))
+    mt = myokit.load_model(os.path.join(data, 'lr-1991.mmt'))
+    p = myokit.pacing.blocktrain(1000, 2.0, offset=.01)
+    f = myokit_b200.SimulationCUDA(mf, p, ncells=(8, 4), precision=DP)
+    f.set_conductance(235, 100)
+    f.set_paced_cells(4, 4, 0, 0)
+    f.set_step_size(0.0012)
+    f.set_kernel_options(block=(8, 2), junction='fiber', **options)
+    t = myokit_b200.SimulationCUDA(mt, p, ncells=(8, 6), precision=DP)
+    t.set_conductance(9, 5)
+    t.set_paced_cells(0, 0, 0, 0)
+    t.set_step_size(0.0012)
+    t.set_kernel_options(block=(8, 2), junction='tissue', **options)
+    out = cuda_shim.run_pair_on_host(f, t, 9.0, 1, 3.0, 0.25)
+    o = OracleFiberTissue(
+        mf, mt, p, ncells_fiber=(8, 4), ncells_tissue=(8, 6), nx_paced=4,
+        g_fiber=(235, 100), g_tissue=(9, 5), g_fiber_tissue=9, dt=0.0012,
+        precision=DP)
+    names = ['membrane.V', 'membrane.i_diff']
+    tt, of, ot = o.run(3.0, names, names, 0.25)
+    assert np.array_equal(out['time'], tt)
+    assert ot['membrane.V'].max() > 0       # driven through the junction
+    if exact:
+        assert np.array_equal(out['fiber']['V'], of['membrane.V'])
+        assert np.array_equal(out['fiber']['idiff'], of['membrane.i_diff'])
+        assert np.array_equal(out['tissue']['V'], ot['membrane.V'])
+        assert np.array_equal(out['tissue']['idiff'], ot['membrane.i_diff'])
+        assert np.array_equal(out['fiber']['state'], o.fiber_state())
+        assert np.array_equal(out['tissue']['state'], o.tissue_state())
+    else:
+        assert np.abs(out['fiber']['V'] - of['membrane.V']).max() <= 1e-8
+        assert np.abs(out['tissue']['V'] - ot['membrane.V']).max() <= 1e-8
+
+
+def test_junction_needs_a_plain_homogeneous_kernel():
+    def make(cls):
+        return lr91_2d(cls)
+    s = make(myokit_b200.SimulationCUDA)
+    s.set_kernel_options(junction='sideways')
+    with pytest.raises(ValueError):
+        s.kernel_source()
+    s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=8)
+    s.set_kernel_options(junction='fiber')
+    with pytest.raises(ValueError):
+        s.kernel_source()
