@@ -256,6 +256,19 @@ int mkb_sim_ghost_connect(mkb_sim* sim, uint32_t n_flags, uint32_t n_peers,
                           const mkb_ghost_peer* peers, int direct,
                           uint32_t n_import, const uint32_t* import_flags);
 
+/* ---- fibre-tissue pair (myokit/_sim/fiber_tissue.py:17, fiber_tissue.c:1001-1155) ----
+ * Two homogeneous 2-d simulations (two models, kernels generated with
+ * junction='fiber' / 'tissue') that take every step together: fibre cell
+ * (nfx - 1, k) is tied to tissue cell (0, cty + k), k < nfy, with conductance
+ * g (diff_step_fiber_tissue, myokit/_sim/openclsim.cl:601-628). Both must be
+ * initialised with the same time span, step size, log interval and protocol.
+ * mkb_sim_step_pair replaces mkb_sim_step for the pair: up to `steps` steps of
+ * both, strictly alternating; returns 1 while there is more to do, 0 when both
+ * have finished, < 0 on error; *halted as for mkb_sim_step (either grid). */
+int mkb_sim_junction_connect(mkb_sim* fiber, mkb_sim* tissue, double g, uint64_t cty);
+int mkb_sim_step_pair(mkb_sim* fiber, mkb_sim* tissue, uint64_t steps,
+                      double* engine_time, int* halted);
+
 /* ---- roofline denominators ----
  * Micro-benchmarks of the pipes the cell step is bound by. out6: fp64 FMA
  * Ginstr/s (thread-level), fp32 FMA Ginstr/s, MUFU.EX2 Gop/s, device copy GB/s

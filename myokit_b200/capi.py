@@ -35,6 +35,7 @@ SYMBOLS = [
     'mkb_sim_halo_export', 'mkb_sim_halo_connect', 'mkb_sim_halo_seed',
     'mkb_sim_rearm', 'mkb_measure_peaks', 'mkb_sim_ghost_connect',
     'mkb_pacing_probe', 'mkb_schedule_probe',
+    'mkb_sim_junction_connect', 'mkb_sim_step_pair',
 ]
 
 
@@ -150,6 +151,10 @@ def library():
         c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(GhostPeer),
         ctypes.c_int, ctypes.c_uint32, c_vp]
     lib.mkb_sim_rearm.argtypes = [c_vp, ctypes.POINTER(RunConfig)]
+    lib.mkb_sim_junction_connect.argtypes = [c_vp, c_vp, ctypes.c_double, c_u64]
+    lib.mkb_sim_step_pair.argtypes = [
+        c_vp, c_vp, c_u64, ctypes.POINTER(ctypes.c_double),
+        ctypes.POINTER(ctypes.c_int)]
     lib.mkb_schedule_probe.argtypes = [
         ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
         ctypes.c_int, c_vp, c_u64, c_vp, c_vp, c_vp, c_vp,

@@ -440,6 +440,11 @@ struct mkb_sim {
     unsigned int n_import = 0;
     bool ghosts_connected = false;
 
+    // fibre-tissue pair (mkb_sim_junction_connect): the other grid, and the
+    // event this one records after each of its step kernels
+    mkb_sim* partner = nullptr;
+    cudaEvent_t ev_step = nullptr;
+
     // counters
     u64 launches = 0, steps = 0;
     double device_ms = 0;
@@ -457,6 +462,14 @@ static void sim_destroy(mkb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->side) cudaStreamSynchronize(s->side);
+    if (s->partner) {
+        // the other grid must not wait for, or read from, this one any more
+        if (s->partner->stream) cudaStreamSynchronize(s->partner->stream);
+        s->partner->grid.junction_v0 = s->partner->grid.junction_v1 = nullptr;
+        s->partner->partner = nullptr;
+        s->partner = nullptr;
+    }
+    if (s->ev_step) cudaEventDestroy(s->ev_step);
     cudaFree(s->d_planes);
     cudaFree(s->d_gx);
     cudaFree(s->d_gy);
@@ -1318,7 +1331,7 @@ static int graph_get(mkb_sim* s, int slot, int parity, cudaGraphExec_t* out) {
 }
 
 template <typename TR>
-static int sim_step_typed(mkb_sim* s) {
+static int sim_step_typed(mkb_sim* s, bool drain = true) {
     u64 steps_left = s->steps_per_call;
     bool timing_started = false;
 
@@ -1371,7 +1384,7 @@ static int sim_step_typed(mkb_sim* s) {
         s->ring_chunk++;
 
         for (size_t i = 0; i < s->recs.size(); i++) {
-            if (s->use_graphs && !s->ghosts_connected && i + kGraphSteps <= s->recs.size()) {
+            if (s->use_graphs && !s->ghosts_connected && !s->partner && i + kGraphSteps <= s->recs.size()) {
                 bool plain = true;
                 for (int j = 0; j < kGraphSteps && plain; j++) plain = !s->recs[i + j].logging;
                 if (plain) {
@@ -1433,11 +1446,17 @@ static int sim_step_typed(mkb_sim* s) {
                                              cudaMemcpyDeviceToDevice, s->stream));
                 }
             }
+            if (s->partner) {
+                // the other grid's previous step: it wrote the V(t) plane this
+                // kernel reads and has finished reading the plane it overwrites
+                CUDA_TRY(cudaStreamWaitEvent(s->stream, s->partner->ev_step, 0));
+            }
             // fused diffusion + cell step: states -> t + dt (openclsim.c:1066-1096)
             const MkbStepParams* sp = dring + i;
             void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
             CUDA_TRY(cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0,
                                       s->stream));
+            if (s->partner) CUDA_TRY(cudaEventRecord(s->ev_step, s->stream));
             s->launches++;
             s->steps++;
             s->parity ^= 1;
@@ -1472,6 +1491,8 @@ static int sim_step_typed(mkb_sim* s) {
             }
         }
     }
+
+    if (!drain) return MKB_OK;      // mkb_sim_step_pair drains both grids itself
 
     // End of call: drain, like the clFinish at openclsim.c:1172-1176
     if (timing_started) CUDA_TRY(cudaEventRecord(s->ev_t1, s->stream));
@@ -1511,6 +1532,93 @@ extern "C" int mkb_sim_step(mkb_sim* s, double* engine_time, int* halted) {
     if (halted) *halted = s->halted ? 1 : 0;
     if (rc) return rc;
     return s->finished ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------
+// Fibre-tissue pair: two grids, two kernels, every step together
+// (myokit/_sim/fiber_tissue.c:1001-1155)
+// ---------------------------------------------------------------------------
+extern "C" int mkb_sim_junction_connect(mkb_sim* f, mkb_sim* t, double g, uint64_t cty) {
+    if (!f || !t) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (f == t) return fail(MKB_ERR_INVALID, "a junction needs two simulations");
+    if (f->partner || t->partner) return fail(MKB_ERR_STATE, "already part of a pair");
+    if (f->diff_mode != MKB_DIFF_HOMOGENEOUS || t->diff_mode != MKB_DIFF_HOMOGENEOUS) {
+        return fail(MKB_ERR_INVALID, "a junction needs two homogeneous grids");
+    }
+    if (f->precision != t->precision || f->device != t->device) {
+        return fail(MKB_ERR_INVALID, "both grids must use the same precision and device");
+    }
+    if (f->d_xchg || t->d_xchg || f->cpt != 1 || t->cpt != 1) {
+        return fail(MKB_ERR_INVALID, "a junction needs unsharded grids with one cell per thread");
+    }
+    if (f->step_index != 0 || t->step_index != 0) {
+        return fail(MKB_ERR_STATE, "junction_connect must precede the first step");
+    }
+    // fiber_tissue.py:168-170, 219-222
+    if (f->ny > t->ny || cty + f->ny > t->ny) {
+        return fail(MKB_ERR_INVALID, "The fiber y-dimension cannot exceed that of the tissue.");
+    }
+    CUDA_TRY(cudaSetDevice(f->device));
+    mkb_sim* both[2] = {f, t};
+    for (mkb_sim* s : both) {
+        if (!s->ev_step) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+    }
+    auto plane = [](mkb_sim* s, bool alt) -> const void* {
+        const u64 k = alt ? s->plane_alt_v : (u64)s->i_vm;
+        return s->d_planes + k * s->stride * s->rs;
+    };
+    // fibre cell (nfx - 1, k) <-> tissue cell (0, cty + k)   (openclsim.cl:617-621)
+    MkbGridArgs& gf = f->grid;
+    gf.junction_v0 = plane(t, false);
+    gf.junction_v1 = plane(t, true);
+    gf.jg = g;
+    gf.jx = f->nx - 1; gf.jy0 = 0; gf.jn = f->ny;
+    gf.joff = 0 + cty * t->nx; gf.jstride = t->nx;
+    MkbGridArgs& gt = t->grid;
+    gt.junction_v0 = plane(f, false);
+    gt.junction_v1 = plane(f, true);
+    gt.jg = g;
+    gt.jx = 0; gt.jy0 = cty; gt.jn = f->ny;
+    gt.joff = f->nx - 1; gt.jstride = f->nx;
+    f->partner = t;
+    t->partner = f;
+    return MKB_OK;
+}
+
+template <typename TR>
+static int sim_drain_typed(mkb_sim* s) {
+    int rc = flush_rows(s);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return finalize_rows<TR>(s);
+}
+
+extern "C" int mkb_sim_step_pair(mkb_sim* f, mkb_sim* t, uint64_t steps, double* engine_time, int* halted) {
+    if (!f || !t) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (f->partner != t || t->partner != f) return fail(MKB_ERR_STATE, "not a connected pair");
+    if (f->parity != t->parity || f->finished != t->finished) {
+        return fail(MKB_ERR_STATE, "the two grids of a pair must have taken the same steps");
+    }
+    CUDA_TRY(cudaSetDevice(f->device));
+    const bool dp = f->precision == MKB_DOUBLE;
+    const u64 keep_f = f->steps_per_call, keep_t = t->steps_per_call;
+    f->steps_per_call = t->steps_per_call = 1;
+    int rc = MKB_OK;
+    for (uint64_t k = 0; k < steps && !f->finished && !t->finished && !rc; k++) {
+        // one step each, strictly alternating: each kernel waits for the event
+        // the other grid recorded after its previous step
+        rc = dp ? sim_step_typed<double>(f, false) : sim_step_typed<float>(f, false);
+        if (!rc) rc = dp ? sim_step_typed<double>(t, false) : sim_step_typed<float>(t, false);
+    }
+    f->steps_per_call = keep_f;
+    t->steps_per_call = keep_t;
+    if (!rc) rc = dp ? sim_drain_typed<double>(f) : sim_drain_typed<float>(f);
+    if (!rc) rc = dp ? sim_drain_typed<double>(t) : sim_drain_typed<float>(t);
+    if (engine_time) *engine_time = f->engine_time;
+    if (halted) *halted = (f->halted || t->halted) ? 1 : 0;
+    if (rc) return rc;
+    if (f->halted || t->halted) f->finished = t->finished = true;
+    return (f->finished && t->finished) ? 0 : 1;
 }
 
 extern "C" int mkb_sim_log_view(mkb_sim* s, const void** data, uint64_t* rows, uint64_t* cols,
