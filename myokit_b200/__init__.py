@@ -12,8 +12,10 @@ from ._myokit import import_myokit as _import_myokit
 _import_myokit()
 
 from .simulation import SimulationCUDA  # noqa: E402
+from .fiber_tissue import FiberTissueSimulationCUDA  # noqa: E402
 from .cuda import CUDA, NoCUDAError  # noqa: E402
 from . import capi  # noqa: E402
 
-__all__ = ['SimulationCUDA', 'CUDA', 'NoCUDAError', 'capi']
+__all__ = ['SimulationCUDA', 'FiberTissueSimulationCUDA', 'CUDA',
+           'NoCUDAError', 'capi']
 __version__ = '0.1.0'

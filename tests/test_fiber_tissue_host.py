@@ -1,0 +1,129 @@
+"""
+Host-side behaviour of FiberTissueSimulationCUDA (no GPU): argument checks with
+the reference's messages (myokit/_sim/fiber_tissue.py:119-325, asserted by the
+reference's tests/test_simulation_fiber_tissue.py::test_creation), state and
+time handling, the kernels it would compile, and the loud failure without a
+device.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import myokit_b200
+import myokit
+from myokit_b200 import capi
+
+DATA = os.path.join(os.path.dirname(myokit.__file__), 'tests', 'data')
+FT = myokit_b200.FiberTissueSimulationCUDA
+
+
+def models():
+    mf = myokit.load_model(os.path.join(DATA, 'dn-1985-normalised.mmt'))
+    mt = myokit.load_model(os.path.join(DATA, 'lr-1991.mmt'))
+    return mf, mt
+
+
+def make(**kw):
+    mf, mt = models()
+    p = myokit.pacing.blocktrain(1000, 2.0, offset=.01)
+    args = dict(ncells_fiber=(8, 4), ncells_tissue=(8, 6), nx_paced=4,
+                g_fiber=(235, 100), g_tissue=(9, 5), g_fiber_tissue=9,
+                dt=0.0012, precision=myokit.DOUBLE_PRECISION)
+    args.update(kw)
+    return FT(mf, mt, p, **args)
+
+
+def test_creation_checks():
+    mf, mt = models()
+    s = make()
+    assert s.fiber_shape() == (4, 8) and s.tissue_shape() == (6, 8)
+    assert s.time() == 0 and s.step_size() == 0.0012
+    with pytest.raises(ValueError, match='fiber size must be a tuple'):
+        make(ncells_fiber=4)
+    with pytest.raises(ValueError, match='tissue size must be a tuple'):
+        make(ncells_tissue=(4, 4, 4))
+    with pytest.raises(ValueError, match='fiber size must be at least'):
+        make(ncells_fiber=(0, 4))
+    with pytest.raises(ValueError, match='tissue size must be at least'):
+        make(ncells_tissue=(8, 0))
+    with pytest.raises(ValueError, match='fiber y-dimension cannot exceed'):
+        make(ncells_fiber=(8, 7))
+    with pytest.raises(ValueError, match='stimulus pulse must be non-negative'):
+        make(nx_paced=-1)
+    with pytest.raises(ValueError, match='fiber conductivity must be a tuple'):
+        make(g_fiber=1)
+    with pytest.raises(ValueError, match='tissue conductivity must be a tuple'):
+        make(g_tissue=(1, 2, 3))
+    with pytest.raises(ValueError, match='step size must be greater than zero'):
+        make(dt=0)
+    with pytest.raises(ValueError, match='single and double precision'):
+        make(precision=16)
+    # labels, bindings, units
+    m2 = mt.clone()
+    m2.label('membrane_potential').set_label(None)
+    with pytest.raises(ValueError, match='labelled as "membrane_potential" in the fiber'):
+        FT(m2, mt)
+    with pytest.raises(ValueError, match='labelled as "membrane_potential" in the tissue'):
+        FT(mt, m2)
+    m2 = mt.clone()
+    m2.binding('diffusion_current').set_binding(None)
+    with pytest.raises(ValueError, match='bound to "diffusion_current"'):
+        FT(mt, m2)
+    m2 = mt.clone()
+    m2.label('membrane_potential').set_unit(None)
+    with pytest.raises(ValueError, match='fiber model must specify a unit for the membrane'):
+        FT(m2, mt)
+    m2 = mt.clone()
+    m2.label('membrane_potential').set_unit('V')
+    with pytest.raises(ValueError, match='same unit in the fiber and the tissue'):
+        FT(mt, m2)
+
+
+def test_states_time_and_reset():
+    s = make()
+    mf, mt = models()
+    nf, nt = mf.count_states(), mt.count_states()
+    assert len(s.fiber_state()) == nf * 32 and len(s.tissue_state()) == nt * 48
+    assert list(s.fiber_state(1, 2)) == list(mf.initial_values(True))
+    st = list(mt.initial_values(True))
+    st[0] = -50.0
+    s.set_tissue_state(st, 3, 4)
+    assert s.tissue_state(3, 4)[0] == -50.0
+    assert s.tissue_state(2, 4)[0] != -50.0
+    assert s.default_tissue_state(3, 4)[0] != -50.0
+    s.set_default_fiber_state(s.fiber_state())
+    s.set_time(12.5)
+    assert s.time() == 12.5
+    s.reset()
+    assert s.time() == 0 and s.tissue_state(3, 4)[0] != -50.0
+    s.set_step_size(0.002)
+    assert s.step_size() == 0.002
+    with pytest.raises(ValueError):
+        s.set_step_size(0)
+    with pytest.raises(ValueError, match="can't be negative"):
+        s.run(-1)
+
+
+def test_kernels_carry_their_side_of_the_junction():
+    s = make()
+    cf = s._f.kernel_source().code
+    ct = s._t.kernel_source().code
+    assert 'idiff += (Real)g.jg * (vc - vo);' in cf
+    assert 'idiff -= (Real)g.jg * (vo - vc);' in ct
+    # one cell per thread even for tiny models, fibre paced over its height
+    assert '#define MKB_CPT' not in cf and '#define MKB_CPT' not in ct
+    assert s._f._paced_cells == (4, 4, 0, 0) and s._t._paced_cells == (0, 0, 0, 0)
+    for src in (s._f.kernel_source(), s._t.kernel_source()):
+        cubin, log = capi.jit_compile(src.code, src.options)
+        assert len(cubin) > 5000
+
+
+def test_no_device_no_run():
+    if capi.device_count() > 0:
+        pytest.skip('a GPU is present')
+    s = make()
+    with pytest.raises(Exception):
+        s.run(1.0)
+    # nothing was advanced or left half-open
+    assert s.time() == 0 and s._f._session is None and s._t._session is None
