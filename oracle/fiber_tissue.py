@@ -133,6 +133,9 @@ class OracleFiberTissue:
     def time(self):
         return self._time
 
+    def set_time(self, time=0):
+        self._time = float(time)
+
     def _events(self):
         ev = []
         if self._protocol is not None:
