@@ -441,9 +441,9 @@ struct mkb_sim {
     bool ghosts_connected = false;
 
     // fibre-tissue pair (mkb_sim_junction_connect): the other grid, and the
-    // event this one records after each of its step kernels
+    // events this one records after its step kernels (odd / even steps)
     mkb_sim* partner = nullptr;
-    cudaEvent_t ev_step = nullptr;
+    cudaEvent_t ev_step[2] = {nullptr, nullptr};
 
     // counters
     u64 launches = 0, steps = 0;
@@ -469,7 +469,9 @@ static void sim_destroy(mkb_sim* s) {
         s->partner->partner = nullptr;
         s->partner = nullptr;
     }
-    if (s->ev_step) cudaEventDestroy(s->ev_step);
+    for (int k = 0; k < 2; k++) {
+        if (s->ev_step[k]) cudaEventDestroy(s->ev_step[k]);
+    }
     cudaFree(s->d_planes);
     cudaFree(s->d_gx);
     cudaFree(s->d_gy);
@@ -1447,16 +1449,18 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
                 }
             }
             if (s->partner) {
-                // the other grid's previous step: it wrote the V(t) plane this
-                // kernel reads and has finished reading the plane it overwrites
-                CUDA_TRY(cudaStreamWaitEvent(s->stream, s->partner->ev_step, 0));
+                // The other grid's PREVIOUS step wrote the V(t) plane this
+                // kernel reads and was the last reader of the plane this
+                // kernel overwrites; its kernel of the same step may overlap.
+                // (An event that was never recorded does not block.)
+                CUDA_TRY(cudaStreamWaitEvent(s->stream, s->partner->ev_step[(rec.p.step - 1u) & 1u], 0));
             }
             // fused diffusion + cell step: states -> t + dt (openclsim.c:1066-1096)
             const MkbStepParams* sp = dring + i;
             void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
             CUDA_TRY(cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0,
                                       s->stream));
-            if (s->partner) CUDA_TRY(cudaEventRecord(s->ev_step, s->stream));
+            if (s->partner) CUDA_TRY(cudaEventRecord(s->ev_step[rec.p.step & 1u], s->stream));
             s->launches++;
             s->steps++;
             s->parity ^= 1;
@@ -1561,7 +1565,9 @@ extern "C" int mkb_sim_junction_connect(mkb_sim* f, mkb_sim* t, double g, uint64
     CUDA_TRY(cudaSetDevice(f->device));
     mkb_sim* both[2] = {f, t};
     for (mkb_sim* s : both) {
-        if (!s->ev_step) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) {
+            if (!s->ev_step[k]) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_step[k], cudaEventDisableTiming));
+        }
     }
     auto plane = [](mkb_sim* s, bool alt) -> const void* {
         const u64 k = alt ? s->plane_alt_v : (u64)s->i_vm;
