@@ -127,3 +127,116 @@ def test_no_device_no_run():
         s.run(1.0)
     # nothing was advanced or left half-open
     assert s.time() == 0 and s._f._session is None and s._t._session is None
+
+
+class _RecordingBackend:
+    """
+    Stands in for the device entry points so that the host-side control flow of
+    a pair run (acquire both, connect once, step until done, read both logs,
+    re-arm on the next run) can be exercised without a GPU. Everything else
+    (JIT, schedule probe, ...) goes to the real library. It computes nothing.
+    """
+
+    def __init__(self, real):
+        self._real = real
+        self.calls = []
+        self._next = 0x1000
+        self._log = {}
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def mkb_sim_init(self, cfg, out):
+        import ctypes
+        c = ctypes.cast(cfg, ctypes.POINTER(capi.SimConfig)).contents
+        self._next += 0x100
+        ctypes.cast(out, ctypes.POINTER(ctypes.c_void_p)).contents.value = self._next
+        self.calls.append(('init', self._next, c.nx, c.ny, c.n_log))
+        self._log[self._next] = (c.n_log, c.tmin, c.tmax, c.log_interval)
+        return 0
+
+    def mkb_sim_rearm(self, sim, rc):
+        import ctypes
+        r = ctypes.cast(rc, ctypes.POINTER(capi.RunConfig)).contents
+        self.calls.append(('rearm', sim.value))
+        self._log[sim.value] = (r.n_log, r.tmin, r.tmax, r.log_interval)
+        return 0
+
+    def mkb_sim_junction_connect(self, f, t, g, cty):
+        self.calls.append(('connect', f.value, t.value, g.value, cty.value))
+        return 0
+
+    def mkb_sim_step_pair(self, f, t, steps, now, halted):
+        import ctypes
+        self.calls.append(('step_pair', f.value, t.value, steps.value))
+        done = sum(1 for c in self.calls if c[0] == 'step_pair'
+                   and c[1] == f.value) % 3 == 0
+        tmin, tmax = self._log[f.value][1:3]
+        ctypes.cast(now, ctypes.POINTER(ctypes.c_double)).contents.value = \
+            tmax if done else 0.5 * (tmin + tmax)
+        return 0 if done else 1
+
+    def mkb_sim_log_view(self, sim, data, rows, cols, rstride):
+        import ctypes
+        import numpy as np
+        n_log, tmin, tmax, li = self._log[sim.value]
+        nrows = int(round((tmax - tmin) / li))
+        buf = np.zeros((nrows, n_log + 1))
+        buf[:, 0] = tmin + li * np.arange(nrows)
+        self._keep = getattr(self, '_keep', []) + [buf]
+        ctypes.cast(data, ctypes.POINTER(ctypes.c_void_p)).contents.value = buf.ctypes.data
+        ctypes.cast(rows, ctypes.POINTER(ctypes.c_uint64)).contents.value = nrows
+        ctypes.cast(cols, ctypes.POINTER(ctypes.c_uint64)).contents.value = n_log
+        ctypes.cast(rstride, ctypes.POINTER(ctypes.c_uint64)).contents.value = n_log + 1
+        return 0
+
+    def mkb_sim_counters(self, sim, launches, steps):
+        return 0
+
+    def mkb_sim_device_ms(self, sim, ms):
+        return 0
+
+    def mkb_sim_get_state(self, sim, out):
+        self.calls.append(('get_state', sim.value))
+        return 0
+
+    def mkb_sim_clean(self, sim):
+        self.calls.append(('clean', sim.value if hasattr(sim, 'value') else sim))
+
+
+def test_pair_run_control_flow(monkeypatch):
+    real = capi.library()
+    fake = _RecordingBackend(real)
+    monkeypatch.setattr(capi, 'library', lambda: fake)
+    s = make()
+    logf, logt = s.run(2.0, logf=['engine.time', 'membrane.V'],
+                       logt=['engine.time', 'membrane.V'], log_interval=0.5)
+    kinds = [c[0] for c in fake.calls]
+    assert kinds[:3] == ['init', 'init', 'connect']
+    assert fake.calls[0][2:4] == (8, 4) and fake.calls[1][2:4] == (8, 6)
+    f, t = fake.calls[0][1], fake.calls[1][1]
+    assert fake.calls[2] == ('connect', f, t, 9.0, 1)        # cty = (6 - 4) / 2
+    assert kinds[3:] == ['step_pair'] * 3
+    assert all(c[1:3] == (f, t) for c in fake.calls[3:])
+    # both logs: 4 rows, every cell of the requested variable
+    assert list(logf['engine.time']) == [0.0, 0.5, 1.0, 1.5]
+    assert len(logf['7.3.membrane.V']) == 4 and len(logt['7.5.membrane.V']) == 4
+    assert len(logf.keys()) == 1 + 32 and len(logt.keys()) == 1 + 48
+    assert s.time() == 2.0 and s._f.time() == 2.0 and s._t.time() == 2.0
+    # second run: both re-armed on the resident state, no second connect
+    n0 = len(fake.calls)
+    s.run(1.0, logf=['membrane.V'], logt=myokit.LOG_NONE, log_interval=0.5)
+    kinds = [c[0] for c in fake.calls[n0:]]
+    assert kinds[:2] == ['rearm', 'rearm'] and 'connect' not in kinds
+    assert s.time() == 3.0
+    # touching one grid restarts both and joins the new pair
+    n0 = len(fake.calls)
+    s.set_tissue_state(s.tissue_state())
+    s.run(1.0, logf=myokit.LOG_NONE, logt=myokit.LOG_NONE)
+    kinds = [c[0] for c in fake.calls[n0:]]
+    assert kinds.count('clean') == 2 and kinds.count('init') == 2
+    assert kinds.count('connect') == 1
+    # pre: time stays, defaults follow
+    s.pre(1.0)
+    assert s.time() == 4.0
+    s.close()
