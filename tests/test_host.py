@@ -605,3 +605,36 @@ def test_opt_in_arithmetic_variants_generate_and_build():
     assert 'mkb_exp_estrin(' in body and 'mkb_exp_poly(' not in body
     cubin, log = capi.jit_compile(src.code, src.options)
     assert len(cubin) > 10000
+
+
+def test_command_line(tmp_path, monkeypatch, capsys):
+    # python -m myokit_b200 cuda / cuda-select (cf. myokit opencl, opencl-select)
+    from myokit_b200 import __main__ as cli
+    from myokit_b200 import cuda as cuda_mod
+    monkeypatch.setattr(cuda_mod.CUDA, '_path',
+                        staticmethod(lambda: str(tmp_path / 'sel.ini')))
+    monkeypatch.delenv('MYOKIT_CUDA_DEVICE', raising=False)
+    assert cli.main(['cuda']) == 0
+    out = capsys.readouterr().out
+    assert ('Device 0' in out) if HAS_GPU else ('No CUDA devices found.' in out)
+    assert cli.main([]) == 2
+    assert cli.main(['cuda-select', '--clear']) == 0
+    if HAS_GPU:
+        assert cli.main(['cuda-select', '--device', '0']) == 0
+        assert cuda_mod.CUDA.load_selection() == 0
+        assert cli.main(['cuda-select', '--device', '99']) == 1
+    else:
+        assert cli.main(['cuda-select', '--device', '0']) == 1
+    # two devices, without the hardware: the selection is stored and shown
+    info = dict(name='B200', compute_capability=(10, 0), sm_count=148,
+                clock_khz=1965000, total_mem=180 << 30, l2_bytes=126 << 20,
+                smem_per_block_optin=232448)
+    monkeypatch.setattr(capi, 'device_count', lambda: 2)
+    monkeypatch.setattr(capi, 'device_info', lambda i: info)
+    capsys.readouterr()
+    assert cli.main(['cuda-select', '--device', '1']) == 0
+    assert cuda_mod.CUDA.load_selection() == 1
+    assert cli.main(['cuda']) == 0
+    out = capsys.readouterr().out
+    assert 'Device 1: B200' in out and '(selected)' in out
+    assert 'Multiprocessors   : 148' in out
