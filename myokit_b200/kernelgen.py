@@ -193,6 +193,8 @@ class _ExpMixin:
     def _ex_exp(self, e):
         if self._fast_exp and not self._sp:
             return self._ex_function(e, self._fast_exp)
+        if self._fast_exp == 'mkb_expf_ex2' and self._sp:
+            return self._ex_function(e, 'mkb_expf_ex2')
         return super()._ex_exp(e)
 
 
@@ -225,6 +227,7 @@ _PRELUDE = r"""
 #ifndef MKB_ASM_RCP64
 #define MKB_ASM_RCP64(r, b) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b))
 #define MKB_ASM_SREG(v, name) asm volatile("mov.u32 %0, %%" name ";" : "=r"(v))
+#define MKB_ASM_EX2F(y, t) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t))
 #endif
 
 // x^k for a compile-time integer k: square-and-multiply, fixed order.
@@ -358,6 +361,23 @@ __device__ __forceinline__ double mkb_exp_poly(double x) {
     const int nc = min(max(n, -1021), 1024);
     const double y = __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
     return y;
+}
+
+// Single precision (option fast_exp = 'ex2'): expf(x) = 2^t with t = x log2(e)
+// carried as a rounded product plus its exact residual, so that the argument
+// error does not grow with |x| as it does in __expf: FMUL, 2 FFMA, MUFU.EX2,
+// FMUL, FFMA = 6 instructions against the 8-10 of libdevice's expf (which
+// splits off 2^n by hand; ex2.approx saturates to 0 / inf by itself).
+// Error: the 2^-22.5 of ex2.approx plus up to 2 ulp. Overflow gives inf and
+// underflow 0 as they should (the correction is a factor next to 1, so it
+// never meets inf - inf); infinite x and |x| > 2e38 are not supported.
+__device__ __forceinline__ float mkb_expf_ex2(float x) {
+    const float t = x * 1.44269502e+0f;
+    float r = fmaf(x, 1.44269502e+0f, -t);      // exact: x * L2E_hi - t
+    r = fmaf(x, 1.92596303e-8f, r);             // + x * L2E_lo
+    float y;
+    MKB_ASM_EX2F(y, t);
+    return y * fmaf(r, 6.93147182e-1f, 1.0f);   // 2^(t + r) = 2^t (1 + r ln 2)
 }
 
 // Estrin variant (option fast_exp = 'estrin'): the same reduction and
@@ -652,8 +672,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         w = _Writer(precision)
         w._fast_div = bool(fast_div)
         w._fast_exp = ({'table': 'mkb_exp_tab', 'poly': 'mkb_exp_poly',
-                        'estrin': 'mkb_exp_estrin'}.get(
+                        'estrin': 'mkb_exp_estrin', 'ex2': 'mkb_expf_ex2'}.get(
             fast_exp, 'mkb_exp_poly') if fast_exp else False)
+        if (fast_exp == 'ex2') != bool(sp) and fast_exp == 'ex2':
+            raise ValueError("fast_exp='ex2' is a single-precision variant.")
         if const_pool and not sp:
             w.enable_pool()
     w._pow_multiply = bool(pow_multiply)
@@ -769,6 +791,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     i_vm = vm.index() if vm is not None else -1
     real = 'float' if sp else 'double'
     exp = 'expf' if sp else (w._fast_exp if fast_exp else 'exp')
+    if sp and fast_exp == 'ex2' and not native_maths:
+        exp = 'mkb_expf_ex2'
     if native_maths and sp:
         exp = '__expf'
     states = list(model.states())

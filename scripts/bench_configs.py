@@ -57,8 +57,10 @@ if 'c2' in which:
     report('C2 LR91 2048^2 fp32', workloads.c2_planar(S, 2048), 500)
 if 'c4' in which:
     report('C4-proxy LR91 8192^2 fp32', workloads.c2_planar(S, 8192), 50, warmup=5)
-    report('C4-proxy LR91 8192^2 fp32 fdiv', workloads.c2_planar(S, 8192), 50, warmup=5, fast_div=True)
-    report('C4-proxy LR91 8192^2 fp32 mb4', workloads.c2_planar(S, 8192), 50, warmup=5, min_blocks=4)
+    # (measured in round 1 and dropped: fast_div=True is the default already; min_blocks=4 is 10 % slower)
+    if os.environ.get('MKB_TEST_EXPERIMENTAL'):
+        # prepared without GPU time left to measure it: 6-instruction expf
+        report('C4-proxy LR91 8192^2 fp32 exp=ex2', workloads.c2_planar(S, 8192), 50, warmup=5, fast_exp='ex2')
 if 'stencil' in which:
     for prec, name in ((myokit.SINGLE_PRECISION, 'fp32'), (myokit.DOUBLE_PRECISION, 'fp64')):
         rs = 4 if name == 'fp32' else 8

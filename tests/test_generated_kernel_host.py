@@ -326,3 +326,22 @@ def test_junction_needs_a_plain_homogeneous_kernel():
     s.set_kernel_options(junction='fiber')
     with pytest.raises(ValueError):
         s.kernel_source()
+
+
+def test_lr91_fp32_lean_exp_variant():
+    # opt-in fast_exp='ex2' (single precision): same accuracy class as the
+    # default fp32 kernel relative to the fp32 oracle
+    def make(cls):
+        return lr91_2d(cls, precision=SP)
+    base, want, _ = both(make, dict(block=(8, 4)), 5.0, 0.5, 10, 7)
+    got, want, _ = both(make, dict(block=(8, 4), fast_exp='ex2'), 5.0, 0.5, 10, 7)
+    e0 = np.abs(base['V'] - want['membrane.V']).max()
+    e1 = np.abs(got['V'] - want['membrane.V']).max()
+    assert e1 <= max(5e-2, 3 * e0)
+    s = make(myokit_b200.SimulationCUDA)
+    s.set_kernel_options(fast_exp='ex2')
+    assert 'mkb_expf_ex2(' in s.kernel_source().code.split('extern "C" __global__')[1]
+    d = lr91_2d(myokit_b200.SimulationCUDA, precision=DP)
+    d.set_kernel_options(fast_exp='ex2')
+    with pytest.raises(ValueError):
+        d.kernel_source()
