@@ -13,6 +13,8 @@ variants = [
     ('div_parallel', dict(div_parallel=True)),
     ('exp estrin', dict(fast_exp='estrin')),
     ('estrin + div_parallel', dict(fast_exp='estrin', div_parallel=True)),
+    ('exp table (fewest FP64 instructions)', dict(fast_exp='table')),
+    ('table + div_parallel', dict(fast_exp='table', div_parallel=True)),
     ('const_div off', dict(const_div=False)),
 ]
 only = os.environ.get('SWEEP_ONLY')
