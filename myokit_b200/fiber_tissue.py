@@ -226,6 +226,72 @@ class FiberTissueSimulationCUDA:
         self._connected = None
 
     # ------------------------------------------------------------------
+    # NaN search
+    # ------------------------------------------------------------------
+    def find_nan(self, logf, logt):
+        """
+        Locates the first ``NaN`` / ``inf`` in a pair of logs made by this
+        simulation (cf. ``fiber_tissue.py:464-687``). The logs must hold all
+        states and bound variables of both parts.
+
+        Returns ``(part, time, icell, variable, value, states, bound)``:
+        ``part`` is ``'fiber'`` or ``'tissue'``, ``icell`` an ``(x, y)``
+        tuple, ``states[0]`` the state of that cell at the logged point where
+        the error shows, ``states[1]``, ``states[2]`` the logged points before
+        it (if any), ``bound`` the bound variables at the same points.
+
+        Unlike the reference, the search works on the logged samples only: it
+        does not re-run the preceding interval with a finer log.
+        """
+        parts = (('fiber', self._f, logf), ('tissue', self._t, logt))
+        for name, sim, log in parts:
+            g = [v.qname() for v in (sim._model.binding(x) for x in
+                                     ('time', 'pace')) if v is not None]
+            need = myokit.prepare_log(
+                myokit.LOG_STATE + myokit.LOG_BOUND, sim._model,
+                dims=sim._dims, global_vars=g)
+            for key in need:
+                if key not in log:
+                    raise myokit.FindNanError(
+                        'Method requires a simulation log from the ' + name
+                        + ' model containing all states and bound variables.'
+                        ' Missing variable <' + key + '>.')
+        # first bad sample of every key, then the earliest over both logs
+        best = None
+        for name, sim, log in parts:
+            for key in log.keys():
+                bad = np.nonzero(~np.isfinite(np.asarray(log[key])))[0]
+                if len(bad) and (best is None or bad[0] < best[0]):
+                    best = (int(bad[0]), name, sim, log, key)
+        if best is None:
+            raise myokit.FindNanError('Error condition not found in logs.')
+        i, name, sim, log, key = best
+        if i == 0:
+            raise myokit.FindNanError(
+                'Unable to work with simulation logs where the error'
+                ' condition is met in the very first data point.')
+        cell, var = myokit.split_key(key)
+        icell = tuple(int(x) for x in cell.split('.') if x != '')
+        model = sim._model
+        time_var = model.time().qname()
+        prefix = '.'.join(str(x) for x in icell) + '.' if icell else ''
+        if not icell:       # a global variable went wrong: report cell (0, 0)
+            icell = (0, 0)
+            prefix = '0.0.'
+        states, bound = [], []
+        for k in range(i, max(i - 3, -1), -1):
+            states.append([log[prefix + s.qname()][k] for s in model.states()])
+            b = {}
+            for label in ('time', 'pace', 'diffusion_current'):
+                v = model.binding(label)
+                if v is None:
+                    continue
+                q = v.qname()
+                b[q] = log[q][k] if q in log else log[prefix + q][k]
+            bound.append(b)
+        return (name, log[time_var][i], icell, var, log[key][i], states, bound)
+
+    # ------------------------------------------------------------------
     # Running
     # ------------------------------------------------------------------
     def pre(self, duration, report_nan=True, progress=None,
@@ -303,9 +369,29 @@ class FiberTissueSimulationCUDA:
                 tmin, tmax, (logf, inter_f), (logt, inter_t), log_interval,
                 progress, msg)
         if report_nan and (halted or logf.has_nan() or logt.has_nan()):
-            part = 'fiber' if logf.has_nan() else 'tissue'
-            raise myokit.SimulationError(
-                'Numerical error found in simulation logs (' + part + ').')
+            txt = ['Numerical error found in simulation logs.']
+            try:
+                part, time, icell, var, value, states, bound = self.find_nan(
+                    logf, logt)
+                model = self._t._model if part == 'tissue' else self._f._model
+                txt.append(
+                    'Encountered numerical error in ' + part + ' simulation at'
+                    ' t = ' + myokit.float.str(time, precision=self._precision)
+                    + ' in cell (' + ','.join(str(x) for x in icell)
+                    + ') when ' + var + ' = '
+                    + myokit.float.str(value, precision=self._precision) + '.')
+                txt.append('State during:')
+                txt.append(model.format_state(
+                    states[0], precision=self._precision))
+                if len(states) > 1:
+                    txt.append('State at the logged point before:')
+                    txt.append(model.format_state(
+                        states[1], precision=self._precision))
+            except myokit.FindNanError as e:
+                txt.append('Unable to pinpoint source of NaN, an error'
+                           ' occurred:')
+                txt.append(str(e))
+            raise myokit.SimulationError('\n'.join(txt))
         return logf, logt
 
     def _run_pair(self, tmin, tmax, fiber, tissue, log_interval, progress,

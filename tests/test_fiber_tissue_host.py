@@ -240,3 +240,37 @@ def test_pair_run_control_flow(monkeypatch):
     s.pre(1.0)
     assert s.time() == 4.0
     s.close()
+
+
+def test_find_nan_on_logs():
+    s = make()
+    mf, mt = models()
+    nt_ = 5
+
+    def full_log(model, nx, ny):
+        log = myokit.DataLog()
+        log['engine.time'] = list(np.arange(nt_) * 0.5)
+        log['engine.pace'] = [0.0] * nt_
+        for y in range(ny):
+            for x in range(nx):
+                pre = '%d.%d.' % (x, y)
+                for st in model.states():
+                    log[pre + st.qname()] = [0.1 * k for k in range(nt_)]
+                log[pre + model.binding('diffusion_current').qname()] = [0.0] * nt_
+        return log
+    logf = full_log(s._f._model, 8, 4)
+    logt = full_log(s._t._model, 8, 6)
+    with pytest.raises(myokit.FindNanError, match='not found'):
+        s.find_nan(logf, logt)
+    vt = s._t._model.label('membrane_potential').qname()
+    logt['3.2.' + vt][3] = float('nan')
+    logt['3.2.' + vt][4] = float('nan')
+    logf['1.1.' + s._f._model.label('membrane_potential').qname()][4] = float('inf')
+    part, time, icell, var, value, states, bound = s.find_nan(logf, logt)
+    assert part == 'tissue' and time == 1.5 and icell == (3, 2) and var == vt
+    assert value != value and len(states) == 3 and len(bound) == 3
+    assert len(states[0]) == s._t._model.count_states()
+    assert bound[0]['engine.time'] == 1.5 and bound[1]['engine.time'] == 1.0
+    del logt['0.0.' + vt]
+    with pytest.raises(myokit.FindNanError, match='tissue model containing all states'):
+        s.find_nan(logf, logt)
