@@ -345,3 +345,50 @@ def test_lr91_fp32_lean_exp_variant():
     d.set_kernel_options(fast_exp='ex2')
     with pytest.raises(ValueError):
         d.kernel_source()
+
+
+# ---------------------------------------------------------------------------
+# More models and option combinations, all bit for bit with the rewrites off
+# ---------------------------------------------------------------------------
+def _data_model(name):
+    import os
+    return myokit.load_model(os.path.join(
+        os.path.dirname(myokit.__file__), 'tests', 'data', name))
+
+
+@pytest.mark.parametrize('case', ['lr91_rl', 'br77', 'decker_fe', 'lr91_hetero_list_field'])
+def test_more_models_bit_for_bit(case):
+    p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)
+    nx, ny = 9, 6
+    rng = np.random.default_rng(5)
+    gxf = rng.uniform(2, 9, size=(ny, nx - 1))
+    gyf = rng.uniform(2, 9, size=(ny - 1, nx))
+    gna = 16.0 * (1 + 0.2 * rng.uniform(-1, 1, size=(ny, nx)))
+
+    def make(cls):
+        if case == 'lr91_rl':
+            m, _, _ = myokit.load('example')
+            s = cls(m, p, ncells=(nx, ny), precision=DP, rl=True)
+            s.set_conductance(8, 5)
+            s.set_paced_cells(2, ny, 0, 0)
+        elif case == 'br77':
+            s = cls(_data_model('beeler-1977-model.mmt'), p, ncells=(nx, ny), precision=DP)
+            s.set_conductance(8, 5)
+            s.set_paced_cells(2, ny, 0, 0)
+        elif case == 'decker_fe':
+            s = cls(_data_model('decker-2009.mmt'), p, ncells=(nx, ny), precision=DP)
+            s.set_conductance(8, 5)
+            s.set_paced_cells(-2, ny, 0, 0)      # the two right-most columns
+        else:
+            m, _, _ = myokit.load('example')
+            s = cls(m, p, ncells=(nx, ny), precision=DP)
+            s.set_conductance_field(gxf, gyf)
+            s.set_paced_cell_list([(0, 0), (1, 0), (0, 1), (8, 5), (4, 3)])
+            s.set_field('ina.gNa', gna)
+        s.set_step_size(0.005)
+        return s
+    got, want, wstate = both(make, dict(EXACT, block=(8, 4)), 3.0, 0.5, nx, ny)
+    assert want['membrane.V'].max() > want['membrane.V'][0].max() + 5     # something happened
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['state'].ravel(), wstate)
