@@ -392,3 +392,94 @@ def test_more_models_bit_for_bit(case):
     assert np.array_equal(got['V'], want['membrane.V'])
     assert np.array_equal(got['idiff'], want['membrane.i_diff'])
     assert np.array_equal(got['state'].ravel(), wstate)
+
+
+# ---------------------------------------------------------------------------
+# Randomised shapes (fixed seeds): grid sizes down to 1 x 1, 1-d and 2-d, block
+# shapes, register patches, conductance fields, pacing rectangles anywhere,
+# both thread orders; row slabs with 2-4 ranks. All bit for bit.
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('seed', [11, 12])
+def test_random_shapes_bit_for_bit(seed):
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(period=1000, duration=1, offset=0.2)
+    rng = np.random.default_rng(seed)
+    for trial in range(5):
+        two_d = rng.random() < 0.8
+        nx = int(rng.integers(1, 14))
+        ny = int(rng.integers(1, 9)) if two_d else 1
+        cpt = int(rng.choice([1, 1, 2, 4]))
+        rpt = int(rng.choice([1, 2, 3, 4])) if cpt > 1 else 1
+        if cpt > 1:
+            nx = max(cpt, nx - nx % cpt)
+        bx = int(rng.choice([2, 4, 8]))
+        by = int(rng.choice([1, 2, 4])) if two_d else 1
+        hetero = two_d and nx > 1 and ny > 1 and rng.random() < 0.4
+        px, py = int(rng.integers(0, nx)), int(rng.integers(0, ny))
+        pnx, pny = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        gxf = rng.uniform(1, 9, size=(ny, max(nx - 1, 0)))
+        gyf = rng.uniform(1, 9, size=(max(ny - 1, 0), nx))
+
+        def make(cls):
+            s = cls(m, p, ncells=(nx, ny) if two_d else nx, precision=DP)
+            if hetero:
+                s.set_conductance_field(gxf, gyf)
+            elif two_d:
+                s.set_conductance(7, 4)
+            else:
+                s.set_conductance(7)
+            if two_d:
+                s.set_paced_cells(pnx, pny, px, py)
+            else:
+                s.set_paced_cells(pnx, x=px)
+            return s
+        a = make(myokit_b200.SimulationCUDA)
+        a.set_kernel_options(block=(bx, by), cells_per_thread=cpt,
+                             rows_per_thread=rpt, **EXACT)
+        out = cuda_shim.run_on_host(a, 1.5, log_interval=0.25,
+                                    reverse=bool(trial & 1))
+        log, ostate = make(OracleSimulation).run(
+            1.5, log=['engine.time', 'membrane.V'], log_interval=0.25)
+        what = (seed, trial, nx, ny, cpt, rpt, bx, by, hetero)
+        assert np.array_equal(out['state'].ravel(), np.asarray(ostate)), what
+
+
+@pytest.mark.parametrize('seed', [21])
+def test_random_row_slabs_bit_for_bit(seed):
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(period=1000, duration=1, offset=0.2)
+    rng = np.random.default_rng(seed)
+    for trial in range(4):
+        nslab = int(rng.integers(2, 5))
+        nx = int(rng.integers(2, 14))
+        ny = int(rng.integers(nslab, nslab * 4 + 3))
+        bx = int(rng.choice([2, 4, 8]))
+        by = int(rng.choice([1, 2, 4]))
+        hetero = rng.random() < 0.5
+        lean = bool(rng.random() < 0.5)
+        px, py = int(rng.integers(0, nx)), int(rng.integers(0, ny))
+        pnx, pny = int(rng.integers(1, 4)), int(rng.integers(1, ny + 1))
+        gxf = rng.uniform(1, 9, size=(ny, nx - 1))
+        gyf = rng.uniform(1, 9, size=(ny - 1, nx))
+
+        def make(comm):
+            kw = {} if comm is None else dict(comm=comm)
+            s = myokit_b200.SimulationCUDA(m, p, ncells=(nx, ny),
+                                           precision=DP, **kw)
+            if hetero:
+                s.set_conductance_field(gxf, gyf)
+            else:
+                s.set_conductance(7, 4)
+            s.set_paced_cells(pnx, pny, px, py)
+            return s
+        opts = dict(EXACT, block=(bx, by))
+        whole = make(None)
+        whole.set_kernel_options(**opts)
+        one = cuda_shim.run_on_host(whole, 1.5, log_interval=0.25)
+        out = cuda_shim.run_slabs_on_host(
+            make, nslab, 1.5, 0.25, dict(opts, slab_lean=lean),
+            reverse=bool(trial & 1))
+        what = (seed, trial, nslab, nx, ny, bx, by, hetero, lean)
+        assert out['halo_error'] == 0, what
+        assert np.array_equal(out['state'], one['state']), what
+        assert np.array_equal(out['V'], one['V']), what
