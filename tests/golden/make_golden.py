@@ -19,6 +19,9 @@ Cases
                     Beeler-Reuter 1977, 10 cells, dt 0.005, 15 ms,
                     log_interval 0.5; time, pace, V, i_diff, Isi.
   sim1d_lr91_rl     LR1991 with Rush-Larsen updates, 32 cells, 80 ms.
+  sim1d_decker_rl   the bench model (decker-2009, 48 states) with Rush-Larsen
+                    updates, 12 cells, dt 0.005, 12 ms with a 2 ms stimulus
+                    from t = 1; V, a gate, a concentration and i_diff.
 """
 import os
 import sys
@@ -77,6 +80,19 @@ def main():
     d = s.run(80, log=['engine.time', 'membrane.V', 'ina.m'], log_interval=1)
     save('sim1d_lr91_rl', d, s.state(),
          dict(ncells=32, dt=0.01, duration=80, log_interval=1, g=10, paced=5))
+
+    md = myokit.load_model(os.path.join(
+        os.path.dirname(myokit.__file__), 'tests', 'data', 'decker-2009.mmt'))
+    s = myokit.Simulation1d(md, pb, ncells=12, rl=True)
+    s.set_conductance(10)
+    s.set_paced_cells(3)
+    s.set_step_size(0.005)
+    d = s.run(12, log=['engine.time', 'engine.pace', 'membrane.V',
+                       'membrane.i_diff', 'ina.m', 'calcium.uCa_i'],
+              log_interval=0.5)
+    save('sim1d_decker_rl', d, s.state(),
+         dict(ncells=12, dt=0.005, duration=12, log_interval=0.5, g=10,
+              paced=3))
 
 
 if __name__ == '__main__':

@@ -101,6 +101,29 @@ def test_golden_lr91_rush_larsen():
     assert np.max(np.abs(st - state)) < 1e-13
 
 
+def test_golden_decker_rush_larsen():
+    # the bench model (48 states), Rush-Larsen, against the reference's
+    # Simulation1d run in the build container
+    log, state, meta = load_golden('sim1d_decker_rl')
+    import os
+    m = myokit.load_model(os.path.join(
+        os.path.dirname(myokit.__file__), 'tests', 'data', 'decker-2009.mmt'))
+    p = myokit.pacing.blocktrain(duration=2, offset=1, period=1000)
+    for kernel in ('port', 'ref'):
+        o = OracleSimulation(m, p, ncells=12, precision=DP, rl=True,
+                             kernel=kernel)
+        o.set_conductance(10)
+        o.set_paced_cells(3)
+        o.set_step_size(0.005)
+        lg, st = o.run(12, log=['engine.time', 'engine.pace', 'membrane.V',
+                                'membrane.i_diff', 'ina.m', 'calcium.uCa_i'],
+                       log_interval=0.5)
+        assert np.max(log['0.membrane.V']) > 0       # the paced end fired
+        assert maxdiff(lg, log, list(log.keys())) < 1e-12
+        rel = np.abs(st - state) / (np.abs(state) + 1e-12)
+        assert rel.max() < 1e-12
+
+
 # ---------------------------------------------------------------------------
 # 2. Port vs the reference's own rendered kernel (oracle/_ref)
 # ---------------------------------------------------------------------------
