@@ -483,3 +483,33 @@ def test_random_row_slabs_bit_for_bit(seed):
         assert out['halo_error'] == 0, what
         assert np.array_equal(out['state'], one['state']), what
         assert np.array_equal(out['V'], one['V']), what
+
+
+def test_generated_kernel_equals_reference_simulation1d_golden():
+    # The bench model, straight against what the REFERENCE computed
+    # (tests/golden/sim1d_decker_rl.npz, made by myokit.Simulation1d): with
+    # the rewrites off the generated CUDA source gives the same bits; with
+    # the defaults it stays within 1e-9 mV.
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden',
+                             'sim1d_decker_rl.npz'))
+    m = _data_model('decker-2009.mmt')
+    p = myokit.pacing.blocktrain(duration=2, offset=1, period=1000)
+    want_v = np.array([g['log:%d.membrane.V' % x] for x in range(12)]).T
+    want_i = np.array([g['log:%d.membrane.i_diff' % x] for x in range(12)]).T
+    for options, exact in ((EXACT, True), ({}, False)):
+        s = myokit_b200.SimulationCUDA(m, p, ncells=12, precision=DP, rl=True)
+        s.set_conductance(10)
+        s.set_paced_cells(3)
+        s.set_step_size(0.005)
+        s.set_kernel_options(block=(8, 1), **options)
+        out = cuda_shim.run_on_host(s, 12, log_interval=0.5)
+        assert np.array_equal(out['time'], g['log:engine.time'])
+        if exact:
+            assert np.array_equal(out['V'], want_v)
+            assert np.array_equal(out['idiff'], want_i)
+            assert np.array_equal(out['state'].ravel(), g['state'])
+        else:
+            assert np.abs(out['V'] - want_v).max() <= 1e-9
+            rel = np.abs(out['state'].ravel() - g['state']) / (np.abs(g['state']) + 1e-12)
+            assert rel.max() <= 1e-6
