@@ -104,6 +104,27 @@ def test_golden_br77_reference_contract():
     assert max_abs_diff(cl, log) <= 1e-9
 
 
+def test_golden_decker_rush_larsen_reference_simulation1d():
+    # the bench model against what the reference's Simulation1d computed
+    # (on the host the generated kernel differs from it by 2e-12 mV)
+    log, state = load_golden('sim1d_decker_rl')
+    m = workloads.data_model('decker-2009.mmt')
+    p = myokit.pacing.blocktrain(duration=2, offset=1, period=1000)
+    s = myokit_b200.SimulationCUDA(m, p, ncells=12, precision=DP, rl=True)
+    s.set_conductance(10)
+    s.set_paced_cells(3)
+    s.set_step_size(0.005)
+    d = s.run(12, log=['engine.time', 'engine.pace', 'membrane.V',
+                       'membrane.i_diff', 'ina.m', 'calcium.uCa_i'],
+              log_interval=0.5)
+    cl = dict((k, np.asarray(v)) for k, v in d.items())
+    assert set(cl.keys()) == set(log.keys())
+    assert max_abs_diff(cl, log, ['engine.time', 'engine.pace']) < 1e-17
+    assert max_abs_diff(cl, log) <= TOL_V
+    rel = np.abs(s.state_array() - state) / (np.abs(state) + 1e-12)
+    assert rel.max() <= 1e-6
+
+
 # ---------------------------------------------------------------------------
 # BASELINE configs[1]: LR1991 2-D planar wave, fp32, activation times
 # ---------------------------------------------------------------------------
