@@ -440,6 +440,11 @@ struct mkb_sim {
     unsigned int n_import = 0;
     bool ghosts_connected = false;
 
+    // kernel "mkb_cell_step_persistent": the block is the grid, consecutive
+    // unlogged steps share one launch (run length in flags >> 8)
+    bool persistent = false;
+    std::vector<u64> runlen;
+
     // fibre-tissue pair (mkb_sim_junction_connect): the other grid, and the
     // events this one records after its step kernels (odd / even steps)
     mkb_sim* partner = nullptr;
@@ -1035,6 +1040,19 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     // Model kernel
     INIT_CUDA(cudaLibraryLoadData(&s->lib, c->cubin, nullptr, nullptr, 0, nullptr, nullptr, 0));
     INIT_CUDA(cudaLibraryGetKernel(&s->kern, s->lib, c->kernel_name));
+    s->persistent = strcmp(c->kernel_name, "mkb_cell_step_persistent") == 0;
+    if (s->persistent) {
+        const u64 cpt = c->cells_per_thread > 0 ? (u64)c->cells_per_thread : 1;
+        const u64 rpt = c->rows_per_thread > 0 ? (u64)c->rows_per_thread : 1;
+        if (c->nx > (uint64_t)c->block_x || c->ny > (uint64_t)c->block_y || cpt != 1 || rpt != 1 ||
+            c->diffusion_mode == MKB_DIFF_CONNECTIONS || c->n_ghost > 0 ||
+            (c->ny_global && c->ny_global != c->ny)) {
+            sim_destroy(s);
+            return fail(MKB_ERR_INVALID, "The persistent kernel needs an unsharded grid that fits one thread block "
+                                         "(%llu x %llu cells, block %d x %d).",
+                        (unsigned long long)c->nx, (unsigned long long)c->ny, c->block_x, c->block_y);
+        }
+    }
     // (Measured on C3: asking for the maximum-L1 carve-out makes the step kernel
     // 50 % slower — 1.58 vs 1.05 ms — because the shared-memory tile then limits
     // residency; the driver's default split is kept.)
@@ -1376,6 +1394,19 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
             CUDA_TRY(cudaEventSynchronize(s->ev_ring[half]));
         }
         for (size_t i = 0; i < s->recs.size(); i++) h[i] = s->recs[i].p;
+        if (s->persistent) {
+            // consecutive unlogged steps share one launch; a logged step is a run of one
+            s->runlen.assign(s->recs.size(), 1);
+            for (size_t i = 0; i < s->recs.size();) {
+                u64 len = 1;
+                if (!s->recs[i].logging) {
+                    while (i + len < s->recs.size() && !s->recs[i + len].logging && len < (1u << 20)) len++;
+                }
+                s->runlen[i] = len;
+                h[i].flags |= (unsigned int)len << 8;
+                i += len;
+            }
+        }
         if (!timing_started) {
             CUDA_TRY(cudaEventRecord(s->ev_t0, s->stream));
             timing_started = true;
@@ -1386,7 +1417,8 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
         s->ring_chunk++;
 
         for (size_t i = 0; i < s->recs.size(); i++) {
-            if (s->use_graphs && !s->ghosts_connected && !s->partner && i + kGraphSteps <= s->recs.size()) {
+            if (s->use_graphs && !s->ghosts_connected && !s->partner && !s->persistent &&
+                i + kGraphSteps <= s->recs.size()) {
                 bool plain = true;
                 for (int j = 0; j < kGraphSteps && plain; j++) plain = !s->recs[i + j].logging;
                 if (plain) {
@@ -1462,7 +1494,13 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
                                       s->stream));
             if (s->partner) CUDA_TRY(cudaEventRecord(s->ev_step[rec.p.step & 1u], s->stream));
             s->launches++;
-            s->steps++;
+            if (s->persistent) {
+                // the launch took runlen[i] steps and left V in the other plane once
+                s->steps += s->runlen[i];
+                i += (size_t)s->runlen[i] - 1;
+            } else {
+                s->steps++;
+            }
             s->parity ^= 1;
             if (!s->gpeers.empty()) {
                 // V(t + dt) of the exported cells -> the peers' slot for the next step

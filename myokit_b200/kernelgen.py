@@ -580,6 +580,7 @@ class KernelSource:
         self.diffusion_mode = diffusion_mode
         self.options = tuple(options)
         self.kernel_name = KERNEL_NAME
+        self.persistent = False
         self.cells_per_thread = 1
         self.rows_per_thread = 1
 
@@ -597,7 +598,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
              rows_per_thread=1, div_int_check=False, partitioned=False,
              const_div=True, slab_lean=False, div_parallel=False,
-             junction=None):
+             junction=None, persistent=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -640,6 +641,14 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         Connection graphs cut over several GPUs: CSR columns beyond the local
         cells are ghost cells whose V is read from the ghost buffer the
         owning GPUs push into.
+    ``persistent``
+        For grids that fit one thread block (``nx <= bx`` and ``ny <= by``;
+        the runtime checks): the kernel ``mkb_cell_step_persistent`` keeps
+        every state in registers and takes all steps up to the next logged
+        one inside a single launch — V travels through shared memory, two
+        barriers per step, nothing goes to global memory in between. For
+        small cables, where a step is otherwise bound by launch latency.
+        One cell per thread; not for connection graphs, slabs or junctions.
     ``junction``
         ``'fiber'`` or ``'tissue'``: the kernel of one of two grids stepped in
         lockstep (``FiberTissueSimulationCUDA``); cells on the junction add
@@ -687,7 +696,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     slab = bool(slab) and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD)
     cpt = int(cells_per_thread or 1)
     if slab or diffusion_mode == DIFF_CONNECTIONS or cpt not in (2, 4, 8) \
-            or (sp and cpt == 2) or junction:
+            or (sp and cpt == 2) or junction or persistent:
         cpt = 1
     if cpt > 1 and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
         # rim-exchange arrays of the register-patch path (static shared memory)
@@ -704,6 +713,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     if junction and (diffusion_mode != DIFF_HOMOGENEOUS or slab or cpt > 1):
         raise ValueError('A junction needs a homogeneous grid kernel with one'
                          ' cell per thread.')
+    if persistent and (diffusion_mode == DIFF_CONNECTIONS or slab or junction
+                       or partitioned):
+        raise ValueError('The persistent kernel is for unsharded grids and'
+                         ' uncoupled cells.')
 
     equations = model.solvable_order()
     del equations['*remaining*']
@@ -808,9 +821,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             src = 'active ? %s : (Real)0' % src
         return '    const Real %s = %s;' % (v(var), src)
 
-    def state_update(var):
+    def state_rhs(var):
         # openclsim.cl:358-364
-        k = var.index()
         if var in rl_states:
             inf, tau = rl_states[var]
             inf, tau, x = v(inf), v(tau), v(var)
@@ -828,9 +840,12 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                         arg = '(-dt * (%s))' % w.ex(trhs[1])
                         if c != 1.0:
                             arg = '(%s * %s)' % (arg, w.ex(myokit.Number(1.0 / c)))
-            rhs = '%s - (%s - %s) * %s(%s)' % (inf, inf, x, exp, arg)
-        else:
-            rhs = '%s + dt * %s' % (v(var), v(var.lhs()))
+            return '%s - (%s - %s) * %s(%s)' % (inf, inf, x, exp, arg)
+        return '%s + dt * %s' % (v(var), v(var.lhs()))
+
+    def state_update(var):
+        k = var.index()
+        rhs = state_rhs(var)
         if k == i_vm and slab:
             return (
                 '    {\n'
@@ -969,6 +984,162 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 var = eq.lhs.var()
                 if var not in fields and var not in folded:
                     consts.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+
+    # ------------------------------------------------------------------
+    # Persistent path: the whole grid in one thread block, many steps per launch
+    # ------------------------------------------------------------------
+    if persistent:
+        o = []
+        q = o.append
+        q('// Generated by myokit_b200.kernelgen for sm_100a — do not edit.')
+        q('// Model: %s (persistent: one block, all steps up to the next logged one)' % model.name())
+        q('#include "mkb_device_abi.h"')
+        q('typedef %s Real;' % real)
+        q('#define MKB_BX %d' % bx)
+        q('#define MKB_BY %d' % by)
+        q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
+        q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
+        q(_PRELUDE)
+        if pooled and w._pool:
+            q('__constant__ double mkb_k[%d] = {' % len(w._pool))
+            for x in w._pool:
+                q('    %r,' % x)
+            q('};')
+        q('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
+        q('%s_persistent(const MkbGridArgs g, const MkbStepParams* __restrict__ sp_first,' % KERNEL_NAME)
+        q('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
+        q('{')
+        q('    // The block is the grid: thread (tx, ty) owns cell (tx, ty).')
+        q('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
+        q('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+        q('    const unsigned long long stride = g.stride;')
+        q('    const unsigned int ix = tx, iy = ty;')
+        q('    const bool active = (ix < nx) && (iy < ny);')
+        q('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
+        q('    Real* const state = (Real*)g.state;')
+        q('    (void)v_in; (void)v_out; (void)stride;')
+        q('    // Every state stays in a register from here to the end of the launch')
+        for var in states:
+            k = var.index()
+            src = 'v_in[cid]' if k == i_vm else 'state[%dull * stride + cid]' % k
+            q('    Real S%d = active ? %s : (Real)0;' % (k, src))
+        for k, var in enumerate(fields):
+            q('    const Real %s = active ? ((const Real*)g.field)[%dull * stride + cid] : (Real)0;'
+              % (v(var), k))
+        if diffusion_mode == DIFF_FIELD:
+            q('    // Edge conductances (openclsim.cl:475-482), constant over the steps')
+            q('    const Real* const gxf = (const Real*)g.gx_field;')
+            q('    const Real* const gyf = (const Real*)g.gy_field;')
+            q('    const bool has_xm = active && nx > 1 && ix > 0;')
+            q('    const bool has_xp = active && nx > 1 && ix < nx - 1;')
+            q('    const bool has_ym = active && ny > 1 && iy > 0;')
+            q('    const bool has_yp = active && ny > 1 && iy < ny - 1;')
+            q('    const Real gxm = has_xm ? gxf[cid - iy - 1] : (Real)0;')
+            q('    const Real gxp = has_xp ? gxf[cid - iy] : (Real)0;')
+            q('    const Real gym = has_ym ? gyf[(long long)cid - (long long)nx] : (Real)0;')
+            q('    const Real gyp = has_yp ? gyf[cid] : (Real)0;')
+        if diffusion:
+            q('    __shared__ Real tile[MKB_BY + 2][MKB_BX + 2];')
+        q('    // number of steps of this launch: upper bits of the first record\'s flags')
+        q('    const unsigned int count = sp_first->flags >> 8;')
+        q('    for (unsigned int it = 0; it < count; it++) {')
+        q('    const MkbStepParams* const sp = sp_first + it;')
+        q('    // Per-step scalars, cast like openclsim.c:1063,1148,1155')
+        q('    const Real time = (Real)sp->time;')
+        q('    const Real dt = (Real)sp->dt;')
+        q('    const Real pace_in = (Real)sp->pace;')
+        q('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
+        q('    (void)time; (void)pace_in; (void)store_aux;')
+        if diffusion:
+            q('    const Real vc = S%d;' % i_vm)
+            q('    // V(t) of the whole grid through shared memory; cells at the rim see')
+            q('    // their own V beyond it (zero flux, openclsim.cl:401-434)')
+            q('    if (active) {')
+            q('        tile[ty + 1][tx + 1] = vc;')
+            q('        if (ix == 0) tile[ty + 1][0] = vc;')
+            q('        if (ix == nx - 1) tile[ty + 1][tx + 2] = vc;')
+            q('        if (iy == 0) tile[0][tx + 1] = vc;')
+            q('        if (iy == ny - 1) tile[ty + 2][tx + 1] = vc;')
+            q('    }')
+            q('    __syncthreads();')
+        q('    if (active) {')
+        if diffusion:
+            q('    const Real vxm = tile[ty + 1][tx], vxp = tile[ty + 1][tx + 2];')
+            q('    const Real vym = tile[ty][tx + 1], vyp = tile[ty + 2][tx + 1];')
+            q('    Real idiff;')
+            if diffusion_mode == DIFF_HOMOGENEOUS:
+                q('    // openclsim.cl:401-434 (diff_step)')
+                q('    const Real gx = (Real)g.gx, gy = (Real)g.gy;')
+                q('    if (nx > 1) {')
+                q('        if (ix == 0) idiff = gx * (vc - vxp);')
+                q('        else if (ix == nx - 1) idiff = gx * (vc - vxm);')
+                q('        else idiff = gx * (2 * vc - vxm - vxp);')
+                q('    } else {')
+                q('        idiff = 0;')
+                q('    }')
+                q('    if (ny > 1) {')
+                q('        if (iy == 0) idiff += gy * (vc - vyp);')
+                q('        else if (iy == ny - 1) idiff += gy * (vc - vym);')
+                q('        else idiff += gy * (2 * vc - vym - vyp);')
+                q('    }')
+            else:
+                q('    // openclsim.cl:469-486 (diff_hetero)')
+                q('    idiff = 0.0;')
+                q('    if (has_xm) { idiff += gxm * (vc - vxm); }')
+                q('    if (has_xp) { idiff += gxp * (vc - vxp); }')
+                q('    if (has_ym) idiff += gym * (vc - vym);')
+                q('    if (has_yp) idiff += gyp * (vc - vyp);')
+            q('    // openclsim.cl:249-280, 322-329')
+            if paced_list:
+                q('    const Real pace = g.paced_mask[cid] ? pace_in : (Real)0;')
+            else:
+                q('    const int pix = (int)ix, piy = (int)iy;')
+                q('    const Real pace = (pix >= (int)g.pace_x0 && pix < (int)g.pace_x1 &&')
+                q('                       piy >= (int)g.pace_y0 && piy < (int)g.pace_y1) ? pace_in : (Real)0;')
+            q('    if (store_aux) ((Real*)g.idiff)[cid] = idiff;')
+        else:
+            q('    const Real pace = pace_in;')
+        q('    (void)pace;')
+        for line in consts:
+            q(line)
+        q('    // the states as this step sees them')
+        for var in states:
+            q('    const Real %s = S%d;' % (v(var), var.index()))
+        for name, eq in todo:
+            if name:
+                q('    // Component: %s' % name)
+            var = eq.lhs.var()
+            q('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+            if var in inter_index and not eq.lhs.is_derivative():
+                q('    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                  % (inter_index[var], v(eq.lhs)))
+        q('    // Update (openclsim.cl:358-364): all from the values of time t')
+        for var in states:
+            q('    const Real N%d = %s;' % (var.index(), state_rhs(var)))
+        for var in states:
+            q('    S%d = N%d;' % (var.index(), var.index()))
+        q('    }   // active')
+        if diffusion:
+            q('    __syncthreads();    // everybody has read the tile')
+        q('    }   // steps')
+        q('    if (active) {')
+        for var in states:
+            k = var.index()
+            if k == i_vm:
+                q('        v_out[cid] = S%d;' % k)
+            else:
+                q('        state[%dull * stride + cid] = S%d;' % (k, k))
+        q('    }')
+        q('}')
+        q('')
+        options = ['--fmad=true' if fmad else '--fmad=false']
+        if max_registers:
+            options.append('--maxrregcount=%d' % int(max_registers))
+        ks = KernelSource('\n'.join(o), block, n_state, i_vm, len(inter_log),
+                          len(fields), diffusion_mode, options)
+        ks.kernel_name = KERNEL_NAME + '_persistent'
+        ks.persistent = True
+        return ks
 
     # ------------------------------------------------------------------
     # Vector path: several x-adjacent cells (and rows) per thread

@@ -50,6 +50,11 @@ which = sys.argv[1:] or ['c1', 'c2', 'c4', 'c5']
 if 'c1' in which:
     report('C1 LR91 1-D 128 fp64', workloads.c1_cable(S, 128), 20000)
     report('C1-like LR91 1-D 16384 fp64', workloads.c1_cable(S, 16384), 5000)
+    if os.environ.get('MKB_TEST_EXPERIMENTAL'):
+        # prepared without GPU time left to measure it: all unlogged steps of a chunk in one launch
+        report('C1 LR91 1-D 128 fp64 persistent', workloads.c1_cable(S, 128), 20000, persistent=True)
+        report('C1-like LR91 1-D 1024 fp64 persistent', workloads.c1_cable(S, 1024), 20000, persistent=True)
+        report('C1-like LR91 1-D 1024 fp64', workloads.c1_cable(S, 1024), 20000)
 if 'c2' in which:
     report('C2 LR91 512^2 fp32', workloads.c2_planar(S, 512), 5000)
     report('C2 LR91 512^2 fp32 b32x8', workloads.c2_planar(S, 512), 5000, block=(32, 8))

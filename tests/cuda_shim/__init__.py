@@ -22,14 +22,15 @@ _BUILD = os.path.join(_HERE, '_build')
 _CSRC = os.path.join(_ROOT, 'myokit_b200', 'csrc')
 
 
-def _compile(code, contract):
+def _compile(code, contract, kernel_name='mkb_cell_step'):
     os.makedirs(_BUILD, exist_ok=True)
     with open(os.path.join(_HERE, 'runner.cpp'), 'rb') as f:
         runner = f.read()
     with open(os.path.join(_HERE, 'mkb_cuda_shim.h'), 'rb') as f:
         shim = f.read()
     key = hashlib.sha1(code.encode('utf-8') + runner + shim
-                       + (b'c' if contract else b'n')).hexdigest()[:20]
+                       + (b'c' if contract else b'n')
+                       + kernel_name.encode('ascii')).hexdigest()[:20]
     so = os.path.join(_BUILD, 'k_%s.so' % key)
     if not os.path.isfile(so):
         cu = os.path.join(_BUILD, 'k_%s.cu.h' % key)
@@ -39,7 +40,8 @@ def _compile(code, contract):
         cmd = ['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-mfma',
                '-ffp-contract=' + ('fast' if contract else 'off'),
                '-Wno-unknown-pragmas', '-Wno-unused-variable',
-               '-DMKB_KERNEL_FILE="%s"' % cu, '-I' + _CSRC, '-I' + _HERE,
+               '-DMKB_KERNEL_FILE="%s"' % cu, '-DMKB_KERNEL_FN=' + kernel_name,
+               '-I' + _CSRC, '-I' + _HERE,
                os.path.join(_HERE, 'runner.cpp'), '-o', tmp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -85,9 +87,12 @@ def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None,
     src = sim.kernel_source(inter_vars)
     if contract is None:
         contract = '--fmad=true' in src.options
-    lib = _compile(src.code, contract)
+    lib = _compile(src.code, contract, src.kernel_name)
     lib.shim_set_thread_order(1 if reverse else 0)
+    lib.shim_set_persistent(1 if getattr(src, 'persistent', False) else 0)
     nx, ny = sim._nx, sim._ny
+    if getattr(src, 'persistent', False):
+        assert nx <= src.block[0] and ny <= src.block[1]
     n = nx * ny
     times, dts, paces, logging = schedule(sim, duration, log_interval)
     rows = int(logging.sum())

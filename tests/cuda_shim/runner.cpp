@@ -28,6 +28,7 @@ ucontext_t g_sched;
 Fiber* g_cur = nullptr;
 int g_or_acc = 0, g_or_res = 0;
 int g_reverse = 0;
+int g_persistent = 0;
 
 struct Launch {
     MkbGridArgs g;
@@ -36,8 +37,12 @@ struct Launch {
     Real* v_out;
 } g_launch;
 
+#ifndef MKB_KERNEL_FN
+#define MKB_KERNEL_FN mkb_cell_step
+#endif
+
 void fiber_main() {
-    mkb_cell_step(g_launch.g, g_launch.sp, g_launch.v_in, g_launch.v_out);
+    MKB_KERNEL_FN(g_launch.g, g_launch.sp, g_launch.v_in, g_launch.v_out);
     g_cur->done = true;
     swapcontext(&g_cur->ctx, &g_sched);
 }
@@ -100,6 +105,9 @@ void run_block(std::vector<Fiber>& fibers, std::vector<char>& stacks, unsigned i
 
 extern "C" int shim_real_size(void) { return (int)sizeof(Real); }
 extern "C" void shim_set_thread_order(int reverse) { g_reverse = reverse; }
+// persistent kernels: consecutive unlogged steps share one launch (as
+// sim_step_typed groups them); the run length rides in flags >> 8
+extern "C" void shim_set_persistent(int on) { g_persistent = on; }
 
 extern "C" int shim_run(
     int nx, int ny, int n_state, int i_vm, int n_inter, int n_field, int diffusion_mode,
@@ -190,13 +198,23 @@ extern "C" int shim_run(
     Real* v_main = (i_vm >= 0) ? state.data() + (size_t)i_vm * stride : nullptr;
     int parity = 0;
     size_t row_out = 0;
-    for (int s = 0; s < n_steps; s++) {
-        MkbStepParams sp;
-        sp.time = st_time[s];
-        sp.dt = st_dt[s];
-        sp.pace = st_pace[s];
-        sp.flags = st_log[s] ? MKB_FLAG_STORE_AUX : 0u;
-        sp.step = (unsigned int)(s + 1);
+    std::vector<MkbStepParams> run;
+    for (int s = 0; s < n_steps;) {
+        // one launch: a single step, or (persistent) a run of unlogged steps
+        int len = 1;
+        if (g_persistent && !st_log[s]) {
+            while (s + len < n_steps && !st_log[s + len]) len++;
+        }
+        run.resize(len);
+        for (int j = 0; j < len; j++) {
+            MkbStepParams& sp = run[j];
+            sp.time = st_time[s + j];
+            sp.dt = st_dt[s + j];
+            sp.pace = st_pace[s + j];
+            sp.flags = st_log[s + j] ? MKB_FLAG_STORE_AUX : 0u;
+            sp.step = (unsigned int)(s + j + 1);
+        }
+        if (g_persistent) run[0].flags |= (unsigned int)len << 8;
         const Real* v_in = v_main ? (parity ? v_alt.data() : v_main) : nullptr;
         Real* v_out = v_main ? (parity ? v_main : v_alt.data()) : nullptr;
         if (st_log[s] && log_v) {
@@ -205,7 +223,7 @@ extern "C" int shim_run(
             for (size_t c = 0; c < n; c++) log_v[row_out * n + c] = (double)vsrc[c];
         }
         g_launch.g = g;
-        g_launch.sp = &sp;
+        g_launch.sp = run.data();
         g_launch.v_in = v_in;
         g_launch.v_out = v_out;
         for (unsigned int bz = 0; bz < gbz; bz++) {
@@ -228,6 +246,7 @@ extern "C" int shim_run(
             row_out++;
         }
         if (v_main) parity ^= 1;
+        s += len;
     }
     if (v_main && parity) memcpy(v_main, v_alt.data(), n * sizeof(Real));
     for (size_t c = 0; c < n; c++) {

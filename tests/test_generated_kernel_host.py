@@ -513,3 +513,77 @@ def test_generated_kernel_equals_reference_simulation1d_golden():
             assert np.abs(out['V'] - want_v).max() <= 1e-9
             rel = np.abs(out['state'].ravel() - g['state']) / (np.abs(g['state']) + 1e-12)
             assert rel.max() <= 1e-6
+
+
+# ---------------------------------------------------------------------------
+# Persistent kernel (opt-in): the block is the grid, all steps up to the next
+# logged one inside one launch, states in registers in between.
+# ---------------------------------------------------------------------------
+def test_persistent_kernel_cable_and_grid_bit_for_bit():
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(period=1000, duration=0.5, offset=1)
+
+    def cable(cls):
+        s = cls(m, p, ncells=40, precision=DP)
+        s.set_conductance(10)
+        s.set_paced_cells(5)
+        return s
+    got, want, wstate = both(cable, dict(EXACT, persistent=True), 6.0, 0.5, 40, 1,
+                             inter_log=['ina.INa'])
+    assert want['membrane.V'].max() > 0
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['inter'][:, 0], want['ina.INa'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+
+    rng = np.random.default_rng(2)
+    gxf = rng.uniform(2, 9, size=(6, 9))
+    gyf = rng.uniform(2, 9, size=(5, 10))
+    gna = 16 * (1 + 0.1 * rng.uniform(-1, 1, size=(6, 10)))
+    p2 = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)
+
+    def grid(cls):
+        s = cls(m, p2, ncells=(10, 6), precision=DP, rl=True)
+        s.set_conductance_field(gxf, gyf)
+        s.set_paced_cells(3, 6, 0, 0)
+        s.set_field('ina.gNa', gna)
+        return s
+    for reverse_opts in (dict(), dict(block=(16, 8))):
+        got, want, wstate = both(grid, dict(EXACT, persistent=True, **reverse_opts),
+                                 4.0, 0.5, 10, 6)
+        assert np.array_equal(got['V'], want['membrane.V'])
+        assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+        assert np.array_equal(got['state'].ravel(), wstate)
+
+    def cells(cls):
+        s = cls(m, p2, ncells=21, diffusion=False, precision=DP)
+        s.set_field('ina.gNa', 16.0 * (1 + 0.3 * np.sin(np.arange(21))))
+        return s
+    got, want, wstate = both(cells, dict(EXACT, persistent=True), 4.0, 0.5, 21, 1)
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+
+
+def test_persistent_kernel_limits_and_name():
+    m, _, _ = myokit.load('example')
+    s = myokit_b200.SimulationCUDA(m, None, ncells=128, precision=DP)
+    s.set_kernel_options(persistent=True)
+    src = s.kernel_source()
+    assert src.kernel_name == 'mkb_cell_step_persistent' and src.persistent
+    assert src.block == (128, 1)
+    assert 'mkb_cell_step_persistent(const MkbGridArgs g' in src.code
+    from myokit_b200 import capi
+    cubin, log = capi.jit_compile(src.code, src.options)
+    assert len(cubin) > 10000
+    big = myokit_b200.SimulationCUDA(m, None, ncells=(64, 32), precision=DP)
+    big.set_kernel_options(persistent=True)
+    with pytest.raises(ValueError, match='fits one thread block'):
+        big.kernel_source()
+    g = myokit_b200.SimulationCUDA(m, None, ncells=16, precision=DP)
+    g.set_connections([(0, 1, 1.0)])
+    g.set_kernel_options(persistent=True)
+    with pytest.raises(ValueError):
+        g.kernel_source()
+    # the default stays the one-step kernel
+    d = myokit_b200.SimulationCUDA(m, None, ncells=128, precision=DP)
+    assert d.kernel_source().kernel_name == 'mkb_cell_step'
