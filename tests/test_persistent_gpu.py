@@ -12,7 +12,6 @@ import pytest
 
 import myokit_b200
 import myokit
-from util import run_pair, max_abs_diff
 
 pytestmark = [
     pytest.mark.gpu,
