@@ -334,6 +334,9 @@ struct mkb_sim {
     // CUDA objects
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kern = nullptr;
+    // optional second kernel of a split step ("mkb_gate_step", kernelgen's
+    // split_gates): launched after kern with the same arguments
+    cudaKernel_t kern2 = nullptr;
     cudaStream_t stream = nullptr, side = nullptr;
     cudaEvent_t ev_ring[2] = {nullptr, nullptr};
     cudaEvent_t ev_rows = nullptr, ev_copied[2] = {nullptr, nullptr};
@@ -724,6 +727,7 @@ template <typename TR>
 static int preload_kernels(mkb_sim* s) {
     cudaFuncAttributes a;
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)s->kern));
+    if (s->kern2) CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)s->kern2));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_log_gather<TR>));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_fill_u32));
     CUDA_TRY(cudaFuncGetAttributes(&a, (const void*)k_push_ghosts<TR>));
@@ -1040,6 +1044,10 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     // Model kernel
     INIT_CUDA(cudaLibraryLoadData(&s->lib, c->cubin, nullptr, nullptr, 0, nullptr, nullptr, 0));
     INIT_CUDA(cudaLibraryGetKernel(&s->kern, s->lib, c->kernel_name));
+    if (cudaLibraryGetKernel(&s->kern2, s->lib, "mkb_gate_step") != cudaSuccess) {
+        s->kern2 = nullptr;     // an ordinary, single-kernel step
+        cudaGetLastError();
+    }
     s->persistent = strcmp(c->kernel_name, "mkb_cell_step_persistent") == 0;
     if (s->persistent) {
         const u64 cpt = c->cells_per_thread > 0 ? (u64)c->cells_per_thread : 1;
@@ -1335,6 +1343,9 @@ static int graph_get(mkb_sim* s, int slot, int parity, cudaGraphExec_t* out) {
             const MkbStepParams* sp = gs.d_params + j;
             void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
             e = cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0, s->stream);
+            if (e == cudaSuccess && s->kern2) {
+                e = cudaLaunchKernel((const void*)s->kern2, s->launch_grid, s->launch_block, args, 0, s->stream);
+            }
             par ^= 1;
         }
         cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
@@ -1438,7 +1449,7 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
                     gs.pending = true;
                     s->graph_seq++;
                     s->graph_launches++;
-                    s->launches += kGraphSteps;
+                    s->launches += (s->kern2 ? 2 : 1) * kGraphSteps;
                     s->steps += kGraphSteps;
                     s->issued += kGraphSteps;
                     i += kGraphSteps - 1;       // parity unchanged: kGraphSteps is even
@@ -1492,6 +1503,12 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
             void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
             CUDA_TRY(cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0,
                                       s->stream));
+            if (s->kern2) {
+                // gates: reads V(t) (v_in) and the states only it updates
+                CUDA_TRY(cudaLaunchKernel((const void*)s->kern2, s->launch_grid, s->launch_block, args, 0,
+                                          s->stream));
+                s->launches++;
+            }
             if (s->partner) CUDA_TRY(cudaEventRecord(s->ev_step[rec.p.step & 1u], s->stream));
             s->launches++;
             if (s->persistent) {

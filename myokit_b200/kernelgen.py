@@ -581,6 +581,8 @@ class KernelSource:
         self.options = tuple(options)
         self.kernel_name = KERNEL_NAME
         self.persistent = False
+        self.gate_kernel = False        # a second kernel, mkb_gate_step
+        self.gate_states = []
         self.cells_per_thread = 1
         self.rows_per_thread = 1
 
@@ -598,7 +600,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
              rows_per_thread=1, div_int_check=False, partitioned=False,
              const_div=True, slab_lean=False, div_parallel=False,
-             junction=None, persistent=False):
+             junction=None, persistent=False, split_gates=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -641,6 +643,14 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         Connection graphs cut over several GPUs: CSR columns beyond the local
         cells are ghost cells whose V is read from the ghost buffer the
         owning GPUs push into.
+    ``split_gates``
+        Two kernels per step instead of one: states whose update needs only V
+        and the state itself (gating variables with voltage-dependent rates)
+        get a kernel of their own, ``mkb_gate_step``, with few live values and
+        therefore high occupancy; ``mkb_cell_step`` reads those states but
+        neither computes their rate equations nor updates them. Same
+        expressions, same results; the gates are read twice. For large models
+        held at low occupancy by their register count. One cell per thread.
     ``persistent``
         For grids that fit one thread block (``nx <= bx`` and ``ny <= by``;
         the runtime checks): the kernel ``mkb_cell_step_persistent`` keeps
@@ -696,7 +706,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     slab = bool(slab) and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD)
     cpt = int(cells_per_thread or 1)
     if slab or diffusion_mode == DIFF_CONNECTIONS or cpt not in (2, 4, 8) \
-            or (sp and cpt == 2) or junction or persistent:
+            or (sp and cpt == 2) or junction or persistent or split_gates:
         cpt = 1
     if cpt > 1 and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
         # rim-exchange arrays of the register-patch path (static shared memory)
@@ -713,6 +723,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     if junction and (diffusion_mode != DIFF_HOMOGENEOUS or slab or cpt > 1):
         raise ValueError('A junction needs a homogeneous grid kernel with one'
                          ' cell per thread.')
+    if split_gates and (persistent or junction):
+        raise ValueError('split_gates cannot be combined with persistent or'
+                         ' junction kernels.')
     if persistent and (diffusion_mode == DIFF_CONNECTIONS or slab or junction
                        or partitioned):
         raise ValueError('The persistent kernel is for unsharded grids and'
@@ -880,12 +893,75 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         return sorted(set(out), key=lambda x: x.index())
 
     # ------------------------------------------------------------------
+    # split_gates: which states can leave the big kernel
+    # ------------------------------------------------------------------
+    gate_states = []        # states updated by mkb_gate_step
+    gate_todo = []          # its equations, in the reference's order
+    # (only with diffusion: the second kernel must still find V(t) after the
+    # first has produced V(t + dt), which takes the two V planes)
+    if split_gates and diffusion:
+        def eq_key(eq):
+            return ('D', eq.lhs.var()) if eq.lhs.is_derivative() else eq.lhs.var()
+        by_key = dict((eq_key(eq), eq) for name, eq in todo)
+        bound_set = set(bound_variables)
+
+        def closure(roots):
+            # equations (keys of todo) and states / bound variables reached
+            keys, reads = set(), set()
+            stack = list(roots)
+            while stack:
+                key = stack.pop()
+                if key in keys or key not in by_key:
+                    continue
+                keys.add(key)
+                for ref in by_key[key].rhs.references():
+                    var = ref.var()
+                    if isinstance(ref, myokit.Derivative):
+                        stack.append(('D', var))
+                    elif var in state_set or var in bound_set:
+                        reads.add(var)
+                    else:
+                        stack.append(var)
+            return keys, reads
+
+        def roots_of(var):
+            if var in rl_states:
+                return list(rl_states[var])
+            return [('D', var)]
+        vtime = model.time()
+        gate_keys = set()
+        for var in states:
+            if var is vm:
+                continue
+            keys, reads = closure(roots_of(var))
+            allowed = set([var, vtime])
+            if vm is not None:
+                allowed.add(vm)
+            if reads <= allowed:
+                gate_states.append(var)
+                gate_keys |= keys
+        rest_keys = set()
+        for var in states:
+            if var not in gate_states:
+                rest_keys |= closure(roots_of(var))[0]
+        only_gates = gate_keys - rest_keys
+        if gate_states:
+            gate_todo = [(name, eq) for name, eq in todo if eq_key(eq) in gate_keys]
+            todo = [(name, eq) for name, eq in todo if eq_key(eq) not in only_gates]
+    gate_set = set(gate_states)
+
+    # ------------------------------------------------------------------
     # Section: model body (equations, loads, stores)
     # ------------------------------------------------------------------
     early = []      # state loads hoisted above the stencil (guarded)
     body = []
     if not lazy_state:
+        used = set()
+        for name, eq in todo:
+            used.update(refs(eq.rhs))
         for var in states:
+            if var in gate_set and var not in used:
+                continue
             early.append(state_load(var, guarded=True))
         for name, eq in todo:
             if name:
@@ -898,7 +974,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                     % (inter_index[var], v(eq.lhs)))
         body.append('    // Update (openclsim.cl:358-364)')
         for var in states:
-            body.append(state_update(var))
+            if var not in gate_set:
+                body.append(state_update(var))
     else:
         # Same equations, same order, same arithmetic; only the position of
         # the loads and stores differs. No thread reads another thread's
@@ -910,11 +987,13 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             for r in refs(eq.rhs):
                 first_use.setdefault(r, i)
         for var in states:      # never referenced: needed by its own update
-            first_use.setdefault(var, len(todo))
-        order = sorted(states, key=lambda x: (first_use[x], x.index()))
+            if var not in gate_set:
+                first_use.setdefault(var, len(todo))
+        order = sorted([x for x in states if x in first_use],
+                       key=lambda x: (first_use[x], x.index()))
         loaded = set()
         have = set()
-        done = set()
+        done = set(gate_set)    # updated by mkb_gate_step, if any
         ahead = max(int(load_ahead), 0)
 
         def emit_loads(limit, dest, guarded):
@@ -984,6 +1063,35 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 var = eq.lhs.var()
                 if var not in fields and var not in folded:
                     consts.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+
+    # The body of mkb_gate_step, rendered here: its literals must be in the
+    # constant table before the table is printed
+    gate_lines = []
+    if gate_states:
+        if vm is not None:
+            if diffusion:
+                gate_lines.append('    const Real %s = v_in[cid];' % v(vm))
+            else:
+                gate_lines.append('    const Real %s = state[%dull * stride + cid];'
+                                  % (v(vm), vm.index()))
+        for k, var in enumerate(fields):
+            gate_lines.append(
+                '    const Real %s = ((const Real*)g.field)[%dull * stride + cid];'
+                % (v(var), k))
+        for var in gate_states:
+            gate_lines.append('    const Real %s = state[%dull * stride + cid];'
+                              % (v(var), var.index()))
+        gate_lines.extend(consts)
+        for name, eq in gate_todo:
+            var = eq.lhs.var()
+            gate_lines.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
+            if var in inter_index and not eq.lhs.is_derivative():
+                gate_lines.append(
+                    '    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                    % (inter_index[var], v(eq.lhs)))
+        for var in gate_states:
+            gate_lines.append('    state[%dull * stride + cid] = %s;'
+                              % (var.index(), state_rhs(var)))
 
     # ------------------------------------------------------------------
     # Persistent path: the whole grid in one thread block, many steps per launch
@@ -1628,10 +1736,42 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    }')
     p('}')
     p('')
+    if gate_states:
+        # The second kernel of a split step: runs after mkb_cell_step on the
+        # same stream, reads V(t) from the plane that kernel only read, and
+        # the gates it alone updates.
+        p('// Gating variables whose rates depend on V alone (%d of %d states):'
+          % (len(gate_states), n_state))
+        p('// ' + ', '.join(x.qname() for x in gate_states))
+        p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
+        p('mkb_gate_step(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,')
+        p('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
+        p('{')
+        p('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+        p('    const unsigned long long stride = g.stride;')
+        p('    const unsigned int nby = (ny + MKB_BY - 1) / MKB_BY;')
+        p('    const unsigned int byr = blockIdx.y + blockIdx.z * gridDim.y;')
+        p('    if (byr >= nby) return;')
+        p('    const unsigned int ix = blockIdx.x * MKB_BX + threadIdx.x;')
+        p('    const unsigned int iy = byr * MKB_BY + threadIdx.y;')
+        p('    if (ix >= nx || iy >= ny) return;')
+        p('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
+        p('    Real* const state = (Real*)g.state;')
+        p('    const Real time = (Real)sp->time;')
+        p('    const Real dt = (Real)sp->dt;')
+        p('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
+        p('    (void)time; (void)store_aux; (void)v_in; (void)v_out;')
+        for line in gate_lines:
+            p(line)
+        p('}')
+        p('')
     code = '\n'.join(out)
 
     options = ['--fmad=true' if fmad else '--fmad=false']
     if max_registers:
         options.append('--maxrregcount=%d' % int(max_registers))
-    return KernelSource(code, block, n_state, i_vm, len(inter_log),
-                        len(fields), diffusion_mode, options)
+    ks = KernelSource(code, block, n_state, i_vm, len(inter_log),
+                      len(fields), diffusion_mode, options)
+    ks.gate_kernel = bool(gate_states)
+    ks.gate_states = [x.qname() for x in gate_states]
+    return ks

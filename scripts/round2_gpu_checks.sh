@@ -6,7 +6,7 @@ O=gpurun_out/round2
 mkdir -p $O
 export MKB_TEST_EXPERIMENTAL=1
 # 1. device paths never run before: fibre-tissue pair, lean row-slab kernel
-timeout 300 python -m pytest tests/test_fiber_tissue_gpu.py tests/test_persistent_gpu.py tests/test_multigpu_gpu.py -q -m gpu -k "fiber or pair or lean or persistent" 2>&1 | tail -15 | tee $O/experimental_tests.log
+timeout 300 python -m pytest tests/test_fiber_tissue_gpu.py tests/test_persistent_gpu.py tests/test_multigpu_gpu.py -q -m gpu -k "fiber or pair or lean or persistent or split" 2>&1 | tail -15 | tee $O/experimental_tests.log
 # 2. the regular GPU suite (the V-tile race fix and the larger kernel argument struct are new)
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee $O/gpu_tests.log
 # 3. C3 kernel variants: default, div_parallel, estrin, both

@@ -11,14 +11,14 @@ from myokit_b200 import workloads, multigpu
 from sass_stats import sass_counts
 
 
-def row(label, src):
+def row(label, src, func='mkb_cell_step'):
     pf, log = sass_counts(src)
-    c = pf['mkb_cell_step']
+    c = pf[func]
     tot = sum(c.values())
     fp64 = c['DFMA'] + c['DADD'] + c['DMUL'] + c['DSETP']
     fp32 = c['FFMA'] + c['FADD'] + c['FMUL']
     mufu = sum(v for k, v in c.items() if k.startswith('MUFU'))
-    m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", log)
+    m = re.search(r"Compiling entry function '%s'.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers" % func, log, re.S)
     st, ss, sl, regs = m.groups() if m else ('?',) * 4
     print('| %s | %d | %d | %d | %d | %s | %s / %s |' % (label, tot, fp64, fp32, mufu, regs, ss, sl))
 
@@ -41,6 +41,10 @@ for label, opts in (('default', {}), ('`const_div=False` (before this round\'s r
     s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=64)
     s.set_kernel_options(**opts)
     row(label, s.kernel_source())
+s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=64)
+s.set_kernel_options(split_gates=True)
+row('`split_gates=True`: `mkb_cell_step`', s.kernel_source())
+row('`split_gates=True`: `mkb_gate_step` (10 gating variables)', s.kernel_source(), 'mkb_gate_step')
 box = {}
 
 

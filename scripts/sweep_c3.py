@@ -15,6 +15,8 @@ variants = [
     ('estrin + div_parallel', dict(fast_exp='estrin', div_parallel=True)),
     ('exp table (fewest FP64 instructions)', dict(fast_exp='table')),
     ('table + div_parallel', dict(fast_exp='table', div_parallel=True)),
+    ('split gates (two kernels per step)', dict(split_gates=True)),
+    ('split gates + div_parallel', dict(split_gates=True, div_parallel=True)),
     ('const_div off', dict(const_div=False)),
 ]
 only = os.environ.get('SWEEP_ONLY')

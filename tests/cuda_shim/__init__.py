@@ -22,7 +22,7 @@ _BUILD = os.path.join(_HERE, '_build')
 _CSRC = os.path.join(_ROOT, 'myokit_b200', 'csrc')
 
 
-def _compile(code, contract, kernel_name='mkb_cell_step'):
+def _compile(code, contract, kernel_name='mkb_cell_step', second=None):
     os.makedirs(_BUILD, exist_ok=True)
     with open(os.path.join(_HERE, 'runner.cpp'), 'rb') as f:
         runner = f.read()
@@ -30,7 +30,8 @@ def _compile(code, contract, kernel_name='mkb_cell_step'):
         shim = f.read()
     key = hashlib.sha1(code.encode('utf-8') + runner + shim
                        + (b'c' if contract else b'n')
-                       + kernel_name.encode('ascii')).hexdigest()[:20]
+                       + kernel_name.encode('ascii')
+                       + (second or '').encode('ascii')).hexdigest()[:20]
     so = os.path.join(_BUILD, 'k_%s.so' % key)
     if not os.path.isfile(so):
         cu = os.path.join(_BUILD, 'k_%s.cu.h' % key)
@@ -43,6 +44,8 @@ def _compile(code, contract, kernel_name='mkb_cell_step'):
                '-DMKB_KERNEL_FILE="%s"' % cu, '-DMKB_KERNEL_FN=' + kernel_name,
                '-I' + _CSRC, '-I' + _HERE,
                os.path.join(_HERE, 'runner.cpp'), '-o', tmp]
+        if second:
+            cmd.insert(-3, '-DMKB_KERNEL_FN2=' + second)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('host build of the generated kernel failed:\n'
@@ -87,7 +90,8 @@ def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None,
     src = sim.kernel_source(inter_vars)
     if contract is None:
         contract = '--fmad=true' in src.options
-    lib = _compile(src.code, contract, src.kernel_name)
+    lib = _compile(src.code, contract, src.kernel_name,
+                   'mkb_gate_step' if getattr(src, 'gate_kernel', False) else None)
     lib.shim_set_thread_order(1 if reverse else 0)
     lib.shim_set_persistent(1 if getattr(src, 'persistent', False) else 0)
     nx, ny = sim._nx, sim._ny
@@ -180,7 +184,8 @@ def run_slabs_on_host(make, n_slabs, duration, log_interval=1.0, options=None,
     src = box['src']
     assert 'peer_lo_halo_hi' in src.code      # the slab variant
     contract = '--fmad=true' in src.options
-    lib = _compile(src.code, contract)
+    lib = _compile(src.code, contract, src.kernel_name,
+                   'mkb_gate_step' if getattr(src, 'gate_kernel', False) else None)
     lib.shim_set_thread_order(1 if reverse else 0)
     nx, ny = whole._nx, whole._ny
     n = nx * ny

@@ -41,7 +41,17 @@ struct Launch {
 #define MKB_KERNEL_FN mkb_cell_step
 #endif
 
+// a split step has a second kernel, launched after the first over the same grid
+int g_second = 0;
+
 void fiber_main() {
+#ifdef MKB_KERNEL_FN2
+    if (g_second) {
+        MKB_KERNEL_FN2(g_launch.g, g_launch.sp, g_launch.v_in, g_launch.v_out);
+        g_cur->done = true;
+        swapcontext(&g_cur->ctx, &g_sched);
+    }
+#endif
     MKB_KERNEL_FN(g_launch.g, g_launch.sp, g_launch.v_in, g_launch.v_out);
     g_cur->done = true;
     swapcontext(&g_cur->ctx, &g_sched);
@@ -226,14 +236,22 @@ extern "C" int shim_run(
         g_launch.sp = run.data();
         g_launch.v_in = v_in;
         g_launch.v_out = v_out;
-        for (unsigned int bz = 0; bz < gbz; bz++) {
-            for (unsigned int by = 0; by < gby; by++) {
-                for (unsigned int bx = 0; bx < gbx; bx++) {
-                    blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-                    run_block(fibers, stacks, (unsigned int)block_x, (unsigned int)block_y);
+#ifdef MKB_KERNEL_FN2
+        for (int pass = 0; pass < 2; pass++) {
+            g_second = pass;
+#else
+        {
+#endif
+            for (unsigned int bz = 0; bz < gbz; bz++) {
+                for (unsigned int by = 0; by < gby; by++) {
+                    for (unsigned int bx = 0; bx < gbx; bx++) {
+                        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                        run_block(fibers, stacks, (unsigned int)block_x, (unsigned int)block_y);
+                    }
                 }
             }
         }
+        g_second = 0;
         if (st_log[s]) {
             if (log_idiff) for (size_t c = 0; c < n; c++) log_idiff[row_out * n + c] = (double)idiff[c];
             if (log_inter) {
@@ -412,14 +430,22 @@ extern "C" int shim_run_slabs(
             g_launch.sp = &sp;
             g_launch.v_in = v_in;
             g_launch.v_out = v_out;
-            for (unsigned int bz = 0; bz < gridDim.z; bz++) {
-                for (unsigned int by = 0; by < gridDim.y; by++) {
-                    for (unsigned int bx = 0; bx < gridDim.x; bx++) {
-                        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-                        run_block(fibers, stacks, (unsigned int)block_x, (unsigned int)block_y);
+#ifdef MKB_KERNEL_FN2
+            for (int pass = 0; pass < 2; pass++) {
+                g_second = pass;
+#else
+            {
+#endif
+                for (unsigned int bz = 0; bz < gridDim.z; bz++) {
+                    for (unsigned int by = 0; by < gridDim.y; by++) {
+                        for (unsigned int bx = 0; bx < gridDim.x; bx++) {
+                            blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                            run_block(fibers, stacks, (unsigned int)block_x, (unsigned int)block_y);
+                        }
                     }
                 }
             }
+            g_second = 0;
             if (st_log[st] && log_idiff) {
                 for (size_t c = 0; c < s.n; c++) log_idiff[row_out * ntot + s.iy0 * nx + c] = (double)s.idiff[c];
             }

@@ -587,3 +587,80 @@ def test_persistent_kernel_limits_and_name():
     # the default stays the one-step kernel
     d = myokit_b200.SimulationCUDA(m, None, ncells=128, precision=DP)
     assert d.kernel_source().kernel_name == 'mkb_cell_step'
+
+
+# ---------------------------------------------------------------------------
+# split_gates (opt-in): gating variables with voltage-dependent rates in a
+# kernel of their own, launched after the big one.
+# ---------------------------------------------------------------------------
+def test_split_gates_two_kernels_equal_one():
+    def make(cls):
+        return workloads.c3_hetero(cls, nx=12, ny=9)
+    s = make(myokit_b200.SimulationCUDA)
+    s.set_kernel_options(split_gates=True)
+    src = s.kernel_source()
+    assert src.gate_kernel and 'ina.m' in src.gate_states and 'ikr.a' in src.gate_states
+    assert 'membrane.V' not in src.gate_states and len(src.gate_states) == 10
+    big, gates = src.code.split('mkb_gate_step(const MkbGridArgs g')
+    # the big kernel neither computes the gates' rates nor stores the gates
+    assert 'V_ina_h_alpha' not in big.split('extern "C" __global__')[1]
+    assert 'V_ina_h_alpha' in gates
+    k = s._model.get('ina.m').index()
+    assert 'state[%dull * stride + cid] =' % k not in big
+    assert 'state[%dull * stride + cid] =' % k in gates
+    # bit for bit with the rewrites off (a logged intermediary of each kernel)
+    got, want, wstate = both(make, dict(EXACT, block=(8, 4), split_gates=True),
+                             3.0, 0.5, 12, 9, inter_log=['ina.h.alpha', 'ikr.IKr'])
+    assert want['membrane.V'].max() > 0
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['inter'][:, 0], want['ina.h.alpha'])
+    assert np.array_equal(got['inter'][:, 1], want['ikr.IKr'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+    # defaults: as close to the oracle as the single kernel
+    got, want, wstate = both(make, dict(block=(8, 4), split_gates=True), 3.0, 0.5, 12, 9)
+    assert np.abs(got['V'] - want['membrane.V']).max() <= 1e-9
+    rel = np.abs(got['state'].ravel() - wstate) / (np.abs(wstate) + 1e-12)
+    assert rel.max() <= 1e-6
+
+
+def test_split_gates_other_models_and_no_gates():
+    # LR1991 forward Euler: m, h, j, d, f, x depend on V only
+    def make(cls):
+        return lr91_2d(cls, nx=9, ny=6)
+    s = make(myokit_b200.SimulationCUDA)
+    s.set_kernel_options(split_gates=True)
+    src = s.kernel_source()
+    assert src.gate_kernel and set(src.gate_states) >= {'ina.m', 'ina.h', 'ina.j'}
+    got, want, wstate = both(make, dict(EXACT, block=(8, 4), split_gates=True), 4.0, 0.5, 9, 6)
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+    # uncoupled cells, Rush-Larsen
+    m, _, _ = myokit.load('example')
+    p = myokit.pacing.blocktrain(period=1000, duration=2, offset=1)
+
+    def cells(cls):
+        return cls(m, p, ncells=13, diffusion=False, precision=DP, rl=True)
+    c = cells(myokit_b200.SimulationCUDA)
+    c.set_kernel_options(split_gates=True)
+    assert not c.kernel_source().gate_kernel    # V is not double-buffered here
+    got, want, wstate = both(cells, dict(EXACT, block=(8, 1), split_gates=True), 4.0, 0.5, 13, 1)
+    assert np.array_equal(got['state'].ravel(), wstate)
+    # a model without such states keeps its single kernel
+    st = workloads.stencil_only(myokit_b200.SimulationCUDA, 16, 8, precision=DP)
+    st.set_kernel_options(split_gates=True)
+    assert not st.kernel_source().gate_kernel
+
+
+def test_split_gates_with_row_slabs():
+    def make(comm):
+        kw = {} if comm is None else dict(comm=comm)
+        return workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=12, ny=11, **kw)
+    opts = dict(EXACT, block=(8, 4))
+    whole = make(None)
+    whole.set_kernel_options(**opts)
+    one = cuda_shim.run_on_host(whole, 3.0, log_interval=0.5)
+    out = cuda_shim.run_slabs_on_host(make, 3, 3.0, 0.5, dict(opts, split_gates=True))
+    assert out['halo_error'] == 0
+    assert np.array_equal(out['V'], one['V'])
+    assert np.array_equal(out['state'], one['state'])

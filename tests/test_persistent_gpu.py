@@ -68,3 +68,24 @@ def test_persistent_small_grid_rush_larsen_fields():
     for k in fb:
         assert np.array_equal(fa[k], fb[k])
     assert np.array_equal(a.state_array(), b.state_array())
+
+
+def test_split_gates_equals_single_kernel_on_device():
+    # kernelgen split_gates: mkb_cell_step + mkb_gate_step per step (also inside
+    # the 64-step graphs) against the single kernel; same expressions, so the
+    # results must be identical
+    from myokit_b200 import workloads
+
+    def make(split):
+        s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=96, ny=40)
+        s.set_kernel_options(split_gates=split)
+        return s
+    a, b = make(True), make(False)
+    assert a.kernel_source().gate_kernel
+    ta, fa = a.run_fields(3.0, ['membrane.V', 'ina.m'], log_interval=0.5)
+    tb, fb = b.run_fields(3.0, ['membrane.V', 'ina.m'], log_interval=0.5)
+    assert fb['membrane.V'].max() > 0
+    for k in fb:
+        assert np.array_equal(fa[k], fb[k]), k
+    assert np.array_equal(a.state_array(), b.state_array())
+    assert a.last_run_info()['kernel_launches'] >= 2 * a.last_run_info()['steps']
