@@ -1044,9 +1044,12 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     // Model kernel
     INIT_CUDA(cudaLibraryLoadData(&s->lib, c->cubin, nullptr, nullptr, 0, nullptr, nullptr, 0));
     INIT_CUDA(cudaLibraryGetKernel(&s->kern, s->lib, c->kernel_name));
-    if (cudaLibraryGetKernel(&s->kern2, s->lib, "mkb_gate_step") != cudaSuccess) {
-        s->kern2 = nullptr;     // an ordinary, single-kernel step
-        cudaGetLastError();
+    // (asked for only when the image names it: ordinary images see no extra call)
+    if (memmem(c->cubin, c->cubin_size, "mkb_gate_step", 13) != nullptr) {
+        if (cudaLibraryGetKernel(&s->kern2, s->lib, "mkb_gate_step") != cudaSuccess) {
+            s->kern2 = nullptr;
+            cudaGetLastError();
+        }
     }
     s->persistent = strcmp(c->kernel_name, "mkb_cell_step_persistent") == 0;
     if (s->persistent) {
