@@ -29,7 +29,7 @@ def test_persistent_cable_equals_default_kernel_and_oracle():
         s = myokit_b200.SimulationCUDA(m, p, ncells=128, precision=DP)
         s.set_conductance(10)
         s.set_paced_cells(5)
-        s.set_kernel_options(persistent=persistent)
+        s.set_kernel_options(persistent=persistent, fmad=False)
         return s
     a, b = make(True), make(False)
     log = ['engine.time', 'membrane.V', 'membrane.i_diff', 'ina.INa']
@@ -59,7 +59,7 @@ def test_persistent_small_grid_rush_larsen_fields():
         s = myokit_b200.SimulationCUDA(m, p, ncells=(10, 6), precision=DP, rl=True)
         s.set_conductance_field(gxf, gyf)
         s.set_paced_cells(3, 6, 0, 0)
-        s.set_kernel_options(persistent=persistent)
+        s.set_kernel_options(persistent=persistent, fmad=False)
         return s
     a, b = make(True), make(False)
     ta, fa = a.run_fields(6, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
@@ -78,7 +78,9 @@ def test_split_gates_equals_single_kernel_on_device():
 
     def make(split):
         s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=96, ny=40)
-        s.set_kernel_options(split_gates=split)
+        # (no FMA contraction: the compiler contracts per kernel, and the two
+        # forms are different kernels)
+        s.set_kernel_options(split_gates=split, fmad=False)
         return s
     a, b = make(True), make(False)
     assert a.kernel_source().gate_kernel
