@@ -113,9 +113,9 @@ def library():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.isfile(path):
-        path = _build.build_library()
+    # (stamp check: a library built from older sources is rebuilt, never
+    # loaded next to a newer generator)
+    path = _build.build_library(force=False)
     lib = ctypes.CDLL(path)
     lib.mkb_abi_version.restype = ctypes.c_int
     lib.mkb_last_error.restype = ctypes.c_char_p

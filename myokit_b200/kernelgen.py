@@ -228,6 +228,8 @@ _PRELUDE = r"""
 #define MKB_ASM_RCP64(r, b) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b))
 #define MKB_ASM_SREG(v, name) asm volatile("mov.u32 %0, %%" name ";" : "=r"(v))
 #define MKB_ASM_EX2F(y, t) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t))
+#define MKB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+#define MKB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
 #endif
 
 // x^k for a compile-time integer k: square-and-multiply, fixed order.
@@ -306,6 +308,25 @@ __device__ __forceinline__ double mkb_div(double a, double b) {
     double r;
     MKB_ASM_RCP64(r, b);
     const double e = fma(-b, r, 1.0);
+#if MKB_DIV_CUBIC
+    // Option div_cubic: one third-order step on the reciprocal, r (1 + e + e^2)
+    // (relative error e^3 < 2^-60 from the >= 20-bit seed), then the product:
+    // 4 FP64 instructions instead of 6, no residual correction and therefore
+    // no NaN from inf - inf for an infinite dividend. A divisor of 0 or inf
+    // gives a seed of inf / 0 and e = NaN; the seed's exponent field (all ones
+    // / all zeros) is tested on the integer pipe and the correction factor is
+    // then replaced by a finite number (one 32-bit select on its high word),
+    // so r stays inf / 0 and a * r is the IEEE quotient (a / 0 = inf,
+    // a / inf = 0, 0 / 0 = NaN). Error <= 1.5 ulp of the quotient (two
+    // roundings: reciprocal and product; reciprocals 1 / b: <= 1 ulp);
+    // denormal divisors count as 0 (rcp.approx.ftz).
+    double e2 = fma(e, e, e);
+    const unsigned int rh = (unsigned int)__double2hiint(r);
+    const bool special = ((rh + 0x00100000u) & 0x7fe00000u) == 0u;
+    e2 = __hiloint2double(special ? 0x3ff00000 : __double2hiint(e2), __double2loint(e2));
+    r = fma(r, e2, r);
+    return a * r;
+#endif
 #if MKB_DIV_PARALLEL
     // Quotient and reciprocal are refined side by side (dependent chain of 4
     // instead of 5 after the seed, same instruction count).
@@ -341,9 +362,10 @@ __device__ __forceinline__ float mkb_div(float a, float b) {
 // integer add, no branches. The coefficients live in constant memory so they
 // arrive as c-bank operands / paired uniform loads instead of two 32-bit
 // moves each. Outside the normal range the result saturates instead of
-// following IEEE: x < -708 gives a value below 2.3e-308 (not a denormal or
-// 0), x > 709.7 gives a huge finite value or NaN (not +inf); NaN gives NaN;
-// |x| >= 2^31 and infinities are not supported.
+// following IEEE, and is never NaN or inf for a finite argument: x < -708
+// gives a value below 4.5e-308 (not a denormal or 0), x > 709.4 a value above
+// 6e307 (not +inf; between 709.4 and 709.78 it is half the true value).
+// NaN gives NaN; |x| >= 2^31 and infinities are not supported.
 __constant__ double mkb_exp_c[14] = {
 @EXP_TABLE@
 };
@@ -358,7 +380,7 @@ __device__ __forceinline__ double mkb_exp_poly(double x) {
     for (int k = 5; k < 14; k++) p = fma(p, r, mkb_exp_c[k]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const int nc = min(max(n, -1021), 1024);
+    const int nc = min(max(n, -1021), 1023);
     const double y = __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
     return y;
 }
@@ -405,7 +427,7 @@ __device__ __forceinline__ double mkb_exp_estrin(double x) {
     const double q = fma(a5, r8, d);
     double p = fma(r2, q, r);
     p += 1.0;
-    const int nc = min(max(n, -1021), 1024);
+    const int nc = min(max(n, -1021), 1023);
     return __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
 }
 
@@ -416,13 +438,41 @@ __device__ __forceinline__ double mkb_exp_estrin(double x) {
 // Measured on C3 it is no faster than the polynomial form (the kernel is as
 // much issue- as FP64-bound and this variant trades 7 FP64 for 6 integer /
 // load instructions), so the polynomial form is the default.
-// Same saturation behaviour as mkb_exp_poly.
+// Saturation as in mkb_exp_stab below.
 __device__ const double mkb_exp_t[64] = {
 @EXP_POW2@
 };
 __constant__ double mkb_expt_c[8] = {
 @EXP_TCOEF@
 };
+// Shared-memory table variant (option fast_exp = 'stab'): the same algorithm
+// with the 64-entry table copied to shared memory by every thread block
+// (short, fixed latency instead of a global load) and the power of two
+// applied to the table entry before the last multiply-add. n is clamped to
+// [-1023 * 64, 1023 * 64 + 63]: at the lower end the scaled entry is exactly
+// 0, so exp underflows to 0 (results below 2^-1022 are flushed, and between
+// -709.8 and -709.1 some tiny denormal comes out); at the upper end it is
+// 1.98 * 2^1023, so exp saturates just below DBL_MAX instead of overflowing
+// to +inf (inf * p + inf would be NaN for a negative p) — never NaN or inf
+// for a finite argument, and 1 / (1 + exp(big)) is 0. 10 FP64-pipe
+// instructions.
+__shared__ double mkb_exp_ts[64];
+#define MKB_EXP_TABLE_INIT(tid, nthreads) do { for (unsigned int i_ = (tid); i_ < 64u; i_ += (nthreads)) mkb_exp_ts[i_] = mkb_exp_t[i_]; } while (0)
+__device__ __forceinline__ double mkb_exp_stab(double x) {
+    double t = fma(x, mkb_expt_c[0], mkb_expt_c[1]);
+    const int n = __double2loint(t);
+    t -= mkb_expt_c[1];
+    double r = fma(t, mkb_expt_c[2], x);
+    r = fma(t, mkb_expt_c[3], r);
+    const int nc = min(max(n, -1023 * 64), 1023 * 64 + 63);
+    const double tj = mkb_exp_ts[nc & 63];
+    double p = fma(mkb_expt_c[4], r, mkb_expt_c[5]);
+    p = fma(p, r, mkb_expt_c[6]);
+    p = fma(p, r, mkb_expt_c[7]);
+    p = fma(r * r, p, r);
+    const double ts = __hiloint2double(__double2hiint(tj) + ((nc >> 6) << 20), __double2loint(tj));
+    return fma(ts, p, ts);
+}
 __device__ __forceinline__ double mkb_exp_tab(double x) {
     double t = fma(x, mkb_expt_c[0], mkb_expt_c[1]);
     const int n = __double2loint(t);
@@ -433,10 +483,10 @@ __device__ __forceinline__ double mkb_exp_tab(double x) {
     p = fma(p, r, mkb_expt_c[6]);
     p = fma(p, r, mkb_expt_c[7]);
     p = fma(r * r, p, r);
-    const int nc = min(max(n, -1021 * 64), 1024 * 64);
+    const int nc = min(max(n, -1023 * 64), 1023 * 64 + 63);
     const double tj = __ldg(&mkb_exp_t[nc & 63]);
-    const double y = fma(tj, p, tj);
-    return __hiloint2double(__double2hiint(y) + ((nc >> 6) << 20), __double2loint(y));
+    const double ts = __hiloint2double(__double2hiint(tj) + ((nc >> 6) << 20), __double2loint(tj));
+    return fma(ts, p, ts);
 }
 """
 
@@ -600,7 +650,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              const_pool=True, load_ahead=8, slab=False, cells_per_thread=1,
              rows_per_thread=1, div_int_check=False, partitioned=False,
              const_div=True, slab_lean=False, div_parallel=False,
-             junction=None, persistent=False, split_gates=False):
+             junction=None, persistent=False, split_gates=False,
+             div_cubic=False, prefetch=None):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -665,6 +716,15 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         the current to / from the other grid's cell to ``idiff`` after their
         own stencil, as ``diff_step_fiber_tissue`` does
         (``openclsim.cl:601-628``). Homogeneous 2-d grids, one cell per thread.
+    ``prefetch``
+        ``'l1'`` or ``'l2'``: every state that is loaded later in the body
+        (``load_ahead``) is prefetched into that cache level at the top of the
+        kernel, so the load proper finds it close by: the memory latency is
+        covered without holding a register for the value.
+    ``div_cubic``
+        ``mkb_div`` with one third-order refinement of the reciprocal and no
+        residual correction: 4 FP64 instructions instead of 6, IEEE results
+        for divisors 0 and inf, at most 1.5 ulp from the quotient.
     ``div_parallel``
         ``mkb_div`` refines quotient and reciprocal side by side: a shorter
         dependent chain, and IEEE results for divisors 0 and inf. Same
@@ -691,6 +751,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         w = _Writer(precision)
         w._fast_div = bool(fast_div)
         w._fast_exp = ({'table': 'mkb_exp_tab', 'poly': 'mkb_exp_poly',
+                        'stab': 'mkb_exp_stab',
                         'estrin': 'mkb_exp_estrin', 'ex2': 'mkb_expf_ex2'}.get(
             fast_exp, 'mkb_exp_poly') if fast_exp else False)
         if (fast_exp == 'ex2') != bool(sp) and fast_exp == 'ex2':
@@ -698,6 +759,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         if const_pool and not sp:
             w.enable_pool()
     w._pow_multiply = bool(pow_multiply)
+    # the shared-memory exp table must be filled by every thread block
+    stab = (fast_exp == 'stab') and not sp and not native_maths
     pooled = getattr(w, '_pool', None) is not None
     fields = list(fields)
     inter_log = list(inter_log)
@@ -954,6 +1017,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     # Section: model body (equations, loads, stores)
     # ------------------------------------------------------------------
     early = []      # state loads hoisted above the stencil (guarded)
+    early_states = set()
+    gate_set_unused = set()
     body = []
     if not lazy_state:
         used = set()
@@ -1020,6 +1085,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                     done.add(var)
 
         emit_loads(ahead, early, True)
+        early_states = set(loaded)
+        gate_set_unused = set(x for x in gate_set if x not in first_use)
         for i, (name, eq) in enumerate(todo):
             if name:
                 body.append('    // Component: %s' % name)
@@ -1107,6 +1174,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_BY %d' % by)
         q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
         q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
+        q('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
         q(_PRELUDE)
         if pooled and w._pool:
             q('__constant__ double mkb_k[%d] = {' % len(w._pool))
@@ -1148,6 +1216,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             q('    const Real gyp = has_yp ? gyf[cid] : (Real)0;')
         if diffusion:
             q('    __shared__ Real tile[MKB_BY + 2][MKB_BX + 2];')
+        if stab:
+            q('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
+            q('    __syncthreads();')
         q('    // number of steps of this launch: upper bits of the first record\'s flags')
         q('    const unsigned int count = sp_first->flags >> 8;')
         q('    for (unsigned int it = 0; it < count; it++) {')
@@ -1266,6 +1337,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_RPT %d' % rpt)
         q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
         q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
+        q('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
         q(_PRELUDE)
         q(_VECTOR_PRELUDE)
         if pooled and w._pool:
@@ -1332,9 +1404,11 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             q('    for (int r = 0; r < MKB_RPT; r++) {')
             q('        const unsigned int iy = iy0 + r;')
             q('        const unsigned int tr = ty * MKB_RPT + r;')
-            q('        col_l[tr][tx + 1] = vc[r][0];')
-            q('        col_r[tr][tx + 1] = vc[r][MKB_CPT - 1];')
+            q('        // (own slots only for threads of the grid: the slot of a thread past the')
+            q('        // last column is the halo slot of its left neighbour, written below)')
             q('        if (in_x && iy < ny) {')
+            q('            col_l[tr][tx + 1] = vc[r][0];')
+            q('            col_r[tr][tx + 1] = vc[r][MKB_CPT - 1];')
             q('            const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
             q('            // halo cells left and right of the block')
             q('            if (tx == 0) col_r[tr][0] = (ix0 > 0) ? v_in[cid0 - 1] : vc[r][0];')
@@ -1363,10 +1437,15 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             q('            for (int c = 0; c < MKB_CPT; c++) row_t[MKB_BY + 1][tx * MKB_CPT + c] = vn[c];')
             q('        }')
             q('    }')
+            if stab:
+                q('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
             q('    __syncthreads();')
             q('    if (!in_x || iy0 >= ny) return;')
             q('    const bool at_x0 = (ix0 == 0), at_x1 = (ix0 + MKB_CPT == nx);')
         else:
+            if stab:
+                q('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
+                q('    __syncthreads();')
             q('    if (!in_x || iy0 >= ny) return;')
         if diffusion_mode == DIFF_HOMOGENEOUS:
             q('    const Real gx = (Real)g.gx, gy = (Real)g.gy;')
@@ -1493,6 +1572,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('#define MKB_BY %d' % by)
     p('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
     p('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
+    p('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
     p(_PRELUDE)
     if pooled and w._pool:
         p('// Model constants (double precision), in order of first use')
@@ -1582,6 +1662,14 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    // Loads issued ahead of use: fields and the first states')
     for line in early:
         p(line)
+    if prefetch and lazy_state:
+        p('    // The other states: only prefetched here, loaded where they are used')
+        p('    if (active) {')
+        for var in states:
+            if var.index() != i_vm and var not in early_states and var not in gate_set_unused:
+                p('        MKB_PREFETCH_%s(state + %dull * stride + cid);'
+                  % ('L1' if prefetch == 'l1' else 'L2', var.index()))
+        p('    }')
     p('')
 
     if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
@@ -1615,6 +1703,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('            tile[ty + 2][tx + 1] = vn;')
         p('        }')
         p('    }')
+        if stab:
+            p('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
         p('    __syncthreads();')
         if slab and not slab_lean:
             p('    if (active) {')
@@ -1658,6 +1748,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('    if (has_ym) idiff += gym * (vc - vym);')
             p('    if (has_yp) idiff += gyp * (vc - vyp);')
     elif diffusion_mode == DIFF_CONNECTIONS:
+        if stab:
+            p('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
+            p('    __syncthreads();')
         p('    if (!active) return;')
         p('    // openclsim.cl:537-556 as a per-cell CSR gather: same terms')
         p('    // g * (V_i - V_j), summed in edge-list order, no atomics.')
@@ -1679,6 +1772,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('        }')
         p('    }')
     else:
+        if stab:
+            p('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
+            p('    __syncthreads();')
         p('    if (!active) return;')
     p('')
 
@@ -1754,6 +1850,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    if (byr >= nby) return;')
         p('    const unsigned int ix = blockIdx.x * MKB_BX + threadIdx.x;')
         p('    const unsigned int iy = byr * MKB_BY + threadIdx.y;')
+        if stab:
+            p('    MKB_EXP_TABLE_INIT(threadIdx.y * MKB_BX + threadIdx.x, MKB_BX * MKB_BY);')
+            p('    __syncthreads();')
         p('    if (ix >= nx || iy >= ny) return;')
         p('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
         p('    Real* const state = (Real*)g.state;')

@@ -1,4 +1,7 @@
-"""Kernel-option sweep on the C3 workload: compile stats here, timings on a GPU."""
+"""Kernel-option sweep on the C3 workload: compile stats here, timings on a GPU.
+
+    SWEEP_SET=r2a SWEEP_STEPS=30 python scripts/sweep_c3.py
+"""
 import os, sys, time, re
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
@@ -7,34 +10,83 @@ from myokit_b200 import workloads, capi
 
 grid = int(os.environ.get('SWEEP_GRID', '2048'))
 steps = int(os.environ.get('SWEEP_STEPS', '20'))
-variants = [
-    ('default', dict()),
-    # prepared in round 1 without GPU time left to measure them:
-    ('div_parallel', dict(div_parallel=True)),
-    ('exp estrin', dict(fast_exp='estrin')),
-    ('estrin + div_parallel', dict(fast_exp='estrin', div_parallel=True)),
-    ('exp table (fewest FP64 instructions)', dict(fast_exp='table')),
-    ('table + div_parallel', dict(fast_exp='table', div_parallel=True)),
-    ('split gates (two kernels per step)', dict(split_gates=True)),
-    ('split gates + div_parallel', dict(split_gates=True, div_parallel=True)),
-    ('const_div off', dict(const_div=False)),
-]
+B3 = dict(div_cubic=True, fast_exp='stab')
+
+
+def also(base, **kw):
+    d = dict(base)
+    d.update(kw)
+    return d
+
+
+SETS = {
+    'r1': [
+        ('default', dict()),
+        ('div_parallel', dict(div_parallel=True)),
+        ('exp estrin', dict(fast_exp='estrin')),
+        ('exp table', dict(fast_exp='table')),
+        ('split gates', dict(split_gates=True)),
+        ('const_div off', dict(const_div=False)),
+    ],
+    # round 2, first pass: cheaper division / exp, thread-block shapes, prefetch
+    'r2a': [
+        ('default', dict()),
+        ('div_cubic', dict(div_cubic=True)),
+        ('exp stab', dict(fast_exp='stab')),
+        ('cubic+stab', B3),
+        ('cubic+stab 64x2 mb4', also(B3, block=(64, 2), min_blocks=4)),
+        ('cubic+stab 32x4 mb4', also(B3, block=(32, 4), min_blocks=4)),
+        ('cubic+stab 128x1 mb4', also(B3, block=(128, 1), min_blocks=4)),
+        ('cubic+stab 32x2 mb8', also(B3, block=(32, 2), min_blocks=8)),
+        ('cubic+stab 64x1 mb8', also(B3, block=(64, 1), min_blocks=8)),
+        ('cubic+stab 64x2 mb5 (96 regs)', also(B3, block=(64, 2), min_blocks=5)),
+        ('cubic+stab 64x2 mb6 (80 regs)', also(B3, block=(64, 2), min_blocks=6)),
+        ('cubic+stab 64x6 mb1 (168 regs)', also(B3, block=(64, 6), min_blocks=1, max_registers=168)),
+        ('cubic+stab 64x3 mb2 (168 regs)', also(B3, block=(64, 3), min_blocks=2, max_registers=168)),
+        ('cubic+stab la4', also(B3, load_ahead=4)),
+        ('cubic+stab la8', also(B3, load_ahead=8)),
+        ('cubic+stab la16', also(B3, load_ahead=16)),
+        ('cubic+stab la64', also(B3, load_ahead=64)),
+        ('cubic+stab pf-l1 la4', also(B3, prefetch='l1', load_ahead=4)),
+        ('cubic+stab pf-l1 la8', also(B3, prefetch='l1', load_ahead=8)),
+        ('cubic+stab pf-l1 la16', also(B3, prefetch='l1', load_ahead=16)),
+        ('cubic+stab pf-l2 la8', also(B3, prefetch='l2', load_ahead=8)),
+        ('cubic+stab pf-l1 la8 64x2 mb4', also(B3, prefetch='l1', load_ahead=8, block=(64, 2), min_blocks=4)),
+        ('cubic+stab split gates', also(B3, split_gates=True)),
+        ('cubic+stab nofmad', also(B3, fmad=False)),
+    ],
+}
+variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
 gpu = capi.device_count() > 0
+s = None
 for name, opts in variants:
     if only and only not in name:
         continue
-    s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=grid if gpu else 16)
-    s.set_kernel_options(**opts)
+    if s is None or not gpu:
+        s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=grid if gpu else 16)
+    # one simulation, re-optioned: the state stays in HBM across variants
+    s.set_kernel_options(**dict(dict(
+        block=(64, 4), min_blocks=2, max_registers=0, load_ahead=32, prefetch=None,
+        div_cubic=False, fast_exp='poly', split_gates=False, div_parallel=False,
+        const_div=True, fmad=True), **opts))
     src = s.kernel_source()
     t0 = time.time()
-    cubin, log = capi.jit_compile(src.code, src.options + ('--ptxas-options=-v',))
+    try:
+        cubin, log = capi.jit_compile(src.code, src.options + ('--ptxas-options=-v',))
+    except Exception as e:
+        print('%-36s compile failed: %s' % (name, str(e)[:200]))
+        continue
     m = re.search(r"Compiling entry function 'mkb_cell_step'.*?Used (\d+) registers", log, re.S)
     sp = re.search(r"mkb_cell_step\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores", log, re.S)
-    line = '%-22s regs %s stack/spill %s cubin %d KB compile %.1fs' % (
-        name, m.group(1) if m else '?', sp.groups() if sp else '?', len(cubin) // 1024, time.time() - t0)
+    line = '%-36s regs %s stack/spill %s' % (
+        name, m.group(1) if m else '?', '/'.join(sp.groups()) if sp else '?')
     if gpu:
-        info = s.benchmark_steps(steps, warmup=3)
-        ms = info['device_ms'] / info['steps']
-        line += '  %.3f ms/step  %.3e cell-steps/s' % (ms, grid * grid / ms * 1e3)
+        try:
+            info = s.benchmark_steps(steps, warmup=3)
+            ms = info['device_ms'] / info['steps']
+            line += '  %.4f ms/step  %.3e cell-steps/s' % (ms, grid * grid / ms * 1e3)
+        except Exception as e:
+            line += '  run failed: %s' % str(e)[:200]
+            s = None
     print(line, flush=True)

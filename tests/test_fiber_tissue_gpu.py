@@ -3,9 +3,8 @@ FiberTissueSimulationCUDA on the device against the fibre-tissue oracle.
 
 The junction kernels already equal the oracle bit for bit on the host
 (tests/test_generated_kernel_host.py); what these tests add is the device
-path: mkb_sim_junction_connect / mkb_sim_step_pair, written after the GPU
-budget of round 1 was spent. They run only with MKB_TEST_EXPERIMENTAL=1 until
-they have passed on a GPU once.
+path: mkb_sim_junction_connect / mkb_sim_step_pair (first run, and green, on
+a B200 in round 2).
 """
 import os
 
@@ -16,12 +15,7 @@ import myokit_b200
 import myokit
 from oracle.fiber_tissue import OracleFiberTissue
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(not os.environ.get('MKB_TEST_EXPERIMENTAL'),
-                       reason='device path of the fibre-tissue pair not yet'
-                              ' run on a GPU; set MKB_TEST_EXPERIMENTAL=1'),
-]
+pytestmark = pytest.mark.gpu
 
 DATA = os.path.join(os.path.dirname(myokit.__file__), 'tests', 'data')
 DP = myokit.DOUBLE_PRECISION

@@ -96,8 +96,12 @@ def test_decker_hetero_rush_larsen_fields():
     dict(const_div=False),
     dict(load_ahead=4, lazy_state=True),
     dict(lazy_state=False),
+    dict(div_cubic=True),
+    dict(fast_exp='stab'),
+    dict(div_cubic=True, fast_exp='stab', prefetch='l1', load_ahead=8),
 ], ids=['default', 'div_parallel', 'estrin', 'table', 'no_const_div',
-        'load_ahead4', 'eager_loads'])
+        'load_ahead4', 'eager_loads', 'div_cubic', 'exp_stab',
+        'cubic_stab_prefetch'])
 def test_decker_arithmetic_rewrites_within_the_fp64_bar(options):
     def make(cls):
         return workloads.c3_hetero(cls, nx=12, ny=9)

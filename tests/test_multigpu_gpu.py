@@ -165,10 +165,6 @@ def test_partitioned_connection_graph_equals_single_gpu(nparts, precision):
     assert np.array_equal(np.concatenate(S), ref.state_array())
 
 
-@pytest.mark.skipif(
-    not __import__('os').environ.get('MKB_TEST_EXPERIMENTAL'),
-    reason='slab_lean is off by default until measured on a GPU box;'
-           ' set MKB_TEST_EXPERIMENTAL=1 to run')
 @pytest.mark.parametrize('nslab', [2, 3])
 def test_lean_slab_kernel_equals_single_gpu(nslab):
     # grid sizes that leave threads outside the grid in every block row/column
