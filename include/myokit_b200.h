@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MKB_ABI_VERSION 2
+#define MKB_ABI_VERSION 3
 
 /* Error codes */
 #define MKB_OK               0
@@ -188,8 +188,8 @@ int mkb_jit_compile(const char* source, const char* options,
 int mkb_sim_init(const mkb_sim_config* cfg, mkb_sim** out);
 /* Starts another run from the state the device holds (the reference keeps
  * its state in a Python list between runs, openclsim.py:1104,1149; here it
- * stays in HBM). Row slabs: call on every rank, barrier, mkb_sim_halo_seed,
- * barrier, then step. */
+ * stays in HBM). Row slabs: call on every rank, then either step straight
+ * away (mkb_sim_halo_live says 1) or barrier, mkb_sim_halo_seed, barrier. */
 int mkb_sim_rearm(mkb_sim* sim, const mkb_run_config* run);
 /* Runs up to steps_per_call time steps. Returns 1 while t < tmax, 0 when the
  * run has finished (final state available), < 0 on error. *engine_time gets
@@ -234,6 +234,12 @@ int mkb_sim_halo_connect(mkb_sim* sim, const void* lower, const void* upper, int
 /* After mkb_sim_rearm (and a barrier): delivers the boundary rows of the
  * current state to the neighbours again. mkb_sim_halo_connect includes it. */
 int mkb_sim_halo_seed(mkb_sim* sim);
+/* After mkb_sim_rearm: *live = 1 when the exchange protocol simply continues
+ * (the previous run ended normally on every rank, so each neighbour already
+ * holds this slab's boundary row for the next step): no barrier and no
+ * mkb_sim_halo_seed are needed before stepping. Every rank gets the same
+ * answer, because they all took the same steps. */
+int mkb_sim_halo_live(mkb_sim* sim, int* live);
 
 /* Partitioned connection graphs: a partition (contiguous cell ids, n_ghost > 0)
  * owns an exchange block [ghost V: 3 x n_ghost][flags: one per rank]. Every

@@ -13,7 +13,7 @@ c_u64 = ctypes.c_uint64
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
 
-MKB_ABI_VERSION = 2
+MKB_ABI_VERSION = 3
 MKB_OK = 0
 MKB_ERR_INVALID = -1
 MKB_ERR_CUDA = -2
@@ -33,7 +33,7 @@ SYMBOLS = [
     'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
     'mkb_sim_reset_counters', 'mkb_sim_clean', 'mkb_sim_halo_info',
     'mkb_sim_halo_export', 'mkb_sim_halo_connect', 'mkb_sim_halo_seed',
-    'mkb_sim_rearm', 'mkb_measure_peaks', 'mkb_sim_ghost_connect',
+    'mkb_sim_rearm', 'mkb_sim_halo_live', 'mkb_measure_peaks', 'mkb_sim_ghost_connect',
     'mkb_pacing_probe', 'mkb_schedule_probe',
     'mkb_sim_junction_connect', 'mkb_sim_step_pair',
 ]
@@ -147,6 +147,7 @@ def library():
     lib.mkb_sim_halo_export.argtypes = [c_vp, c_vp, ctypes.POINTER(c_vp)]
     lib.mkb_sim_halo_connect.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int]
     lib.mkb_sim_halo_seed.argtypes = [c_vp]
+    lib.mkb_sim_halo_live.argtypes = [c_vp, ctypes.POINTER(ctypes.c_int)]
     lib.mkb_sim_ghost_connect.argtypes = [
         c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(GhostPeer),
         ctypes.c_int, ctypes.c_uint32, c_vp]

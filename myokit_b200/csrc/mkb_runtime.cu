@@ -418,6 +418,8 @@ struct mkb_sim {
     bool peer_lo_ipc = false, peer_hi_ipc = false;
     bool has_lo = false, has_hi = false;
     u64 step_index = 0;                 // steps taken in this run (1-based in the kernel)
+    bool halo_live = false;             // exchange block consistent with step_index (see arm_run)
+    bool halo_connected = false;        // halo_connect / ghost_connect + first seed done
 
     // partitioned connection graphs: ghost cells (multi-GPU)
     u64 n_ghost = 0;
@@ -926,7 +928,12 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
     s->engine_time = r->tmin;
     s->finished = s->sched.finished();
     s->halted = false;
-    s->step_index = 0;
+    // Sharded simulations whose last run ended normally keep counting: the
+    // ghost rows / ghost cells for step_index + 1 are already in their slots
+    // on every neighbour (the last step kernel delivered them), so a re-armed
+    // run continues the exchange protocol where it stopped — no flag reset,
+    // no barrier, no re-seed.
+    if (!s->halo_live) s->step_index = 0;
     s->issued = 0;
     s->throttle_count = 0;
     s->ring_chunk = 0;
@@ -1852,6 +1859,7 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
         s->grid.n_ghost_import = n_import;
     }
     s->ghosts_connected = true;
+    s->halo_connected = true;
     return mkb_sim_halo_seed(s);
 }
 
@@ -1859,13 +1867,16 @@ extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
     if (!r) return fail(MKB_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(s->device));
+    // (a run that halted on a NaN or was abandoned half way leaves ranks at
+    // different steps: start the exchange protocol afresh then)
+    s->halo_live = s->d_xchg && s->halo_connected && s->finished && !s->halted;
     int rc = arm_run(s, r);
     if (rc) return rc;
     // counters describe one run
     s->launches = 0;
     s->steps = 0;
     s->device_ms = 0;
-    if (s->d_xchg) {
+    if (s->d_xchg && !s->halo_live) {
         // Arrival flags restart from zero; the caller barriers, then reseeds
         const size_t keep = s->n_ghost ? (3 * s->n_ghost * s->rs + 255) / 256 * 256
                                        : 2 * 3 * s->nx * s->rs;
@@ -1875,8 +1886,15 @@ extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
     return MKB_OK;
 }
 
+extern "C" int mkb_sim_halo_live(mkb_sim* s, int* live) {
+    if (!s || !live) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    *live = s->halo_live ? 1 : 0;
+    return MKB_OK;
+}
+
 extern "C" int mkb_sim_halo_seed(mkb_sim* s) {
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (s->halo_live) return MKB_OK;    // nothing to deliver: see arm_run
     if (s->ghosts_connected) {
         if (s->step_index != 0) return fail(MKB_ERR_STATE, "halo_seed must precede the first step");
         CUDA_TRY(cudaSetDevice(s->device));
@@ -1921,6 +1939,7 @@ static int halo_connect_typed(mkb_sim* s) {
         g.peer_hi_halo_lo = b;
         g.peer_hi_flag_lo = (unsigned int*)(b + 2 * halo);
     }
+    s->halo_connected = true;
     return halo_seed_typed<TR>(s);
 }
 

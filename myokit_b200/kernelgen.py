@@ -232,6 +232,13 @@ _PRELUDE = r"""
 #define MKB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
 #endif
 
+// Plane k of a cell, from the cell's address in plane 0. (Forms that were
+// tried to get below two integer instructions per access and did not: a 32-bit
+// stride, which the compiler turns into the same chains of 64-bit additions,
+// and an inline mad.wide.u32, which ptxas splits into a uniform multiply and
+// the same additions.)
+#define MKB_AT(base, k) ((base)[(unsigned long long)(k) * stride])
+
 // x^k for a compile-time integer k: square-and-multiply, fixed order.
 template <int N>
 __device__ __forceinline__ Real mkb_powi(Real x) {
@@ -651,7 +658,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              rows_per_thread=1, div_int_check=False, partitioned=False,
              const_div=True, slab_lean=False, div_parallel=False,
              junction=None, persistent=False, split_gates=False,
-             div_cubic=False, prefetch=None):
+             div_cubic=False, prefetch=None, debug_mem=None):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -721,6 +728,11 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         (``load_ahead``) is prefetched into that cache level at the top of the
         kernel, so the load proper finds it close by: the memory latency is
         covered without holding a register for the value.
+    ``debug_mem``
+        Diagnostic builds that give WRONG results, for measuring where the
+        time of a step goes: ``'l1'`` reads every state but V from one of
+        256 cells (always a cache hit: the kernel without its load latency),
+        ``'l1ns'`` also predicates every state store off.
     ``div_cubic``
         ``mkb_div`` with one third-order refinement of the reciprocal and no
         residual correction: 4 FP64 instructions instead of 6, IEEE results
@@ -892,7 +904,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         k = var.index()
         if k == i_vm:
             return '    const Real %s = vc;' % v(var)
-        src = 'state[%dull * stride + cid]' % k
+        src = 'MKB_AT(state_c, %d)' % k
+        if debug_mem:
+            src = 'MKB_AT(state + (cid & 255ull), %d)' % k
         if guarded:
             src = 'active ? %s : (Real)0' % src
         return '    const Real %s = %s;' % (v(var), src)
@@ -935,7 +949,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 '    }' % rhs)
         if k == i_vm:
             return '    v_out[cid] = %s;' % rhs
-        return '    state[%dull * stride + cid] = %s;' % (k, rhs)
+        if debug_mem == 'l1ns':
+            return '    { const Real vnew = %s; if (dt < (Real)0) MKB_AT(state_c, %d) = vnew; }' % (rhs, k)
+        return '    MKB_AT(state_c, %d) = %s;' % (k, rhs)
 
     # Equations to emit, in the reference's order (openclsim.cl:235-243)
     todo = []       # (component name or None, equation)
@@ -1035,7 +1051,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             body.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
             if var in inter_index and not eq.lhs.is_derivative():
                 body.append(
-                    '    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                    '    if (store_aux) MKB_AT(inter_c, %d) = %s;'
                     % (inter_index[var], v(eq.lhs)))
         body.append('    // Update (openclsim.cl:358-364)')
         for var in states:
@@ -1099,7 +1115,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 have.add(var)
                 if var in inter_index:
                     body.append(
-                        '    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                        '    if (store_aux) MKB_AT(inter_c, %d) = %s;'
                         % (inter_index[var], v(eq.lhs)))
             flush_updates()
         emit_loads(len(todo), body, False)
@@ -1112,7 +1128,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     consts = []
     for k, var in enumerate(fields):
         early.append(
-            '    const Real %s = active ? ((const Real*)g.field)[%dull * stride + cid] : (Real)0;'
+            '    const Real %s = active ? MKB_AT(field_c, %d) : (Real)0;'
             % (v(var), k))
     consts.append('    // Literal constants (openclsim.cl:173-178)')
     for group in equations.values():
@@ -1139,14 +1155,14 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             if diffusion:
                 gate_lines.append('    const Real %s = v_in[cid];' % v(vm))
             else:
-                gate_lines.append('    const Real %s = state[%dull * stride + cid];'
+                gate_lines.append('    const Real %s = MKB_AT(state_c, %d);'
                                   % (v(vm), vm.index()))
         for k, var in enumerate(fields):
             gate_lines.append(
-                '    const Real %s = ((const Real*)g.field)[%dull * stride + cid];'
+                '    const Real %s = MKB_AT(field_c, %d);'
                 % (v(var), k))
         for var in gate_states:
-            gate_lines.append('    const Real %s = state[%dull * stride + cid];'
+            gate_lines.append('    const Real %s = MKB_AT(state_c, %d);'
                               % (v(var), var.index()))
         gate_lines.extend(consts)
         for name, eq in gate_todo:
@@ -1154,10 +1170,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             gate_lines.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
             if var in inter_index and not eq.lhs.is_derivative():
                 gate_lines.append(
-                    '    if (store_aux) ((Real*)g.inter)[%dull * stride + cid] = %s;'
+                    '    if (store_aux) MKB_AT(inter_c, %d) = %s;'
                     % (inter_index[var], v(eq.lhs)))
         for var in gate_states:
-            gate_lines.append('    state[%dull * stride + cid] = %s;'
+            gate_lines.append('    MKB_AT(state_c, %d) = %s;'
                               % (var.index(), state_rhs(var)))
 
     # ------------------------------------------------------------------
@@ -1632,6 +1648,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    const bool active = (ix < nx) && (iy < ny);')
     p('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
     p('    Real* const state = (Real*)g.state;')
+    p('    Real* const state_c = state + cid;')
+    p('    const Real* const field_c = (const Real*)g.field + cid;')
+    p('    Real* const inter_c = (Real*)g.inter + cid;')
+    p('    (void)state_c; (void)field_c; (void)inter_c;')
     p('    // Per-step scalars, cast like openclsim.c:1063,1148,1155')
     p('    const Real time = (Real)sp->time;')
     p('    const Real dt = (Real)sp->dt;')
@@ -1667,7 +1687,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    if (active) {')
         for var in states:
             if var.index() != i_vm and var not in early_states and var not in gate_set_unused:
-                p('        MKB_PREFETCH_%s(state + %dull * stride + cid);'
+                p('        MKB_PREFETCH_%s(&MKB_AT(state_c, %d));'
                   % ('L1' if prefetch == 'l1' else 'L2', var.index()))
         p('    }')
     p('')
@@ -1856,6 +1876,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    if (ix >= nx || iy >= ny) return;')
         p('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
         p('    Real* const state = (Real*)g.state;')
+        p('    Real* const state_c = state + cid;')
+        p('    const Real* const field_c = (const Real*)g.field + cid;')
+        p('    Real* const inter_c = (Real*)g.inter + cid;')
+        p('    (void)state_c; (void)field_c; (void)inter_c; (void)state;')
         p('    const Real time = (Real)sp->time;')
         p('    const Real dt = (Real)sp->dt;')
         p('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')

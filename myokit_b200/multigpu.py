@@ -35,21 +35,44 @@ import numpy as np
 
 
 class TorchComm:
-    """Communicator over an initialised ``torch.distributed`` process group."""
+    """
+    Communicator over an initialised ``torch.distributed`` process group.
 
-    def __init__(self, group=None):
+    Host-side agreement (handles, NaN flags, barriers) goes over a ``gloo``
+    side group when the default group is NCCL: an ``all_gather_object`` over
+    NCCL costs a device synchronisation, two collectives and pickling on
+    every call (~0.5 ms each, measured as 1.6 ms of fixed cost per run at 8
+    GPUs), and nothing here is device data.
+    """
+
+    def __init__(self, group=None, host_group=None):
+        import torch
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError('torch.distributed is not initialised.')
         self._dist = dist
-        self._group = group
+        self._torch = torch
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
+        if host_group is None:
+            if dist.get_backend(group) == 'gloo':
+                host_group = group
+            else:
+                ranks = (None if group is None
+                         else dist.get_process_group_ranks(group))
+                host_group = dist.new_group(ranks=ranks, backend='gloo')
+        self._group = host_group
 
     def allgather(self, obj):
         out = [None] * self.size
         self._dist.all_gather_object(out, obj, group=self._group)
         return out
+
+    def any(self, flag):
+        """True on every rank if ``flag`` is true on any."""
+        t = self._torch.tensor([1 if flag else 0], dtype=self._torch.int32)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX, group=self._group)
+        return bool(t.item())
 
     def barrier(self):
         self._dist.barrier(group=self._group)
@@ -86,6 +109,9 @@ class ThreadComm:
         out = list(sh.slots)
         sh.barrier.wait()
         return out
+
+    def any(self, flag):
+        return any(self.allgather(bool(flag)))
 
     def barrier(self):
         self._shared.barrier.wait()

@@ -18,5 +18,8 @@ elif name == 'lr91_fp32':
     s = workloads.c2_planar(S, 4096)
 else:
     raise SystemExit('unknown workload ' + name)
+if os.environ.get('MKB_PROFILE_OPTS'):
+    # kernel options of the variant to capture, e.g. "dict(div_cubic=True)"
+    s.set_kernel_options(**eval(os.environ['MKB_PROFILE_OPTS']))
 info = s.benchmark_steps(steps, warmup=3)
 print(name, info)

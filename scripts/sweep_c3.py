@@ -55,6 +55,23 @@ SETS = {
         ('cubic+stab split gates', also(B3, split_gates=True)),
         ('cubic+stab nofmad', also(B3, fmad=False)),
     ],
+    # round 2, second pass: where does the time go (diagnostic builds, wrong results)
+    'r2b': [
+        ('default', dict()),
+        ('default, loads hit L1 (diagnostic)', dict(debug_mem='l1')),
+        ('default, L1 loads + no stores (diag.)', dict(debug_mem='l1ns')),
+        ('cubic pf-l1 la16', dict(div_cubic=True, prefetch='l1', load_ahead=16)),
+        ('cubic pf-l1 la32', dict(div_cubic=True, prefetch='l1', load_ahead=32)),
+        ('cubic pf-l1 la24', dict(div_cubic=True, prefetch='l1', load_ahead=24)),
+        ('cubic+stab pf-l1 la16', also(B3, prefetch='l1', load_ahead=16)),
+        ('cubic+stab pf-l1 la16 (diag. l1)', also(B3, prefetch='l1', load_ahead=16, debug_mem='l1')),
+        ('cubic+stab pf-l1 la16 (diag. l1ns)', also(B3, prefetch='l1', load_ahead=16, debug_mem='l1ns')),
+        ('cubic+stab la4 (diag. l1)', also(B3, load_ahead=4, debug_mem='l1')),
+        ('cubic+stab la4 (diag. l1ns)', also(B3, load_ahead=4, debug_mem='l1ns')),
+        ('cubic+stab la4 168 regs 64x3 (diag. l1ns)', also(B3, load_ahead=4, debug_mem='l1ns', block=(64, 3), min_blocks=2, max_registers=168)),
+        ('cubic+stab la4 96 regs 64x2 (diag. l1ns)', also(B3, load_ahead=4, debug_mem='l1ns', block=(64, 2), min_blocks=5)),
+        ('cubic+stab la4 80 regs 64x2 (diag. l1ns)', also(B3, load_ahead=4, debug_mem='l1ns', block=(64, 2), min_blocks=6)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -69,7 +86,7 @@ for name, opts in variants:
     s.set_kernel_options(**dict(dict(
         block=(64, 4), min_blocks=2, max_registers=0, load_ahead=32, prefetch=None,
         div_cubic=False, fast_exp='poly', split_gates=False, div_parallel=False,
-        const_div=True, fmad=True), **opts))
+        const_div=True, fmad=True, debug_mem=None), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:

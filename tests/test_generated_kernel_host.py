@@ -610,8 +610,8 @@ def test_split_gates_two_kernels_equal_one():
     assert 'V_ina_h_alpha' not in big.split('extern "C" __global__')[1]
     assert 'V_ina_h_alpha' in gates
     k = s._model.get('ina.m').index()
-    assert 'state[%dull * stride + cid] =' % k not in big
-    assert 'state[%dull * stride + cid] =' % k in gates
+    assert 'MKB_AT(state_c, %d) =' % k not in big
+    assert 'MKB_AT(state_c, %d) =' % k in gates
     # bit for bit with the rewrites off (a logged intermediary of each kernel)
     got, want, wstate = both(make, dict(EXACT, block=(8, 4), split_gates=True),
                              3.0, 0.5, 12, 9, inter_log=['ina.h.alpha', 'ikr.IKr'])

@@ -233,7 +233,7 @@ def test_generated_source_follows_reference_arithmetic():
     assert 'gx * (vc - vxp)' in code and 'gx * (2 * vc - vxm - vxp)' in code
     # forward Euler update, V goes to the second V plane
     assert 'v_out[cid] = V_V + dt * D_V;' in code
-    assert 'state[1ull * stride + cid] = V_m + dt * D_m;' in code
+    assert 'MKB_AT(state_c, 1) = V_m + dt * D_m;' in code
     # Rush-Larsen update, openclsim.cl:362
     code = variants()['2d_hetero_rl_field'].kernel_source().code
     # (tau = 1 / X: the exponent -dt / tau is written -dt * X)
@@ -262,7 +262,7 @@ def test_logged_intermediaries_are_stored_only_on_logged_steps():
     s = myokit_b200.SimulationCUDA(m, p, ncells=8, precision=DP)
     src = s.kernel_source([s._model.get('ica.ICa')])
     assert src.n_inter == 1
-    assert 'if (store_aux) ((Real*)g.inter)[0ull * stride + cid] = V_ICa;' \
+    assert 'if (store_aux) MKB_AT(inter_c, 0) = V_ICa;' \
         in src.code
 
 
