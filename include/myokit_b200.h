@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MKB_ABI_VERSION 3
+#define MKB_ABI_VERSION 4
 
 /* Error codes */
 #define MKB_OK               0
@@ -149,7 +149,26 @@ typedef struct mkb_sim_config {
     /* Tuning (0 = default) */
     uint64_t steps_per_call;    /* steps before mkb_sim_step returns (openclsim.c:1046-1047) */
     int use_graphs;             /* 1: replay batches of steps as CUDA graphs */
+
+    /* What the image is expected to hold beyond `kernel_name`; a missing
+     * symbol is an error (never a silent single-kernel run). */
+    int state_uniform;          /* 1: state_in holds ONE cell's n_state values, which
+                                   every cell starts from (the reference's default:
+                                   openclsim.py:236 tiles the model's initial state) */
+    const char* second_kernel_name; /* NULL, or the kernel launched after every
+                                       `kernel_name` launch ("mkb_gate_step") */
+    int kernel_flags;           /* MKB_KERNEL_* */
 } mkb_sim_config;
+
+/* kernel_flags */
+#define MKB_KERNEL_PERSISTENT 1 /* kernel_name takes `flags >> 8` steps per launch; the
+                                   grid fits one thread block */
+#define MKB_KERNEL_STREAM     2 /* kernel_name is a persistent-warp streaming kernel:
+                                   launched with sm_count * blocks_per_sm thread blocks
+                                   of block_x * block_y threads and `stream_smem` bytes
+                                   of dynamic shared memory */
+#define MKB_KERNEL_FLAG_SHIFT_BLOCKS 8   /* bits 8..15: thread blocks per SM (stream) */
+#define MKB_KERNEL_FLAG_SHIFT_SMEM   16  /* bits 16..31: dynamic shared memory, in 256-byte units */
 
 /* A run on the state that is already resident on the device (mkb_sim_rearm):
  * the time span, step size, protocol and log selection of mkb_sim_config. */
@@ -169,6 +188,12 @@ typedef struct mkb_run_config {
 int mkb_abi_version(void);
 const char* mkb_last_error(void);
 void mkb_free(void* p);
+
+/* Page-locked host memory for states and logs the caller wants moved at PCIe
+ * speed (mkb_sim_config::state_in, mkb_sim_get_state: any host pointer works,
+ * pinned ones are copied by asynchronous DMA). */
+int mkb_host_alloc(size_t bytes, void** out);
+void mkb_host_free(void* p);
 
 /* ---- devices (replaces mcl.h device selection / info) ---- */
 int mkb_device_count(void);                                 /* < 0 on error */

@@ -7,13 +7,15 @@ raises — there is no Python or CPU fallback.
 import ctypes
 import os
 
+import numpy as np
+
 from . import build as _build
 
 c_u64 = ctypes.c_uint64
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
 
-MKB_ABI_VERSION = 3
+MKB_ABI_VERSION = 4
 MKB_OK = 0
 MKB_ERR_INVALID = -1
 MKB_ERR_CUDA = -2
@@ -27,7 +29,7 @@ LOG_STATE_FIELD, LOG_INTER_FIELD, LOG_IDIFF_FIELD = 5, 6, 7
 
 # Every symbol include/myokit_b200.h declares
 SYMBOLS = [
-    'mkb_abi_version', 'mkb_last_error', 'mkb_free', 'mkb_device_count',
+    'mkb_abi_version', 'mkb_host_alloc', 'mkb_host_free', 'mkb_last_error', 'mkb_free', 'mkb_device_count',
     'mkb_device_info', 'mkb_device_abi_header', 'mkb_jit_compile',
     'mkb_sim_init', 'mkb_sim_step', 'mkb_sim_log_view', 'mkb_sim_get_state',
     'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
@@ -77,7 +79,14 @@ class SimConfig(ctypes.Structure):
         ('n_log', c_u64), ('log_kind', c_vp), ('log_index', c_vp),
         ('iy_offset', c_u64), ('ny_global', c_u64),
         ('steps_per_call', c_u64), ('use_graphs', ctypes.c_int),
+        ('state_uniform', ctypes.c_int),
+        ('second_kernel_name', ctypes.c_char_p),
+        ('kernel_flags', ctypes.c_int),
     ]
+
+
+KERNEL_PERSISTENT = 1
+KERNEL_STREAM = 2
 
 
 class RunConfig(ctypes.Structure):
@@ -96,6 +105,41 @@ class GhostPeer(ctypes.Structure):
         ('peer_n_flags', ctypes.c_uint32), ('flag_index', ctypes.c_uint32),
         ('n_export', c_u64), ('src_cell', c_vp), ('dst_slot', c_vp),
     ]
+
+
+class _PinnedBlock:
+    """Page-locked host memory from mkb_host_alloc, freed with the last view."""
+    def __init__(self, nbytes):
+        lib = library()
+        ptr = c_vp()
+        check(lib.mkb_host_alloc(ctypes.c_size_t(nbytes), ctypes.byref(ptr)))
+        self.ptr, self.nbytes, self._free = ptr.value, nbytes, lib.mkb_host_free
+
+    def __del__(self):
+        try:
+            self._free(c_vp(self.ptr))
+        except Exception:   # pragma: no cover
+            pass
+
+
+def host_array(count, dtype=np.float64, pinned_from=1 << 20):
+    """
+    An uninitialised 1-d host array; page-locked (copied to and from the
+    device by asynchronous DMA at PCIe speed) when it is at least
+    ``pinned_from`` bytes and a CUDA device is there, ordinary memory otherwise.
+    """
+    dtype = np.dtype(dtype)
+    nbytes = int(count) * dtype.itemsize
+    if nbytes >= pinned_from:
+        try:
+            blk = _PinnedBlock(nbytes)
+        except BackendError:
+            blk = None
+        if blk is not None:
+            buf = (ctypes.c_char * nbytes).from_address(blk.ptr)
+            buf._mkb_block = blk        # the array keeps buf, buf keeps blk
+            return np.frombuffer(buf, dtype=dtype, count=int(count))
+    return np.empty(int(count), dtype=dtype)
 
 
 class BackendError(Exception):
@@ -121,6 +165,9 @@ def library():
     lib.mkb_last_error.restype = ctypes.c_char_p
     lib.mkb_free.argtypes = [c_vp]
     lib.mkb_free.restype = None
+    lib.mkb_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(c_vp)]
+    lib.mkb_host_free.argtypes = [c_vp]
+    lib.mkb_host_free.restype = None
     lib.mkb_device_count.restype = ctypes.c_int
     lib.mkb_device_info.argtypes = [ctypes.c_int, ctypes.POINTER(DeviceInfo)]
     lib.mkb_device_abi_header.restype = ctypes.c_char_p

@@ -114,6 +114,8 @@ class _PowMixin:
             if x2 is not None and x2 == int(x2) and 0 < x2 <= 15:
                 k = (int(x2) - 1) // 2
                 sq = 'sqrtf' if self._sp else 'sqrt'
+                if getattr(self, '_fast_libm', False) and not self._sp:
+                    sq = 'mkb_sqrt'
                 if k == 0:
                     return '%s(%s)' % (sq, self.ex(e[0]))
                 return 'mkb_powh<%d>(%s)' % (k, self.ex(e[0]))
@@ -198,7 +200,75 @@ class _ExpMixin:
         return super()._ex_exp(e)
 
 
-class _Writer(_ConstPoolMixin, _PowMixin, _DivMixin, _ExpMixin,
+class _LibmMixin:
+    """
+    Optional branch-free double-precision ``sqrt`` / ``log`` / ``cos`` /
+    ``acos`` / general ``pow`` (``mkb_sqrt`` ..., see the prelude), and
+    conditional expressions as selects: both arms are evaluated and one is
+    chosen (``mkb_sel``), where the ternary operator the host framework's
+    writer emits becomes a branch whenever an arm holds a division or an exp.
+    Either keeps the kernel body one straight line for the instruction
+    scheduler.
+    """
+    _fast_libm = False
+    _select = False
+
+    def _libm(self, e, name, fallback):
+        if self._fast_libm and not self._sp:
+            return self._ex_function(e, name)
+        return fallback(e)
+
+    def _ex_sqrt(self, e):
+        return self._libm(e, 'mkb_sqrt', super()._ex_sqrt)
+
+    def _ex_log(self, e):
+        if len(e) != 1:
+            return super()._ex_log(e)
+        return self._libm(e, 'mkb_log', super()._ex_log)
+
+    def _ex_cos(self, e):
+        return self._libm(e, 'mkb_cos', super()._ex_cos)
+
+    def _ex_acos(self, e):
+        return self._libm(e, 'mkb_acos', super()._ex_acos)
+
+    def _ex_power(self, e):
+        text = super()._ex_power(e)
+        if self._fast_libm and not self._sp and text.startswith('pow('):
+            return 'mkb_pow(' + self.ex(e[0]) + ', ' + self.ex(e[1]) + ')'
+        return text
+
+    _COSTLY = (myokit.Exp, myokit.Log, myokit.Log10, myokit.Power, myokit.Sin,
+               myokit.Cos, myokit.Tan, myokit.ASin, myokit.ACos, myokit.ATan)
+
+    def _selectable(self, arms):
+        """Whether evaluating all ``arms`` is cheap enough to drop the branch."""
+        if self._select == 'cheap':
+            for arm in arms:
+                if isinstance(arm, self._COSTLY):
+                    return False
+                for x in arm.walk(self._COSTLY):
+                    return False
+        return bool(self._select)
+
+    def _ex_if(self, e):
+        if not self._selectable([e._t, e._e]):
+            return super()._ex_if(e)
+        return 'mkb_sel(%s, %s, %s)' % (
+            self.ex(e._i), self.ex(e._t), self.ex(e._e))
+
+    def _ex_piecewise(self, e):
+        if not self._selectable(list(e._e)):
+            return super()._ex_piecewise(e)
+        ifs = [self.ex(x) for x in e._i]
+        thens = [self.ex(x) for x in e._e]
+        text = thens[-1]
+        for c, t in zip(reversed(ifs), reversed(thens[:-1])):
+            text = 'mkb_sel(%s, %s, %s)' % (c, t, text)
+        return text
+
+
+class _Writer(_ConstPoolMixin, _LibmMixin, _PowMixin, _DivMixin, _ExpMixin,
               CudaExpressionWriter):
     """
     The writer used for all but ``native_maths`` kernels. ``fold`` (set by
@@ -226,6 +296,7 @@ _PRELUDE = r"""
 // source (tests/cuda_shim, test infrastructure) can supply its own.
 #ifndef MKB_ASM_RCP64
 #define MKB_ASM_RCP64(r, b) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b))
+#define MKB_ASM_RSQRT64(r, b) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b))
 #define MKB_ASM_SREG(v, name) asm volatile("mov.u32 %0, %%" name ";" : "=r"(v))
 #define MKB_ASM_EX2F(y, t) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t))
 #define MKB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
@@ -238,6 +309,10 @@ _PRELUDE = r"""
 // and an inline mad.wide.u32, which ptxas splits into a uniform multiply and
 // the same additions.)
 #define MKB_AT(base, k) ((base)[(unsigned long long)(k) * stride])
+
+// Conditional expression with both arms evaluated (function arguments are),
+// then one select: no branch.
+__device__ __forceinline__ Real mkb_sel(bool c, Real a, Real b) { return c ? a : b; }
 
 // x^k for a compile-time integer k: square-and-multiply, fixed order.
 template <int N>
@@ -293,12 +368,6 @@ __device__ __forceinline__ void mkb_wait_flag(
             break;
         }
     }
-}
-
-// x^(K + 1/2) = x^K * sqrt(x)
-template <int K>
-__device__ __forceinline__ Real mkb_powh(Real x) {
-    return mkb_powi<K>(x) * sqrt(x);
 }
 
 // Branch-free division (option fast_div): hardware reciprocal seed (~2^-23),
@@ -365,17 +434,39 @@ __device__ __forceinline__ float mkb_div(float a, float b) {
 
 // exp(x) in double precision (option fast_exp): Cody-Waite reduction with a
 // fused multiply-add, degree-11 polynomial (scripts/gen_exp_coeffs.py, max
-// error 0.85 ulp against mpmath for |x| < 708), exponent inserted with one
-// integer add, no branches. The coefficients live in constant memory so they
-// arrive as c-bank operands / paired uniform loads instead of two 32-bit
-// moves each. Outside the normal range the result saturates instead of
-// following IEEE, and is never NaN or inf for a finite argument: x < -708
-// gives a value below 4.5e-308 (not a denormal or 0), x > 709.4 a value above
-// 6e307 (not +inf; between 709.4 and 709.78 it is half the true value).
-// NaN gives NaN; |x| >= 2^31 and infinities are not supported.
+// error 0.85 ulp against mpmath for |x| < 708), no branches. The power of two
+// is built on the integer pipe from n clamped to [-1023, 1024] and applied
+// with one multiplication, so the ends of the range follow IEEE: the scale is
+// exactly 0 for n <= -1023 (exp underflows to 0; results below 2^-1022 are
+// flushed instead of going through the denormals) and +inf for n >= 1024 (exp
+// overflows to +inf, from x > 709.44 on: up to 0.05 % below the true
+// threshold 709.78). NaN gives NaN. Valid for |x| < 2^31 ln 2 = 1.4e9; beyond
+// that, and for infinite x, n wraps and the result is unspecified (mkb_pow
+// clamps its exponent argument for that reason). The coefficients live in
+// constant memory so they arrive as c-bank operands / paired uniform loads
+// instead of two 32-bit moves each.
 __constant__ double mkb_exp_c[14] = {
 @EXP_TABLE@
 };
+__device__ __forceinline__ double mkb_exp_scale(int n) {
+    const int nc = min(max(n, -1023), 1024);
+    return __hiloint2double((nc + 1023) << 20, 0);
+}
+// p 2^n for p in [1/2, 2): by multiplication (above), or — option
+// exp_scale='add' — by adding n to the exponent field, one integer
+// instruction instead of one on the FP64 pipe; the result then saturates
+// (x > 709.4: above 6e307 but finite; x < -708: below 4.5e-308 but not 0).
+#ifndef MKB_EXP_SCALE_ADD
+#define MKB_EXP_SCALE_ADD 0
+#endif
+__device__ __forceinline__ double mkb_exp_apply(double p, int n) {
+#if MKB_EXP_SCALE_ADD
+    const int nc = min(max(n, -1021), 1023);
+    return __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
+#else
+    return p * mkb_exp_scale(n);
+#endif
+}
 __device__ __forceinline__ double mkb_exp_poly(double x) {
     double t = fma(x, mkb_exp_c[0], mkb_exp_c[1]);
     const int n = __double2loint(t);
@@ -387,9 +478,7 @@ __device__ __forceinline__ double mkb_exp_poly(double x) {
     for (int k = 5; k < 14; k++) p = fma(p, r, mkb_exp_c[k]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const int nc = min(max(n, -1021), 1023);
-    const double y = __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
-    return y;
+    return mkb_exp_apply(p, n);
 }
 
 // Single precision (option fast_exp = 'ex2'): expf(x) = 2^t with t = x log2(e)
@@ -434,8 +523,7 @@ __device__ __forceinline__ double mkb_exp_estrin(double x) {
     const double q = fma(a5, r8, d);
     double p = fma(r2, q, r);
     p += 1.0;
-    const int nc = min(max(n, -1021), 1023);
-    return __hiloint2double(__double2hiint(p) + (nc << 20), __double2loint(p));
+    return mkb_exp_apply(p, n);
 }
 
 // Table variant (option fast_exp = 'table'): exp(x) = 2^m T[j] e^r
@@ -495,8 +583,173 @@ __device__ __forceinline__ double mkb_exp_tab(double x) {
     const double ts = __hiloint2double(__double2hiint(tj) + ((nc >> 6) << 20), __double2loint(tj));
     return fma(ts, p, ts);
 }
+
+// ---------------------------------------------------------------------------
+// Branch-free double-precision sqrt / log / cos / acos / pow (option
+// fast_libm). libdevice's versions are accurate but each contains branches
+// (special operands, slow paths), and a branch ends the region in which ptxas
+// can interleave independent dependency chains: a large model kernel built on
+// them is a string of short blocks, each waiting on its own chain of FP64
+// latencies. These have no branches, handle special operands with selects,
+// and use fewer integer instructions. Polynomials: scripts/gen_libm_coeffs.py.
+// Accuracy (tests/test_prelude_math_host.py, _gpu.py): sqrt <= 0.5 ulp + 2^-20,
+// log, cos <= 1 ulp, acos <= 1.5 ulp, pow <= 1 + |y ln x| ulp.
+// ---------------------------------------------------------------------------
+
+// sqrt: reciprocal-square-root seed (>= 20 bits), one coupled Newton step on
+// (g, h) ~ (sqrt x, 1 / (2 sqrt x)), one residual correction. x = 0, +inf and
+// denormals (seed inf / 0 / inf) return x itself; x < 0 gives NaN.
+__device__ __forceinline__ double mkb_sqrt(double x) {
+    double y;
+    MKB_ASM_RSQRT64(y, x);
+    double g = x * y;
+    double h = 0.5 * y;
+    const double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    g = fma(d, h, g);
+    const unsigned int u = (unsigned int)__double2hiint(y) << 1;
+    return (u == 0xffe00000u || u == 0u) ? x : g;
+}
+
+__constant__ double mkb_libm_c[] = {
+    // [0..6] log: R(z) / z = 2 (A0 + A1 z + ...), log(1 + f) = f - f^2 / 2 + s (f^2 / 2 + R)
+    0x1.5555555555558p-1, 0x1.99999999952d7p-2, 0x1.2492492df281ap-2, 0x1.c71c62e3f11e6p-3,
+    0x1.7462b51cb66b1p-3, 0x1.39fe51a7c18f9p-3, 0x1.2b5900de53b32p-3,
+    // [7] ln2 head (32 bits), [8] ln2 tail
+    0x1.62e42fee00000p-1, 0x1.a39ef35793c76p-33,
+    // [9] spare
+    0.0,
+    // [10..15] cos kernel (even quadrants): cos r = 1 - z / 2 + z^2 C(z)
+    0x1.5555555555555p-5, -0x1.6c16c16c16963p-10, 0x1.a01a019f4ddfdp-16,
+    -0x1.27e4fa16cc2d1p-22, 0x1.1eeb67d026ec6p-29, -0x1.907cd8ff5ede7p-37,
+    // [16..21] sin kernel (odd quadrants): sin r = r + r z S(z)
+    -0x1.5555555555555p-3, 0x1.1111111110babp-7, -0x1.a01a019e820aep-13,
+    0x1.71de37946ed6dp-19, -0x1.ae6008d114485p-26, 0x1.5e0a4fc16be59p-33,
+    // [22] 2 / pi, [23..25] pi / 2 as a sum of three doubles
+    0x1.45f306dc9c883p-1, 0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54, -0x1.f1976b7ed8fbcp-110,
+    // [26..38] asin kernel: asin s = s + s z R(z), z = s^2 <= 1 / 4
+    0x1.5555555555556p-3, 0x1.3333333332ec4p-4, 0x1.6db6db6e3292ep-5, 0x1.f1c71c1d4aa0dp-6,
+    0x1.6e8bb1d89492bp-6, 0x1.1c4d343fa57f6p-6, 0x1.c9cf3759fd8ffp-7, 0x1.78246f32d075cp-7,
+    0x1.524ea8b3aad31p-7, 0x1.653a8f8cfd43cp-8, 0x1.1d661531b222ep-6, -0x1.e7a24f548c99fp-7,
+    0x1.d78189767524ep-6,
+    // [39] spare
+    0.0,
+    // acos = (c0_hi + (c1 p + c0_lo)), index = 2 [|x| > 1/2] + [x < 0]:
+    // [40..43] c1, [44..47] c0_hi, [48..51] c0_lo
+    -1.0, 1.0, 2.0, -2.0,
+    0x1.921fb54442d18p+0, 0x1.921fb54442d18p+0, 0.0, 0x1.921fb54442d18p+1,
+    0x1.1a62633145c07p-54, 0x1.1a62633145c07p-54, 0.0, 0x1.1a62633145c07p-53,
+};
+
+// log: x = m 2^e with m in [sqrt(1/2), sqrt(2)), s = f / (2 + f), f = m - 1;
+// the scheme of fdlibm's e_log.c with this file's division and coefficients.
+// x < 0 and NaN give NaN, +inf gives +inf, 0 and denormals give -inf.
+__device__ __forceinline__ double mkb_log(double x) {
+    const int hx = __double2hiint(x);
+    const int ha = hx + (0x3ff00000 - 0x3fe6a09e);
+    const int e = (ha >> 20) - 1023;
+    const double m = __hiloint2double((ha & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+    const double f = m - 1.0;
+    const double s = mkb_div(f, 2.0 + f);
+    const double z = s * s;
+    double p = mkb_libm_c[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) p = fma(p, z, mkb_libm_c[k]);
+    const double hfsq = (0.5 * f) * f;
+    // (e as a double without a conversion instruction: 2^52 + 2^31 + e)
+    const double dk = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+    double t = fma(z, p, hfsq);                 // hfsq + R
+    t = fma(s, t, dk * mkb_libm_c[8]);
+    t = f - (hfsq - t);
+    double res = fma(dk, mkb_libm_c[7], t);
+    const unsigned int ux = (unsigned int)hx;
+    // not a positive normal number
+    const double odd = fma(x, __hiloint2double(0x7ff00000, 0), __hiloint2double(0x7ff00000, 0));
+    if (ux - 0x00100000u >= 0x7fe00000u) res = odd;         // +inf -> +inf, negative / NaN -> NaN
+    if ((ux << 1) < 0x00200000u) res = __hiloint2double(0xfff00000, 0);     // +-0, denormals -> -inf
+    return res;
+}
+
+// cos: n = rint(x 2 / pi), r = x - n pi / 2 with pi / 2 in three parts
+// (three fused multiply-adds), then the sin or cos kernel on |r| <= pi / 4
+// chosen by the parity of n with an indexed constant load, sign from n mod 4.
+// Valid for |x| < 2^31 (libdevice switches to Payne-Hanek above 1e5: the
+// three-part reduction stays below 1 ulp far beyond that); inf / NaN -> NaN.
+__device__ __forceinline__ double mkb_cos(double x) {
+    double t = fma(x, mkb_libm_c[22], 6755399441055744.0);
+    const int j = __double2loint(t);
+    t -= 6755399441055744.0;
+    double r = fma(-t, mkb_libm_c[23], x);
+    r = fma(-t, mkb_libm_c[24], r);
+    r = fma(-t, mkb_libm_c[25], r);
+    const double z = r * r;
+    const bool odd = (j & 1) != 0;
+    const double* c = mkb_libm_c + (odd ? 16 : 10);
+    double p = c[5];
+#pragma unroll
+    for (int k = 4; k >= 0; k--) p = fma(p, z, c[k]);
+    const double a = odd ? r : z;
+    const double b = odd ? r : fma(z, -0.5, 1.0);
+    const double res = fma(a * z, p, b);
+    // cos x = cos r, -sin r, -cos r, sin r for n mod 4 = 0, 1, 2, 3
+    return __hiloint2double(__double2hiint(res) ^ (((j + 1) & 2) << 30), __double2loint(res));
+}
+
+// acos: for |x| <= 1/2, pi / 2 - asin x; beyond, 2 asin(sqrt((1 - |x|) / 2))
+// (from pi for negative x), with one polynomial for asin on [0, 1/2]. Both
+// reductions are computed and selected; |x| > 1 gives NaN through the sqrt.
+__device__ __forceinline__ double mkb_acos(double x) {
+    const int hx = __double2hiint(x);
+    const double a = fabs(x);
+    const bool big = (unsigned int)(hx & 0x7fffffff) >= 0x3fe00000u;    // |x| >= 1/2
+    const double zb = fma(a, -0.5, 0.5);
+    const double sb = mkb_sqrt(zb);
+    const double z = big ? zb : a * a;
+    const double s = big ? sb : a;
+    double p = mkb_libm_c[38];
+#pragma unroll
+    for (int k = 37; k >= 26; k--) p = fma(p, z, mkb_libm_c[k]);
+    p = fma(s * z, p, s);                       // asin(s)
+    const int idx = (big ? 2 : 0) + (hx < 0 ? 1 : 0);
+    return mkb_libm_c[44 + idx] + fma(mkb_libm_c[40 + idx], p, mkb_libm_c[48 + idx]);
+}
+
+// pow for exponents that are not small integer literals: exp(y log x), the
+// product clamped to +-1024 so that 0^y and overflow come out as 0 / inf.
+// Error <= 1 + |y ln x| ulp (OpenCL allows its pow 16 ulp). A negative base
+// gives NaN also for integer-valued y (integer literals never get here: they
+// are multiplication chains), and 0^0 is NaN.
+#ifndef MKB_EXP_FN
+#define MKB_EXP_FN mkb_exp_poly
+#endif
+#ifndef MKB_FAST_LIBM
+#define MKB_FAST_LIBM 0
+#endif
+__device__ __forceinline__ double mkb_pow(double x, double y) {
+    double a = y * mkb_log(x);
+    const int ha = __double2hiint(a);
+    if ((unsigned int)((ha & 0x7fffffff) - 0x40900000) <= 0x3f600000u)  // 1024 <= |a| <= inf
+        a = __hiloint2double((ha & 0x80000000) | 0x40900000, 0);
+    return MKB_EXP_FN(a);
+}
+
+// x^(K + 1/2) = x^K * sqrt(x)
+__device__ __forceinline__ float mkb_sqrt(float x) { return sqrtf(x); }
+template <int K>
+__device__ __forceinline__ Real mkb_powh(Real x) {
+#if MKB_FAST_LIBM
+    return mkb_powi<K>(x) * mkb_sqrt(x);
+#else
+    return mkb_powi<K>(x) * sqrt(x);
+#endif
+}
 """
 
+
+# Unary double-precision routines of the prelude (tests/prelude_math.py)
+PRELUDE_UNARY = ['mkb_sqrt', 'mkb_log', 'mkb_cos', 'mkb_acos']
 
 _VECTOR_PRELUDE = r"""
 // N consecutive Reals as one 8/16-byte access (two for 32 bytes). The address
@@ -619,7 +872,8 @@ def default_options(precision, n_state):
                     cells_per_thread=4 if n_state <= 4 else 1,
                     rows_per_thread=4 if n_state <= 4 else 1)
     return dict(min_blocks=2 if n_state > 16 else None, fast_div=True,
-                fast_exp='poly', load_ahead=32,
+                fast_exp='poly', load_ahead=32, div_cubic=True,
+                fast_libm=True, select=True,
                 cells_per_thread=2 if n_state <= 4 else 1,
                 rows_per_thread=4 if n_state <= 4 else 1)
 
@@ -639,6 +893,7 @@ class KernelSource:
         self.kernel_name = KERNEL_NAME
         self.persistent = False
         self.gate_kernel = False        # a second kernel, mkb_gate_step
+        self.kernel_flags = 0           # MKB_KERNEL_* of include/myokit_b200.h
         self.gate_states = []
         self.cells_per_thread = 1
         self.rows_per_thread = 1
@@ -658,7 +913,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              rows_per_thread=1, div_int_check=False, partitioned=False,
              const_div=True, slab_lean=False, div_parallel=False,
              junction=None, persistent=False, split_gates=False,
-             div_cubic=False, prefetch=None, debug_mem=None):
+             div_cubic=False, prefetch=None, debug_mem=None,
+             fast_libm=False, select=False, exp_scale='mul'):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -770,7 +1026,14 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             raise ValueError("fast_exp='ex2' is a single-precision variant.")
         if const_pool and not sp:
             w.enable_pool()
+        w._fast_libm = bool(fast_libm) and not sp
+        w._select = select if select == 'cheap' else bool(select)
     w._pow_multiply = bool(pow_multiply)
+    math_defines = '#define MKB_EXP_SCALE_ADD %d\n#define MKB_FAST_LIBM %d\n#define MKB_EXP_FN %s' % (
+        1 if exp_scale == 'add' else 0,
+        1 if (fast_libm and not sp and not native_maths) else 0,
+        getattr(w, '_fast_exp', None) if (getattr(w, '_fast_exp', None)
+                                          and not sp) else 'exp')
     # the shared-memory exp table must be filled by every thread block
     stab = (fast_exp == 'stab') and not sp and not native_maths
     pooled = getattr(w, '_pool', None) is not None
@@ -1191,6 +1454,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
         q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
         q('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
+        q(math_defines)
         q(_PRELUDE)
         if pooled and w._pool:
             q('__constant__ double mkb_k[%d] = {' % len(w._pool))
@@ -1333,6 +1597,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         ks = KernelSource('\n'.join(o), block, n_state, i_vm, len(inter_log),
                           len(fields), diffusion_mode, options)
         ks.kernel_name = KERNEL_NAME + '_persistent'
+        ks.kernel_flags = 1             # MKB_KERNEL_PERSISTENT
         ks.persistent = True
         return ks
 
@@ -1354,6 +1619,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
         q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
         q('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
+        q(math_defines)
         q(_PRELUDE)
         q(_VECTOR_PRELUDE)
         if pooled and w._pool:
@@ -1589,6 +1855,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
     p('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
     p('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
+    p(math_defines)
     p(_PRELUDE)
     if pooled and w._pool:
         p('// Model constants (double precision), in order of first use')

@@ -10,7 +10,9 @@ from myokit_b200 import workloads, capi
 
 grid = int(os.environ.get('SWEEP_GRID', '2048'))
 steps = int(os.environ.get('SWEEP_STEPS', '20'))
-B3 = dict(div_cubic=True, fast_exp='stab')
+B3 = dict(div_cubic=True, fast_exp='stab', fast_libm=False, select=False)
+OLD = dict(div_cubic=False, fast_libm=False, select=False)
+LM = dict(select=False)
 
 
 def also(base, **kw):
@@ -21,7 +23,7 @@ def also(base, **kw):
 
 SETS = {
     'r1': [
-        ('default', dict()),
+        ('default', dict(OLD)),
         ('div_parallel', dict(div_parallel=True)),
         ('exp estrin', dict(fast_exp='estrin')),
         ('exp table', dict(fast_exp='table')),
@@ -72,6 +74,52 @@ SETS = {
         ('cubic+stab la4 96 regs 64x2 (diag. l1ns)', also(B3, load_ahead=4, debug_mem='l1ns', block=(64, 2), min_blocks=5)),
         ('cubic+stab la4 80 regs 64x2 (diag. l1ns)', also(B3, load_ahead=4, debug_mem='l1ns', block=(64, 2), min_blocks=6)),
     ],
+    # round 2, third pass: branch-free body (selects, in-line sqrt/log/cos/acos/pow)
+    'r2c': [
+        ('old default (libdevice libm, ternaries)', dict(OLD)),
+        ('old + cubic', also(OLD, div_cubic=True)),
+        ('select only', also(OLD, div_cubic=True, select=True)),
+        ('libm only', also(OLD, div_cubic=True, fast_libm=True)),
+        ('NEW default (cubic, libm, select)', dict()),
+        ('new la16', dict(load_ahead=16)),
+        ('new la8', dict(load_ahead=8)),
+        ('new la4', dict(load_ahead=4)),
+        ('new la64', dict(load_ahead=64)),
+        ('new 64x3 mb2 (168 regs)', dict(block=(64, 3), min_blocks=2, max_registers=168)),
+        ('new 64x2 mb3 (168 regs)', dict(block=(64, 2), min_blocks=3, max_registers=168)),
+        ('new 64x2 mb2 (255 regs)', dict(block=(64, 2), min_blocks=2, max_registers=255)),
+        ('new 64x4 mb1 (255 regs)', dict(block=(64, 4), min_blocks=1, max_registers=255)),
+        ('new 64x2 mb5 (96 regs)', dict(block=(64, 2), min_blocks=5)),
+        ('new 128x1 mb4', dict(block=(128, 1), min_blocks=4)),
+        ('new 32x4 mb4', dict(block=(32, 4), min_blocks=4)),
+        ('new pf-l1 la16', dict(prefetch='l1', load_ahead=16)),
+        ('new estrin', dict(fast_exp='estrin')),
+        ('new stab', dict(fast_exp='stab')),
+        ('new nofmad', dict(fmad=False)),
+        ('new (diag. l1)', dict(debug_mem='l1')),
+    ],
+    'r2d': [
+        ('libm', dict(LM)),
+        ('libm exp-add', also(LM, exp_scale='add')),
+        ('libm la16', also(LM, load_ahead=16)),
+        ('libm la48', also(LM, load_ahead=48)),
+        ('libm pf-l1 la16', also(LM, prefetch='l1', load_ahead=16)),
+        ('libm 64x2 mb3 (168 regs)', also(LM, block=(64, 2), min_blocks=3, max_registers=168)),
+        ('libm 64x3 mb2 (168 regs)', also(LM, block=(64, 3), min_blocks=2, max_registers=168)),
+        ('libm 32x3 mb5 (136 regs)', also(LM, block=(32, 3), min_blocks=5, max_registers=136)),
+        ('libm 64x1 mb7 (144 regs)', also(LM, block=(64, 1), min_blocks=7, max_registers=144)),
+        ('libm cheap-select', also(LM, select='cheap')),
+        ('libm cheap-select exp-add', also(LM, select='cheap', exp_scale='add')),
+        ('libm cheap-select 64x2 mb3 (168 regs)', also(LM, select='cheap', block=(64, 2), min_blocks=3, max_registers=168)),
+        ('libm cheap-select la16', also(LM, select='cheap', load_ahead=16)),
+        ('libm select 64x2 mb3 (168) la16', dict(block=(64, 2), min_blocks=3, max_registers=168, load_ahead=16)),
+        ('libm select 64x2 mb3 (168) la8', dict(block=(64, 2), min_blocks=3, max_registers=168, load_ahead=8)),
+        ('libm select 64x2 mb3 (168) exp-add', dict(block=(64, 2), min_blocks=3, max_registers=168, exp_scale='add')),
+        ('libm select 32x4 mb3 (168)', dict(block=(32, 4), min_blocks=3, max_registers=168)),
+        ('libm select 128x1 mb3 (168)', dict(block=(128, 1), min_blocks=3, max_registers=168)),
+        ('libm (diag. l1)', also(LM, debug_mem='l1')),
+        ('libm cheap-select (diag. l1)', also(LM, select='cheap', debug_mem='l1')),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -85,8 +133,9 @@ for name, opts in variants:
     # one simulation, re-optioned: the state stays in HBM across variants
     s.set_kernel_options(**dict(dict(
         block=(64, 4), min_blocks=2, max_registers=0, load_ahead=32, prefetch=None,
-        div_cubic=False, fast_exp='poly', split_gates=False, div_parallel=False,
-        const_div=True, fmad=True, debug_mem=None), **opts))
+        div_cubic=True, fast_libm=True, select=True,
+        fast_exp='poly', split_gates=False, div_parallel=False,
+        const_div=True, fmad=True, debug_mem=None, exp_scale='mul'), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:

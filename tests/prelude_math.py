@@ -38,7 +38,9 @@ def host_library(div='newton'):
             kernelgen._PRELUDE, 'extern "C" {',
             'void f_init() { MKB_EXP_TABLE_INIT(0u, 1u); }',
             'void f_div(const double* a, const double* b, double* out, long n) {'
-            ' for (long i = 0; i < n; i++) out[i] = mkb_div(a[i], b[i]); }']
+            ' for (long i = 0; i < n; i++) out[i] = mkb_div(a[i], b[i]); }',
+            'void f_pow(const double* a, const double* b, double* out, long n) {'
+            ' for (long i = 0; i < n; i++) out[i] = mkb_pow(a[i], b[i]); }']
     for name in UNARY:
         code.append('void f_%s(const double* x, double* out, long n) {'
                     ' for (long i = 0; i < n; i++) out[i] = %s(x[i]); }' % (name, name))
@@ -81,6 +83,14 @@ def device_source(div='newton'):
             'extern "C" __global__ void f_div(const double* a, const double* b, double* out, long n) {',
             '    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;',
             '    if (i < n) out[i] = mkb_div(a[i], b[i]);',
+            '}',
+            'extern "C" __global__ void f_pow(const double* a, const double* b, double* out, long n) {',
+            '    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;',
+            '    if (i < n) out[i] = mkb_pow(a[i], b[i]);',
+            '}',
+            'extern "C" __global__ void f_rsqrt_seed(const double* b, double* out, long n) {',
+            '    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;',
+            '    if (i < n) { double r; MKB_ASM_RSQRT64(r, b[i]); out[i] = r; }',
             '}',
             # the raw seed, to pin the host model of rcp.approx.ftz.f64
             'extern "C" __global__ void f_rcp_seed(const double* b, double* out, long n) {',

@@ -26,7 +26,7 @@ import cuda_shim
 DP = myokit.DOUBLE_PRECISION
 SP = myokit.SINGLE_PRECISION
 EXACT = dict(fast_div=False, fast_exp=False, pow_multiply=False, fmad=False,
-             const_div=False)
+             const_div=False, fast_libm=False)
 
 
 def oracle_fields(o, duration, li, nx, ny, names):

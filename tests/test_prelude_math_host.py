@@ -88,13 +88,87 @@ def test_exp_table_forms_saturate(name):
 
 
 @pytest.mark.parametrize('name', ['mkb_exp_poly', 'mkb_exp_estrin'])
-def test_exp_polynomial_forms_never_produce_nan(name):
-    # saturating forms: huge / tiny finite values outside the double range
+def test_exp_polynomial_forms_overflow_and_underflow_like_ieee(name):
+    # the power of two is applied with a multiplication: +inf / 0 outside the
+    # double range (the advisor's case: 1 / (1 + exp(big)) must be 0)
     lib = host_library()
-    x = np.array([800.0, 710.0, 2000.0, -800.0, -2000.0])
+    x = np.array([800.0, 710.0, 2000.0, 1e9, -800.0, -2000.0, -1e9, 709.0, -708.0, 0.0])
     y = call_host(lib, name, x)
-    assert np.all(np.isfinite(y)) and np.all(y > 0), y
-    assert np.all(y[:3] > 6e307) and np.all(y[3:] < 1e-300)
+    assert np.all(np.isposinf(y[:4])), y
+    assert np.all(y[4:7] == 0.0), y
+    assert abs(y[7] / np.exp(709.0) - 1) < 1e-15 and abs(y[8] / np.exp(-708.0) - 1) < 1e-15
+    assert y[9] == 1.0
+    assert np.isnan(call_host(lib, name, np.array([np.nan])))[0]
     lib_c = host_library('cubic')
-    q = call_host(lib_c, 'div', np.ones(5), 1.0 + y)
-    assert np.all(q[:3] < 2e-308) and np.all(q[3:] == 1.0)
+    q = call_host(lib_c, 'div', np.ones(7), 1.0 + y[:7])
+    assert np.all(q[:4] == 0.0) and np.all(q[4:] == 1.0)
+
+
+def _mp_ulp_error(lib, name, x, f):
+    import mpmath as mp
+    mp.mp.dps = 40
+    y = call_host(lib, name, x)
+    worst = 0.0
+    for xi, yi in zip(x, y):
+        want = f(mp.mpf(float(xi)))
+        ulp = mp.mpf(float(np.spacing(abs(float(want)))))
+        worst = max(worst, float(abs(mp.mpf(float(yi)) - want) / ulp))
+    return worst
+
+
+def test_branch_free_libm_accuracy():
+    import mpmath as mp
+    lib = host_library('cubic')
+    rng = np.random.default_rng(8)
+    n = 4000
+    wide = np.exp(rng.uniform(-700, 700, n))
+    assert _mp_ulp_error(lib, 'mkb_sqrt', wide, mp.sqrt) <= 0.501
+    assert _mp_ulp_error(lib, 'mkb_log', wide, mp.log) <= 1.0
+    assert _mp_ulp_error(lib, 'mkb_log', rng.uniform(0.4, 2.5, n), mp.log) <= 1.0
+    assert _mp_ulp_error(lib, 'mkb_log', 1 + rng.uniform(-1e-3, 1e-3, n), mp.log) <= 1.0
+    assert _mp_ulp_error(lib, 'mkb_cos', rng.uniform(-10, 10, n), mp.cos) <= 1.6
+    assert _mp_ulp_error(lib, 'mkb_cos', rng.uniform(-1e5, 1e5, n), mp.cos) <= 1.6
+    assert _mp_ulp_error(lib, 'mkb_cos', rng.uniform(-1e9, 1e9, n), mp.cos) <= 1.6
+    assert _mp_ulp_error(lib, 'mkb_acos', rng.uniform(-1, 1, n), mp.acos) <= 1.5
+    near = np.concatenate([1 - np.exp(rng.uniform(-30, 0, n)), np.exp(rng.uniform(-30, 0, n)) - 1])
+    assert _mp_ulp_error(lib, 'mkb_acos', near, mp.acos) <= 1.5
+
+
+def test_branch_free_libm_special_operands():
+    lib = host_library('cubic')
+    inf, nan = np.inf, np.nan
+    x = np.array([0.0, -0.0, inf, -inf, nan, -1.0, 1.0, 4.0])
+    y = call_host(lib, 'mkb_sqrt', x)
+    assert y[0] == 0 and y[1] == 0 and np.signbit(y[1]) and y[2] == inf
+    assert np.all(np.isnan(y[3:6])) and y[6] == 1.0 and y[7] == 2.0
+    y = call_host(lib, 'mkb_log', x)
+    assert y[0] == -inf and y[1] == -inf and y[2] == inf
+    assert np.all(np.isnan(y[3:6])) and y[6] == 0.0
+    y = call_host(lib, 'mkb_cos', x)
+    assert y[0] == 1.0 and y[1] == 1.0 and np.all(np.isnan(y[2:5]))
+    y = call_host(lib, 'mkb_acos', np.array([1.0, -1.0, 0.0, 2.0, -2.0, nan, 0.5, -0.5]))
+    assert y[0] == 0.0 and y[1] == np.pi and y[2] == np.pi / 2
+    assert np.all(np.isnan(y[3:6]))
+    assert abs(y[6] - np.pi / 3) < 3e-16 and abs(y[7] - 2 * np.pi / 3) < 5e-16
+
+
+def test_pow_through_exp_and_log():
+    import mpmath as mp
+    mp.mp.dps = 40
+    lib = host_library('cubic')
+    rng = np.random.default_rng(9)
+    x = np.exp(rng.uniform(-8, 8, 3000))
+    y = rng.uniform(-6, 6, 3000)
+    got = call_host(lib, 'pow', x, y)
+    worst = 0.0
+    for xi, yi, gi in zip(x, y, got):
+        want = mp.power(mp.mpf(float(xi)), mp.mpf(float(yi)))
+        ulp = mp.mpf(float(np.spacing(float(want))))
+        err = float(abs(mp.mpf(float(gi)) - want) / ulp)
+        worst = max(worst, err / (1.5 + abs(yi * np.log(xi))))
+    assert worst <= 1.0, worst
+    # 0^y, overflow and underflow, NaN
+    got = call_host(lib, 'pow', np.array([0.0, 0.0, 10.0, 10.0, np.nan, 2.0]),
+                    np.array([1.4, -1.4, 400.0, -400.0, 1.0, 0.5]))
+    assert got[0] == 0.0 and got[1] == np.inf and got[2] == np.inf and got[3] == 0.0
+    assert np.isnan(got[4]) and abs(got[5] - np.sqrt(2.0)) < 5e-16
