@@ -216,6 +216,11 @@ int mkb_sim_init(const mkb_sim_config* cfg, mkb_sim** out);
  * stays in HBM). Row slabs: call on every rank, then either step straight
  * away (mkb_sim_halo_live says 1) or barrier, mkb_sim_halo_seed, barrier. */
 int mkb_sim_rearm(mkb_sim* sim, const mkb_run_config* run);
+/* Replaces the resident state between runs (before mkb_sim_rearm) without
+ * rebuilding the simulation: `state_in` as in mkb_sim_config, `uniform` as
+ * mkb_sim_config::state_uniform. The reference re-creates its buffers and
+ * uploads the state on every run (openclsim.c:512-562). */
+int mkb_sim_set_state(mkb_sim* sim, const void* state_in, int uniform);
 /* Runs up to steps_per_call time steps. Returns 1 while t < tmax, 0 when the
  * run has finished (final state available), < 0 on error. *engine_time gets
  * the current time. *halted (may be null) is set when a NaN was found in the

@@ -35,7 +35,7 @@ SYMBOLS = [
     'mkb_sim_counters', 'mkb_sim_device_ms', 'mkb_sim_set_steps_per_call',
     'mkb_sim_reset_counters', 'mkb_sim_clean', 'mkb_sim_halo_info',
     'mkb_sim_halo_export', 'mkb_sim_halo_connect', 'mkb_sim_halo_seed',
-    'mkb_sim_rearm', 'mkb_sim_halo_live', 'mkb_measure_peaks', 'mkb_sim_ghost_connect',
+    'mkb_sim_rearm', 'mkb_sim_set_state', 'mkb_sim_halo_live', 'mkb_measure_peaks', 'mkb_sim_ghost_connect',
     'mkb_pacing_probe', 'mkb_schedule_probe',
     'mkb_sim_junction_connect', 'mkb_sim_step_pair',
 ]
@@ -194,6 +194,7 @@ def library():
     lib.mkb_sim_halo_export.argtypes = [c_vp, c_vp, ctypes.POINTER(c_vp)]
     lib.mkb_sim_halo_connect.argtypes = [c_vp, c_vp, c_vp, ctypes.c_int]
     lib.mkb_sim_halo_seed.argtypes = [c_vp]
+    lib.mkb_sim_set_state.argtypes = [c_vp, c_vp, ctypes.c_int]
     lib.mkb_sim_halo_live.argtypes = [c_vp, ctypes.POINTER(ctypes.c_int)]
     lib.mkb_sim_ghost_connect.argtypes = [
         c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(GhostPeer),

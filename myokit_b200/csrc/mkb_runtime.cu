@@ -447,6 +447,7 @@ struct mkb_sim {
     u64 step_index = 0;                 // steps taken in this run (1-based in the kernel)
     bool halo_live = false;             // exchange block consistent with step_index (see arm_run)
     bool halo_connected = false;        // halo_connect / ghost_connect + first seed done
+    bool state_replaced = false;        // mkb_sim_set_state since the last run
 
     // partitioned connection graphs: ghost cells (multi-GPU)
     u64 n_ghost = 0;
@@ -1785,6 +1786,35 @@ extern "C" int mkb_sim_get_state(mkb_sim* s, void* state_out) {
     return download_aos<float, float>(s, state_out);
 }
 
+template <typename TR>
+static int set_state_typed(mkb_sim* s, const void* state_in, int uniform) {
+    const bool host_double = (s->host_precision == MKB_DOUBLE);
+    int rc;
+    if (uniform) {
+        rc = host_double ? upload_uniform<double, TR>(s, state_in, plane_ptr<TR>(s, 0), s->n_state)
+                         : upload_uniform<TR, TR>(s, state_in, plane_ptr<TR>(s, 0), s->n_state);
+    } else {
+        rc = host_double ? upload_aos<double, TR>(s, state_in, plane_ptr<TR>(s, 0), s->n_state)
+                         : upload_aos<TR, TR>(s, state_in, plane_ptr<TR>(s, 0), s->n_state);
+    }
+    return rc;
+}
+
+extern "C" int mkb_sim_set_state(mkb_sim* s, const void* state_in, int uniform) {
+    if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
+    if (!state_in) return fail(MKB_ERR_INVALID, "state_in is null");
+    CUDA_TRY(cudaSetDevice(s->device));
+    // nothing of the previous run may still be in flight
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->side));
+    int rc = (s->precision == MKB_DOUBLE) ? set_state_typed<double>(s, state_in, uniform)
+                                          : set_state_typed<float>(s, state_in, uniform);
+    if (rc) return rc;
+    s->parity = 0;              // V(t) is in its own plane again
+    s->state_replaced = true;   // ghost rows / cells on the neighbours are stale
+    return MKB_OK;
+}
+
 extern "C" int mkb_sim_counters(mkb_sim* s, uint64_t* kernel_launches, uint64_t* steps) {
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
     if (kernel_launches) *kernel_launches = s->launches;
@@ -1943,7 +1973,8 @@ extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
     CUDA_TRY(cudaSetDevice(s->device));
     // (a run that halted on a NaN or was abandoned half way leaves ranks at
     // different steps: start the exchange protocol afresh then)
-    s->halo_live = s->d_xchg && s->halo_connected && s->finished && !s->halted;
+    s->halo_live = s->d_xchg && s->halo_connected && s->finished && !s->halted && !s->state_replaced;
+    s->state_replaced = false;
     int rc = arm_run(s, r);
     if (rc) return rc;
     // counters describe one run

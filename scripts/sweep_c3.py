@@ -120,6 +120,27 @@ SETS = {
         ('libm (diag. l1)', also(LM, debug_mem='l1')),
         ('libm cheap-select (diag. l1)', also(LM, select='cheap', debug_mem='l1')),
     ],
+    'r2e': [
+        ('libm pf-l1 la16', also(LM, prefetch='l1', load_ahead=16)),
+        ('libm pf-l1 la8', also(LM, prefetch='l1', load_ahead=8)),
+        ('libm pf-l1 la4', also(LM, prefetch='l1', load_ahead=4)),
+        ('libm pf-l1 la24', also(LM, prefetch='l1', load_ahead=24)),
+        ('libm pf-l1 la32', also(LM, prefetch='l1', load_ahead=32)),
+        ('libm pf-l2 la16', also(LM, prefetch='l2', load_ahead=16)),
+        ('libm pf-l1 la16 128x1 mb4', also(LM, prefetch='l1', load_ahead=16, block=(128, 1), min_blocks=4)),
+        ('libm pf-l1 la16 128x2 mb2', also(LM, prefetch='l1', load_ahead=16, block=(128, 2), min_blocks=2)),
+        ('libm pf-l1 la16 64x2 mb4', also(LM, prefetch='l1', load_ahead=16, block=(64, 2), min_blocks=4)),
+        ('libm pf-l1 la16 32x8 mb2', also(LM, prefetch='l1', load_ahead=16, block=(32, 8), min_blocks=2)),
+        ('libm pf-l1 la16 cheap-select', also(LM, prefetch='l1', load_ahead=16, select='cheap')),
+        ('libm pf-l1 la8 cheap-select', also(LM, prefetch='l1', load_ahead=8, select='cheap')),
+        ('libm pf-l1 la16 select 128x1 mb3 (168)', dict(prefetch='l1', load_ahead=16, block=(128, 1), min_blocks=3, max_registers=168)),
+        ('libm pf-l1 la8 select 128x1 mb3 (168)', dict(prefetch='l1', load_ahead=8, block=(128, 1), min_blocks=3, max_registers=168)),
+        ('libm pf-l1 la16 64x1 mb7', also(LM, prefetch='l1', load_ahead=16, block=(64, 1), min_blocks=7, max_registers=144)),
+        ('libm pf-l1 la16 nofmad', also(LM, prefetch='l1', load_ahead=16, fmad=False)),
+        ('libm pf-l1 la16 div newton', also(LM, prefetch='l1', load_ahead=16, div_cubic=False)),
+        ('libm pf-l1 la16 estrin', also(LM, prefetch='l1', load_ahead=16, fast_exp='estrin')),
+        ('libm pf-l1 la16 (diag. l1)', also(LM, prefetch='l1', load_ahead=16, debug_mem='l1')),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')

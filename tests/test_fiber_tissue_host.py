@@ -162,6 +162,10 @@ class _RecordingBackend:
         self._log[sim.value] = (r.n_log, r.tmin, r.tmax, r.log_interval)
         return 0
 
+    def mkb_sim_set_state(self, sim, state, uniform):
+        self.calls.append(('set_state', sim.value, uniform))
+        return 0
+
     def mkb_sim_junction_connect(self, f, t, g, cty):
         self.calls.append(('connect', f.value, t.value, g.value, cty.value))
         return 0
@@ -229,16 +233,23 @@ def test_pair_run_control_flow(monkeypatch):
     kinds = [c[0] for c in fake.calls[n0:]]
     assert kinds[:2] == ['rearm', 'rearm'] and 'connect' not in kinds
     assert s.time() == 3.0
-    # touching one grid restarts both and joins the new pair
+    # a new state goes into the resident pair: no restart, no new junction
     n0 = len(fake.calls)
     s.set_tissue_state(s.tissue_state())
+    s.run(1.0, logf=myokit.LOG_NONE, logt=myokit.LOG_NONE)
+    kinds = [c[0] for c in fake.calls[n0:]]
+    assert kinds.count('set_state') == 1 and kinds.count('rearm') == 2
+    assert 'init' not in kinds and 'connect' not in kinds
+    # touching what the kernels were built for restarts both and joins the new pair
+    n0 = len(fake.calls)
+    s._t.set_conductance(3, 2)
     s.run(1.0, logf=myokit.LOG_NONE, logt=myokit.LOG_NONE)
     kinds = [c[0] for c in fake.calls[n0:]]
     assert kinds.count('clean') == 2 and kinds.count('init') == 2
     assert kinds.count('connect') == 1
     # pre: time stays, defaults follow
     s.pre(1.0)
-    assert s.time() == 4.0
+    assert s.time() == 5.0
     s.close()
 
 
