@@ -368,7 +368,21 @@ def run_ours(args, rank, world):
     cold_s = max_over_ranks(time.perf_counter() - t0, world, dist, torch)
     cold_info = s.last_run_info()
     x = s.state_array(copy=False)       # page-locked; this rank's cells
-    v = x.reshape(-1, n_state)[:, i_vm]
+    # A wave train: after the advance only the columns next to the paced
+    # edge have fired (the front moves ~7 cells per ms). The first
+    # `args.wave_period` columns — resting tissue ahead of the front, the
+    # upstroke, the plateau behind it — are repeated across the grid, so the
+    # timed steps see cells in every phase of the action potential (the
+    # libdevice-free kernel has few data-dependent paths left, but the
+    # model's own piecewise branches are among them).
+    ny_local = x.size // (n_state * n)
+    grid_view = x.reshape(ny_local, n, n_state)
+    wp = args.wave_period
+    if wp and wp < n:
+        for c0 in range(wp, n, wp):
+            w = min(wp, n - c0)
+            grid_view[:, c0:c0 + w, :] = grid_view[:, :w, :]
+    v = grid_view[:, :, i_vm]
     wave = np.array([float((v > -60.0).sum()), float(v.size)])
     if world > 1:
         t = torch.from_numpy(wave).cuda()
@@ -376,8 +390,10 @@ def run_ours(args, rank, world):
         wave = t.cpu().numpy()
     wave = {'advance_steps': int(cold_info['steps']),
             't_ms': float(s.time()),
+            'wave_train_period_columns': wp,
             'cells_above_-60mV': wave[0] / wave[1],
             'v_min_max_mV': [float(v.min()), float(v.max())]}
+    s.set_state(x)                      # (our own array: adopted, uploaded by the next run)
 
     # ---- device-resident timing ---------------------------------------
     sampler = ClockSampler(local)
@@ -540,7 +556,9 @@ def main():
     ap.add_argument('--grid', type=int, default=2048)
     ap.add_argument('--cpu-grid', type=int, default=256)
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--advance', type=int, default=2000,
+    ap.add_argument('--wave-period', type=int, default=128,
+                    help='columns of the advanced tissue repeated across the grid (0: off)')
+    ap.add_argument('--advance', type=int, default=4000,
                     help='untimed time steps before anything is timed')
     ap.add_argument('--scale-grid', type=int, default=8192,
                     help='second grid timed in the same process (0: none)')

@@ -1016,6 +1016,7 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
 extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     if (!c || !out) return fail(MKB_ERR_INVALID, "null argument");
     *out = nullptr;
+    double t_phase = wall_s();
     if (c->abi_version != MKB_ABI_VERSION) {
         return fail(MKB_ERR_INVALID, "ABI version mismatch: library %d, caller %d", MKB_ABI_VERSION,
                     c->abi_version);
@@ -1120,6 +1121,7 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     INIT_CUDA(cudaEventCreate(&s->ev_t0));
     INIT_CUDA(cudaEventCreate(&s->ev_t1));
 
+    MKB_PHASE("init: streams + events");
     // Model kernel
     INIT_CUDA(cudaLibraryLoadData(&s->lib, c->cubin, nullptr, nullptr, 0, nullptr, nullptr, 0));
     INIT_CUDA(cudaLibraryGetKernel(&s->kern, s->lib, c->kernel_name));
@@ -1150,14 +1152,18 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     // 50 % slower — 1.58 vs 1.05 ms — because the shared-memory tile then limits
     // residency; the driver's default split is kept.)
 
+    MKB_PHASE("init: kernel image");
     // Buffers
     if (c->precision == MKB_DOUBLE) {
         INIT_TRY(preload_kernels<double>(s));
+        MKB_PHASE("init: preload kernels");
         INIT_TRY(sim_init_typed<double>(s, c));
     } else {
         INIT_TRY(preload_kernels<float>(s));
+        MKB_PHASE("init: preload kernels");
         INIT_TRY(sim_init_typed<float>(s, c));
     }
+    MKB_PHASE("init: planes, state, fields");
 
     // Paced cells: rectangle stays symbolic, a list becomes a byte mask
     s->grid.pace_x0 = s->grid.pace_x1 = s->grid.pace_y0 = s->grid.pace_y1 = 0;

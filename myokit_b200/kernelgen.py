@@ -848,10 +848,14 @@ _PRELUDE = _PRELUDE.replace('@EXP_POW2@', '\n'.join(
     '    %r,' % float.fromhex(h) for h in _EXP_POW2))
 
 
-def default_block(nx, ny, precision):
+def default_block(nx, ny, precision, n_state=0):
     """Thread-block tile ``(bx, by)`` for a grid of ``nx * ny`` cells."""
     if ny <= 1:
         return (128, 1) if nx <= 4096 else (256, 1)
+    if nx >= 256 and ny >= 2 and n_state > 16 \
+            and precision == myokit.DOUBLE_PRECISION:
+        # (C3 sweep: 128 x 2 is 1.5 % faster than 64 x 4 for the large model)
+        return (128, 2)
     if nx >= 64:
         return (64, 4)
     return (32, 8) if ny >= 8 else (32, 4)
@@ -860,9 +864,10 @@ def default_block(nx, ny, precision):
 def default_options(precision, n_state):
     """
     Generator defaults, from sweeps on a B200 (profiles/): double precision
-    uses the in-line division and exp and asks for two resident 256-thread
-    CTAs per SM (128 registers per thread) with states loaded 32 equations
-    ahead of use.
+    uses the in-line division, exp and branch-free sqrt / log / cos / acos /
+    pow, and for large models asks for two resident 256-thread CTAs per SM
+    (128 registers per thread), prefetches every state plane into L1 at the
+    top of the kernel and loads each state 24 equations ahead of its use.
     """
     if precision == myokit.SINGLE_PRECISION:
         # __fdividef: 2 ulp, inside the 2.5 ulp OpenCL allows its single-
@@ -871,9 +876,17 @@ def default_options(precision, n_state):
                     load_ahead=32,
                     cells_per_thread=4 if n_state <= 4 else 1,
                     rows_per_thread=4 if n_state <= 4 else 1)
-    return dict(min_blocks=2 if n_state > 16 else None, fast_div=True,
-                fast_exp='poly', load_ahead=32, div_cubic=True,
-                fast_libm=True, select=True,
+    big = n_state > 16
+    return dict(min_blocks=2 if big else None, fast_div=True,
+                fast_exp='poly', div_cubic=True, fast_libm=True,
+                # (measured on C3, profiles/r02_sweeps.md: conditionals as
+                # selects make the whole body one scheduling region, which
+                # ptxas fills until it spills 430 bytes per thread at 128
+                # registers — slower than leaving the model's own branches)
+                select=False,
+                load_ahead=24 if big else 32,
+                prefetch='l1' if big else None,
+                slab_lean=True,
                 cells_per_thread=2 if n_state <= 4 else 1,
                 rows_per_thread=4 if n_state <= 4 else 1)
 

@@ -27,6 +27,7 @@ for dur in (5, 10, 20):
     scale = np.abs(sb).reshape(-1, ns).max(axis=0)
     for name, opts in (('default', None), ('ieee div', dict(fast_div=False)), ('ieee div nofmad', dict(fast_div=False, fmad=False))):
         sa = run(myokit_b200.SimulationCUDA, {}, {}, opts, dur=dur)
+        print('   nan: cuda', int(np.isnan(sa).sum()), 'oracle', int(np.isnan(sb).sum()), 'scale', scale)
         rel = np.abs(sa - sb).reshape(-1, ns) / scale
         k = np.unravel_index(np.argmax(rel), rel.shape)
         print(dur, name, 'rel max %.3g' % rel.max(), 'state', k[1], 'cell', divmod(int(k[0]), n), 'p99.99 %.3g' % np.quantile(rel, 0.9999), flush=True)

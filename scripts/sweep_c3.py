@@ -141,6 +141,17 @@ SETS = {
         ('libm pf-l1 la16 estrin', also(LM, prefetch='l1', load_ahead=16, fast_exp='estrin')),
         ('libm pf-l1 la16 (diag. l1)', also(LM, prefetch='l1', load_ahead=16, debug_mem='l1')),
     ],
+    'r2f': [
+        ('default', dict(block=None, min_blocks=2, load_ahead=24, prefetch='l1', select=False)),
+        ('64x4 la24', also(LM, prefetch='l1', load_ahead=24)),
+        ('128x2 la24', also(LM, prefetch='l1', load_ahead=24, block=(128, 2))),
+        ('128x2 la20', also(LM, prefetch='l1', load_ahead=20, block=(128, 2))),
+        ('128x2 la28', also(LM, prefetch='l1', load_ahead=28, block=(128, 2))),
+        ('256x1 la24', also(LM, prefetch='l1', load_ahead=24, block=(256, 1))),
+        ('128x2 la24 pf-l2', also(LM, prefetch='l2', load_ahead=24, block=(128, 2))),
+        ('128x4 mb1 la24', also(LM, prefetch='l1', load_ahead=24, block=(128, 4), min_blocks=1, max_registers=128)),
+        ('128x2 la24 (diag. l1)', also(LM, prefetch='l1', load_ahead=24, block=(128, 2), debug_mem='l1')),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
