@@ -927,7 +927,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              const_div=True, slab_lean=False, div_parallel=False,
              junction=None, persistent=False, split_gates=False,
              div_cubic=False, prefetch=None, debug_mem=None,
-             fast_libm=False, select=False, exp_scale='mul'):
+             fast_libm=False, select=False, exp_scale='mul', stream=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -1068,6 +1068,11 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 'Tile too large: block %dx%d with cells_per_thread=%d,'
                 ' rows_per_thread=%d needs %d bytes of shared memory for its'
                 ' rim exchange (limit 49152).' % (bx, by, cpt, rpt_, smem))
+
+    # Streaming form of the vector path (see the emitter below): regular 2-d
+    # grids whose rows are 16-byte multiples, one warp across a tile row
+    stream = bool(stream) and cpt > 1 and diffusion_mode in (
+        DIFF_HOMOGENEOUS, DIFF_FIELD) and bx == 32 and not stab
 
     if junction not in (None, 'fiber', 'tissue'):
         raise ValueError('junction must be None, "fiber" or "tissue".')
@@ -1640,108 +1645,219 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             for x in w._pool:
                 q('    %r,' % x)
             q('};')
-        q('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
-        q('%s(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
-        q('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
-        q('{')
-        q('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
-        q('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
-        q('    const unsigned long long stride = g.stride;')
-        q('    const unsigned int nby = (ny + MKB_BY * MKB_RPT - 1) / (MKB_BY * MKB_RPT);')
-        q('    const unsigned int byr = blockIdx.y + blockIdx.z * gridDim.y;')
-        q('    if (byr >= nby) return;')
-        q('    // This thread owns the patch of cells ix0 .. ix0 + MKB_CPT - 1 (nx is a')
-        q('    // multiple of MKB_CPT: all inside or all outside) by rows iy0 .. iy0 +')
-        q('    // MKB_RPT - 1. Neighbours inside the patch are in registers; only the')
-        q('    // rim of the patch is exchanged through shared memory.')
-        q('    const unsigned int ix0 = (blockIdx.x * MKB_BX + tx) * MKB_CPT;')
-        q('    const unsigned int iy0 = (byr * MKB_BY + ty) * MKB_RPT;')
-        q('    const bool in_x = ix0 < nx;')
-        q('    Real* const state = (Real*)g.state;')
-        q('    const Real time = (Real)sp->time;')
-        q('    const Real dt = (Real)sp->dt;')
-        q('    const Real pace_in = (Real)sp->pace;')
-        q('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
-        q('    (void)time; (void)pace_in; (void)store_aux; (void)v_in; (void)v_out;')
-        q('')
-        q('    // All vector loads of this thread first: they are in flight together')
-        if diffusion:
-            q('    Real vc[MKB_RPT][MKB_CPT];')
-        for var in states:
-            if var.index() != i_vm:
-                q('    Real S%d[MKB_RPT][MKB_CPT];' % var.index())
-        for k, var in enumerate(fields):
-            q('    Real F%d[MKB_RPT][MKB_CPT];' % k)
-        q('    #pragma unroll')
-        q('    for (int r = 0; r < MKB_RPT; r++) {')
-        q('        const unsigned int iy = iy0 + r;')
-        q('        const bool active = in_x && (iy < ny);')
-        q('        const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
-        if diffusion:
-            q('        mkb_vload<MKB_CPT>(vc[r], v_in + cid0, active);')
-        for var in states:
-            if var.index() != i_vm:
-                q('        mkb_vload<MKB_CPT>(S%d[r], state + %dull * stride + cid0, active);'
-                  % (var.index(), var.index()))
-        for k, var in enumerate(fields):
-            q('        mkb_vload<MKB_CPT>(F%d[r], (const Real*)g.field + %dull * stride + cid0, active);'
-              % (k, k))
-        q('    }')
-        if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+        if stream:
+            # ----------------------------------------------------------
+            # Streaming form: persistent thread blocks walk the tiles of
+            # the grid; the V tile with its halo arrives in shared memory
+            # by TMA (cp.async.bulk.tensor.2d, out-of-grid cells zero
+            # filled) into a two-stage ring guarded by mbarriers, so the
+            # next tile's load is in flight while this one is computed and
+            # no thread holds a register or issues an instruction for it.
+            # One warp spans a tile row: left / right neighbours of a
+            # thread's patch come by shuffle, rows above / below from the
+            # tile. Everything after the loads is the vector path's code.
+            # ----------------------------------------------------------
+            q('#define MKB_TW (MKB_BX * MKB_CPT)')
+            q('#define MKB_TH (MKB_BY * MKB_RPT)')
+            q('#define MKB_PAD (16 / (int)sizeof(Real))')
+            q('#define MKB_BW (MKB_TW + 2 * MKB_PAD)')
+            q('#define MKB_BH (MKB_TH + 2)')
+            q('#define MKB_STAGES 2')
+            q('#define MKB_I_VM %d' % i_vm)
+            q('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY, %d)' % int(min_blocks or 2))
+            q('%s(const __grid_constant__ MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
+            q('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
+            q('{')
+            q('    __shared__ alignas(128) Real tile[MKB_STAGES][MKB_BH][MKB_BW];')
+            q('    __shared__ alignas(8) unsigned long long full[MKB_STAGES];')
+            q('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
+            q('    const unsigned int tid = ty * MKB_BX + tx;')
+            q('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+            q('    const unsigned long long stride = g.stride;')
+            q('    const unsigned int ntx = (nx + MKB_TW - 1) / MKB_TW;')
+            q('    const unsigned int n_tiles = ntx * ((ny + MKB_TH - 1) / MKB_TH);')
+            q('    Real* const state = (Real*)g.state;')
+            q('    // descriptor of the V plane this step reads')
+            q('    const void* const tmap = (v_in == state + (unsigned long long)MKB_I_VM * stride)')
+            q('        ? (const void*)g.tmap[0] : (const void*)g.tmap[1];')
+            q('    const Real time = (Real)sp->time;')
+            q('    const Real dt = (Real)sp->dt;')
+            q('    const Real pace_in = (Real)sp->pace;')
+            q('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
+            q('    (void)time; (void)pace_in; (void)store_aux; (void)v_out;')
             q('    const unsigned int nyg = (unsigned int)g.ny_global;')
-            q('    // Rim exchange: first / last column of every row of the patch, first')
-            q('    // and last row of the patch; block-edge threads fetch the true halo.')
-            q('    __shared__ Real col_l[MKB_BY * MKB_RPT][MKB_BX + 2];   // [row][tx + 1]: first cell')
-            q('    __shared__ Real col_r[MKB_BY * MKB_RPT][MKB_BX + 2];   // [row][tx + 1]: last cell')
-            q('    __shared__ Real row_t[MKB_BY + 2][MKB_BX * MKB_CPT];   // [ty + 1]: first row')
-            q('    __shared__ Real row_b[MKB_BY + 2][MKB_BX * MKB_CPT];   // [ty + 1]: last row')
+            q('    if (tid == 0) {')
+            q('        for (int s = 0; s < MKB_STAGES; s++) MKB_MBAR_INIT(&full[s], 1);')
+            q('        MKB_MBAR_FENCE_INIT();')
+            q('        for (unsigned int s = 0; s < MKB_STAGES; s++) {')
+            q('            const unsigned int t = blockIdx.x + s * gridDim.x;')
+            q('            if (t < n_tiles) {')
+            q('                const unsigned int tyb = t / ntx, txb = t - tyb * ntx;')
+            q('                MKB_TMA_LOAD_2D(&tile[s][0][0], tmap, (int)(txb * MKB_TW) - MKB_PAD, (int)(tyb * MKB_TH) - 1,')
+            q('                                &full[s], MKB_BW, MKB_BH, (unsigned int)(MKB_BW * MKB_BH * sizeof(Real)));')
+            q('            }')
+            q('        }')
+            q('    }')
+            q('    __syncthreads();')
+            q('    unsigned int k_iter = 0;')
+            q('    for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x, k_iter++) {')
+            q('    const unsigned int stg = k_iter % MKB_STAGES, phase = (k_iter / MKB_STAGES) & 1u;')
+            q('    const unsigned int tyb = t / ntx, txb = t - tyb * ntx;')
+            q('    const unsigned int ix0 = txb * MKB_TW + tx * MKB_CPT;')
+            q('    const unsigned int iy0 = tyb * MKB_TH + ty * MKB_RPT;')
+            q('    const bool in_x = ix0 < nx;')
+            q('    // Vector loads of the other planes first: in flight while the tile is awaited')
+            q('    Real vc[MKB_RPT][MKB_CPT];')
+            for var in states:
+                if var.index() != i_vm:
+                    q('    Real S%d[MKB_RPT][MKB_CPT];' % var.index())
+            for k, var in enumerate(fields):
+                q('    Real F%d[MKB_RPT][MKB_CPT];' % k)
+            if len(states) > 1 or fields:
+                q('    #pragma unroll')
+                q('    for (int r = 0; r < MKB_RPT; r++) {')
+                q('        const unsigned int iy = iy0 + r;')
+                q('        const bool active = in_x && (iy < ny);')
+                q('        const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
+                for var in states:
+                    if var.index() != i_vm:
+                        q('        mkb_vload<MKB_CPT>(S%d[r], state + %dull * stride + cid0, active);'
+                          % (var.index(), var.index()))
+                for k, var in enumerate(fields):
+                    q('        mkb_vload<MKB_CPT>(F%d[r], (const Real*)g.field + %dull * stride + cid0, active);'
+                      % (k, k))
+                q('    }')
+            q('    MKB_MBAR_WAIT(&full[stg], phase);')
+            q('    // this thread\'s patch, the rows above and below it, the cells left and right')
+            q('    Real v_up[MKB_CPT], v_dn[MKB_CPT], v_lf[MKB_RPT], v_rt[MKB_RPT];')
+            q('    {')
+            q('        const Real (*tl)[MKB_BW] = tile[stg];')
+            q('        const unsigned int c0 = MKB_PAD + tx * MKB_CPT, r0 = ty * MKB_RPT + 1;')
+            q('        mkb_vload<MKB_CPT>(v_up, &tl[r0 - 1][c0], true);')
+            q('        mkb_vload<MKB_CPT>(v_dn, &tl[r0 + MKB_RPT][c0], true);')
+            q('        #pragma unroll')
+            q('        for (int r = 0; r < MKB_RPT; r++) {')
+            q('            mkb_vload<MKB_CPT>(vc[r], &tl[r0 + r][c0], true);')
+            q('            const Real lf = MKB_SHFL_UP(vc[r][MKB_CPT - 1], 1);')
+            q('            const Real rt = MKB_SHFL_DOWN(vc[r][0], 1);')
+            q('            v_lf[r] = (tx == 0) ? tl[r0 + r][MKB_PAD - 1] : lf;')
+            q('            v_rt[r] = (tx == MKB_BX - 1) ? tl[r0 + r][MKB_PAD + MKB_TW] : rt;')
+            q('        }')
+            q('    }')
+            q('    __syncthreads();        // every thread has read the stage: refill it')
+            q('    if (tid == 0) {')
+            q('        const unsigned int tn = t + MKB_STAGES * gridDim.x;')
+            q('        if (tn < n_tiles) {')
+            q('            const unsigned int nyb = tn / ntx, nxb = tn - nyb * ntx;')
+            q('            MKB_TMA_LOAD_2D(&tile[stg][0][0], tmap, (int)(nxb * MKB_TW) - MKB_PAD, (int)(nyb * MKB_TH) - 1,')
+            q('                            &full[stg], MKB_BW, MKB_BH, (unsigned int)(MKB_BW * MKB_BH * sizeof(Real)));')
+            q('        }')
+            q('    }')
+            q('    if (!in_x || iy0 >= ny) continue;')
+            q('    const bool at_x0 = (ix0 == 0), at_x1 = (ix0 + MKB_CPT == nx);')
+        else:
+            q('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
+            q('%s(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
+            q('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
+            q('{')
+            q('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
+            q('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+            q('    const unsigned long long stride = g.stride;')
+            q('    const unsigned int nby = (ny + MKB_BY * MKB_RPT - 1) / (MKB_BY * MKB_RPT);')
+            q('    const unsigned int byr = blockIdx.y + blockIdx.z * gridDim.y;')
+            q('    if (byr >= nby) return;')
+            q('    // This thread owns the patch of cells ix0 .. ix0 + MKB_CPT - 1 (nx is a')
+            q('    // multiple of MKB_CPT: all inside or all outside) by rows iy0 .. iy0 +')
+            q('    // MKB_RPT - 1. Neighbours inside the patch are in registers; only the')
+            q('    // rim of the patch is exchanged through shared memory.')
+            q('    const unsigned int ix0 = (blockIdx.x * MKB_BX + tx) * MKB_CPT;')
+            q('    const unsigned int iy0 = (byr * MKB_BY + ty) * MKB_RPT;')
+            q('    const bool in_x = ix0 < nx;')
+            q('    Real* const state = (Real*)g.state;')
+            q('    const Real time = (Real)sp->time;')
+            q('    const Real dt = (Real)sp->dt;')
+            q('    const Real pace_in = (Real)sp->pace;')
+            q('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
+            q('    (void)time; (void)pace_in; (void)store_aux; (void)v_in; (void)v_out;')
+            q('')
+            q('    // All vector loads of this thread first: they are in flight together')
+            if diffusion:
+                q('    Real vc[MKB_RPT][MKB_CPT];')
+            for var in states:
+                if var.index() != i_vm:
+                    q('    Real S%d[MKB_RPT][MKB_CPT];' % var.index())
+            for k, var in enumerate(fields):
+                q('    Real F%d[MKB_RPT][MKB_CPT];' % k)
             q('    #pragma unroll')
             q('    for (int r = 0; r < MKB_RPT; r++) {')
             q('        const unsigned int iy = iy0 + r;')
-            q('        const unsigned int tr = ty * MKB_RPT + r;')
-            q('        // (own slots only for threads of the grid: the slot of a thread past the')
-            q('        // last column is the halo slot of its left neighbour, written below)')
-            q('        if (in_x && iy < ny) {')
-            q('            col_l[tr][tx + 1] = vc[r][0];')
-            q('            col_r[tr][tx + 1] = vc[r][MKB_CPT - 1];')
-            q('            const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
-            q('            // halo cells left and right of the block')
-            q('            if (tx == 0) col_r[tr][0] = (ix0 > 0) ? v_in[cid0 - 1] : vc[r][0];')
-            q('            if (tx == MKB_BX - 1 || ix0 + MKB_CPT >= nx)')
-            q('                col_l[tr][tx + 2] = (ix0 + MKB_CPT < nx) ? v_in[cid0 + MKB_CPT] : vc[r][MKB_CPT - 1];')
-            q('        }')
+            q('        const bool active = in_x && (iy < ny);')
+            q('        const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
+            if diffusion:
+                q('        mkb_vload<MKB_CPT>(vc[r], v_in + cid0, active);')
+            for var in states:
+                if var.index() != i_vm:
+                    q('        mkb_vload<MKB_CPT>(S%d[r], state + %dull * stride + cid0, active);'
+                      % (var.index(), var.index()))
+            for k, var in enumerate(fields):
+                q('        mkb_vload<MKB_CPT>(F%d[r], (const Real*)g.field + %dull * stride + cid0, active);'
+                  % (k, k))
             q('    }')
-            q('    #pragma unroll')
-            q('    for (int c = 0; c < MKB_CPT; c++) {')
-            q('        row_t[ty + 1][tx * MKB_CPT + c] = vc[0][c];')
-            q('        row_b[ty + 1][tx * MKB_CPT + c] = vc[MKB_RPT - 1][c];')
-            q('    }')
-            q('    if (in_x && iy0 < ny) {')
-            q('        if (ty == 0) {')
-            q('            // row above the block')
-            q('            Real vn[MKB_CPT];')
-            q('            mkb_vload<MKB_CPT>(vn, v_in + (unsigned long long)(iy0 - 1) * nx + ix0, iy0 > 0);')
-            q('            #pragma unroll')
-            q('            for (int c = 0; c < MKB_CPT; c++) row_b[0][tx * MKB_CPT + c] = vn[c];')
-            q('        }')
-            q('        if (ty == MKB_BY - 1) {')
-            q('            // row below the block')
-            q('            Real vn[MKB_CPT];')
-            q('            mkb_vload<MKB_CPT>(vn, v_in + (unsigned long long)(iy0 + MKB_RPT) * nx + ix0, iy0 + MKB_RPT < ny);')
-            q('            #pragma unroll')
-            q('            for (int c = 0; c < MKB_CPT; c++) row_t[MKB_BY + 1][tx * MKB_CPT + c] = vn[c];')
-            q('        }')
-            q('    }')
-            if stab:
-                q('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
-            q('    __syncthreads();')
-            q('    if (!in_x || iy0 >= ny) return;')
-            q('    const bool at_x0 = (ix0 == 0), at_x1 = (ix0 + MKB_CPT == nx);')
-        else:
-            if stab:
-                q('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
+            if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+                q('    const unsigned int nyg = (unsigned int)g.ny_global;')
+                q('    // Rim exchange: first / last column of every row of the patch, first')
+                q('    // and last row of the patch; block-edge threads fetch the true halo.')
+                q('    __shared__ Real col_l[MKB_BY * MKB_RPT][MKB_BX + 2];   // [row][tx + 1]: first cell')
+                q('    __shared__ Real col_r[MKB_BY * MKB_RPT][MKB_BX + 2];   // [row][tx + 1]: last cell')
+                q('    __shared__ Real row_t[MKB_BY + 2][MKB_BX * MKB_CPT];   // [ty + 1]: first row')
+                q('    __shared__ Real row_b[MKB_BY + 2][MKB_BX * MKB_CPT];   // [ty + 1]: last row')
+                q('    #pragma unroll')
+                q('    for (int r = 0; r < MKB_RPT; r++) {')
+                q('        const unsigned int iy = iy0 + r;')
+                q('        const unsigned int tr = ty * MKB_RPT + r;')
+                q('        // (own slots only for threads of the grid: the slot of a thread past the')
+                q('        // last column is the halo slot of its left neighbour, written below)')
+                q('        if (in_x && iy < ny) {')
+                q('            col_l[tr][tx + 1] = vc[r][0];')
+                q('            col_r[tr][tx + 1] = vc[r][MKB_CPT - 1];')
+                q('            const unsigned long long cid0 = (unsigned long long)iy * nx + ix0;')
+                q('            // halo cells left and right of the block')
+                q('            if (tx == 0) col_r[tr][0] = (ix0 > 0) ? v_in[cid0 - 1] : vc[r][0];')
+                q('            if (tx == MKB_BX - 1 || ix0 + MKB_CPT >= nx)')
+                q('                col_l[tr][tx + 2] = (ix0 + MKB_CPT < nx) ? v_in[cid0 + MKB_CPT] : vc[r][MKB_CPT - 1];')
+                q('        }')
+                q('    }')
+                q('    #pragma unroll')
+                q('    for (int c = 0; c < MKB_CPT; c++) {')
+                q('        row_t[ty + 1][tx * MKB_CPT + c] = vc[0][c];')
+                q('        row_b[ty + 1][tx * MKB_CPT + c] = vc[MKB_RPT - 1][c];')
+                q('    }')
+                q('    if (in_x && iy0 < ny) {')
+                q('        if (ty == 0) {')
+                q('            // row above the block')
+                q('            Real vn[MKB_CPT];')
+                q('            mkb_vload<MKB_CPT>(vn, v_in + (unsigned long long)(iy0 - 1) * nx + ix0, iy0 > 0);')
+                q('            #pragma unroll')
+                q('            for (int c = 0; c < MKB_CPT; c++) row_b[0][tx * MKB_CPT + c] = vn[c];')
+                q('        }')
+                q('        if (ty == MKB_BY - 1) {')
+                q('            // row below the block')
+                q('            Real vn[MKB_CPT];')
+                q('            mkb_vload<MKB_CPT>(vn, v_in + (unsigned long long)(iy0 + MKB_RPT) * nx + ix0, iy0 + MKB_RPT < ny);')
+                q('            #pragma unroll')
+                q('            for (int c = 0; c < MKB_CPT; c++) row_t[MKB_BY + 1][tx * MKB_CPT + c] = vn[c];')
+                q('        }')
+                q('    }')
+                if stab:
+                    q('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
                 q('    __syncthreads();')
-            q('    if (!in_x || iy0 >= ny) return;')
+                q('    if (!in_x || iy0 >= ny) return;')
+                q('    const bool at_x0 = (ix0 == 0), at_x1 = (ix0 + MKB_CPT == nx);')
+            else:
+                if stab:
+                    q('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
+                    q('    __syncthreads();')
+                q('    if (!in_x || iy0 >= ny) return;')
         if diffusion_mode == DIFF_HOMOGENEOUS:
             q('    const Real gx = (Real)g.gx, gy = (Real)g.gy;')
         if diffusion_mode == DIFF_FIELD:

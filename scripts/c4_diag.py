@@ -14,7 +14,7 @@ ih, ij = m.get('ina.h').index(), m.get('ina.j').index()
 state[:n // 2, 40:60, iv] = 10.0
 state[:n // 2, 0:40, ih] = 0.0
 state[:n // 2, 0:40, ij] = 0.0
-state[:n // 2, 0:40, iv] = -40.0
+state[:n // 2, 0:40, iv] = -55.0
 def run(cls, kw, run_kw, opts=None, dur=20):
     s = cls(m, None, ncells=(n, n), precision=SP, **kw)
     s.set_conductance(1, 1); s.set_paced_cells(0, 0, 0, 0); s.set_step_size(0.005)

@@ -40,7 +40,14 @@ class Recorder(unittest.TestResult):
 
     def _first(self, text):
         lines = [x for x in str(text).strip().splitlines() if x.strip()]
-        return lines[-1][:160] if lines else ''
+        if not lines:
+            return ''
+        # (compilation errors of the host framework's own CVODE simulation end
+        # with an argument dump: name the exception instead)
+        for x in lines:
+            if 'Error' in x and not x.startswith(' '):
+                return x[:160]
+        return lines[-1][:160]
 
     def addSuccess(self, test):
         self.rows.append((test.id(), 'pass', ''))

@@ -88,10 +88,13 @@ def test_c4_proxy_512_fp32_20_ms_state_within_1e3():
     iv = m.get('membrane.V').index()
     ih, ij = m.get('ina.h').index(), m.get('ina.j').index()
     # broken wave: depolarised band in the lower half, refractory tail beside it
+    # (the tail starts below -47.13 mV: the model's ina.m.alpha is 0 / 0 there,
+    # and cells that relax slowly through that value in single precision hit it
+    # — in this back-end and in the oracle alike: NaN in 4976 cells after 5 ms)
     state[:n // 2, 40:60, iv] = 10.0
     state[:n // 2, 0:40, ih] = 0.0
     state[:n // 2, 0:40, ij] = 0.0
-    state[:n // 2, 0:40, iv] = -40.0
+    state[:n // 2, 0:40, iv] = -55.0
     res = []
     for cls, kw, run_kw in ((myokit_b200.SimulationCUDA, {}, {}),
                             (OracleSimulation, dict(openmp=True), dict(nthreads=CORES))):
