@@ -158,17 +158,18 @@ typedef struct mkb_sim_config {
     const char* second_kernel_name; /* NULL, or the kernel launched after every
                                        `kernel_name` launch ("mkb_gate_step") */
     int kernel_flags;           /* MKB_KERNEL_* */
+    int stream_box_w, stream_box_h; /* MKB_KERNEL_STREAM: the TMA box (cells, rows) the
+                                       kernel loads per tile, halo included */
 } mkb_sim_config;
 
 /* kernel_flags */
 #define MKB_KERNEL_PERSISTENT 1 /* kernel_name takes `flags >> 8` steps per launch; the
                                    grid fits one thread block */
-#define MKB_KERNEL_STREAM     2 /* kernel_name is a persistent-warp streaming kernel:
-                                   launched with sm_count * blocks_per_sm thread blocks
-                                   of block_x * block_y threads and `stream_smem` bytes
-                                   of dynamic shared memory */
+#define MKB_KERNEL_STREAM     2 /* kernel_name is a streaming kernel: a persistent grid of
+                                   min(tiles, sm_count * blocks_per_sm) thread blocks walks
+                                   the tiles of the grid; the V tile + halo arrives by TMA
+                                   through the descriptors in MkbGridArgs::tmap */
 #define MKB_KERNEL_FLAG_SHIFT_BLOCKS 8   /* bits 8..15: thread blocks per SM (stream) */
-#define MKB_KERNEL_FLAG_SHIFT_SMEM   16  /* bits 16..31: dynamic shared memory, in 256-byte units */
 
 /* A run on the state that is already resident on the device (mkb_sim_rearm):
  * the time span, step size, protocol and log selection of mkb_sim_config. */

@@ -77,7 +77,7 @@ def build_library(force=False, verbose=False):
         '-Xcompiler', '-fPIC,-Wall', '-shared', '-cudart', 'static',
         '-o', tmp,
     ] + [os.path.join(CSRC, s) for s in SOURCES] + [
-        '-L' + libdir, '-lnvrtc', '-Xlinker', '-rpath=' + libdir,
+        '-L' + libdir, '-lnvrtc', '-ldl', '-Xlinker', '-rpath=' + libdir,
     ]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')

@@ -82,6 +82,7 @@ class SimConfig(ctypes.Structure):
         ('state_uniform', ctypes.c_int),
         ('second_kernel_name', ctypes.c_char_p),
         ('kernel_flags', ctypes.c_int),
+        ('stream_box_w', ctypes.c_int), ('stream_box_h', ctypes.c_int),
     ]
 
 

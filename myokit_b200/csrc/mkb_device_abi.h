@@ -103,6 +103,12 @@ struct MkbGridArgs {
     const void* junction_v1;
     double jg;
     unsigned long long jx, jy0, jn, joff, jstride;
+    /* Streaming kernels (kernelgen stream=True): TMA descriptors
+     * (cuTensorMapEncodeTiled) of the two membrane-potential planes as 2-d
+     * tensors [ny][nx] with the box the kernel was generated for: tmap[0] the
+     * plane inside `state`, tmap[1] the second V plane. A kernel that uses them
+     * declares its grid argument __grid_constant__. Zero elsewhere. */
+    alignas(64) unsigned long long tmap[2][16];
 };
 
 #endif

@@ -19,8 +19,10 @@
 //
 // No CPU fallback exists: every compute entry point fails with MKB_ERR_CUDA
 // when there is no device.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <nvrtc.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <chrono>
@@ -561,6 +563,15 @@ static void sim_destroy(mkb_sim* s) {
     delete s;
 }
 
+// NVTX range for the lifetime of a scope (shows up in Nsight Systems / ncu
+// --nvtx timelines: init, arm, step calls, log flush, state transfers).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 static int grid_for(u64 n) {
     u64 b = (n + 255) / 256;
     return (int)std::min<u64>(std::max<u64>(b, 1), 148 * 16);
@@ -831,6 +842,7 @@ static double wall_s() {
 // rings, pacing (openclsim.c:488-496), schedule (:501, :1018-1022). Used by
 // mkb_sim_init and mkb_sim_rearm.
 static int arm_run(mkb_sim* s, const mkb_run_config* r) {
+    NvtxRange nvtx_("mkb: arm run");
     if (!(r->dt > 0)) return fail(MKB_ERR_INVALID, "Step size must be greater than zero.");
     if (r->tmax < r->tmin) return fail(MKB_ERR_INVALID, "Simulation time can't be negative.");
     double t_phase = wall_s();
@@ -1014,6 +1026,7 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
 }
 
 extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
+    NvtxRange nvtx_("mkb_sim_init");
     if (!c || !out) return fail(MKB_ERR_INVALID, "null argument");
     *out = nullptr;
     double t_phase = wall_s();
@@ -1267,6 +1280,51 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
         }
         s->launch_grid = dim3((unsigned int)bx, (unsigned int)gy, (unsigned int)gz);
         s->launch_block = dim3((unsigned int)s->block_x, (unsigned int)s->block_y, 1);
+        if (c->kernel_flags & MKB_KERNEL_STREAM) {
+            // Streaming kernel: a persistent grid walks the tiles; the two V
+            // planes are described to the TMA unit as [ny][nx] tensors with
+            // the kernel's box (halo included; cells outside arrive as zeros).
+            if (s->i_vm < 0 || c->stream_box_w <= 0 || c->stream_box_h <= 0 || c->stream_box_w > 256 ||
+                c->stream_box_h > 256 || (s->nx * s->rs) % 16 != 0 || (c->stream_box_w * s->rs) % 16 != 0) {
+                sim_destroy(s);
+                return fail(MKB_ERR_INVALID, "Streaming kernel: rows of %llu cells / a box of %d x %d cannot be "
+                                             "described to the TMA unit (16-byte multiples, at most 256 per side).",
+                            (unsigned long long)s->nx, c->stream_box_w, c->stream_box_h);
+            }
+            typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                          CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                          CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            INIT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) {
+                sim_destroy(s);
+                return fail(MKB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+            }
+            static_assert(sizeof(CUtensorMap) == sizeof(g.tmap[0]), "tensor map size");
+            const u64 planes[2] = {(u64)std::max(s->i_vm, 0), s->plane_alt_v};
+            for (int k = 0; k < 2; k++) {
+                const cuuint64_t dims[2] = {s->nx, s->ny};
+                const cuuint64_t strides[1] = {s->nx * s->rs};
+                const cuuint32_t box[2] = {(cuuint32_t)c->stream_box_w, (cuuint32_t)c->stream_box_h};
+                const cuuint32_t estr[2] = {1, 1};
+                CUresult r = ((encode_fn)fn)(
+                    (CUtensorMap*)g.tmap[k], s->rs == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                    2, s->d_planes + planes[k] * s->stride * s->rs, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    sim_destroy(s);
+                    return fail(MKB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+                }
+            }
+            int sms = 0;
+            INIT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+            const u64 per_sm = std::max<u64>(1, ((u64)c->kernel_flags >> MKB_KERNEL_FLAG_SHIFT_BLOCKS) & 0xff);
+            const u64 tiles = bx * by;
+            s->launch_grid = dim3((unsigned int)std::min<u64>(tiles, (u64)sms * per_sm), 1, 1);
+        }
     }
 
     // Logging, pacing and schedule of the first run
@@ -1341,6 +1399,7 @@ static int ensure_host_rows(mkb_sim* s, u64 rows) {
 
 // Issues the D2H copy of rows [rows_flushed, rows_written) on the side stream.
 static int flush_rows(mkb_sim* s) {
+    NvtxRange nvtx_("mkb: flush log rows");
     if (s->rows_flushed == s->rows_written) return MKB_OK;
     int rc = ensure_host_rows(s, s->rows_written);
     if (rc) return rc;
@@ -1454,6 +1513,7 @@ static int graph_get(mkb_sim* s, int slot, int parity, cudaGraphExec_t* out) {
 
 template <typename TR>
 static int sim_step_typed(mkb_sim* s, bool drain = true) {
+    NvtxRange nvtx_("mkb: step batch");
     u64 steps_left = s->steps_per_call;
     bool timing_started = false;
 
@@ -1666,6 +1726,7 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
 }
 
 extern "C" int mkb_sim_step(mkb_sim* s, double* engine_time, int* halted) {
+    NvtxRange nvtx_("mkb_sim_step");
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
     if (s->n_ghost > 0 && !s->ghosts_connected) {
         return fail(MKB_ERR_STATE, "Graph partition not connected to its peers (mkb_sim_ghost_connect).");
@@ -1739,6 +1800,7 @@ extern "C" int mkb_sim_junction_connect(mkb_sim* f, mkb_sim* t, double g, uint64
 
 template <typename TR>
 static int sim_drain_typed(mkb_sim* s) {
+    NvtxRange nvtx_("mkb: drain log");
     int rc = flush_rows(s);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1784,6 +1846,7 @@ extern "C" int mkb_sim_log_view(mkb_sim* s, const void** data, uint64_t* rows, u
 }
 
 extern "C" int mkb_sim_get_state(mkb_sim* s, void* state_out) {
+    NvtxRange nvtx_("mkb_sim_get_state");
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
     if (!state_out) return fail(MKB_ERR_INVALID, "state_out is null");
     CUDA_TRY(cudaSetDevice(s->device));
@@ -1807,6 +1870,7 @@ static int set_state_typed(mkb_sim* s, const void* state_in, int uniform) {
 }
 
 extern "C" int mkb_sim_set_state(mkb_sim* s, const void* state_in, int uniform) {
+    NvtxRange nvtx_("mkb_sim_set_state");
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
     if (!state_in) return fail(MKB_ERR_INVALID, "state_in is null");
     CUDA_TRY(cudaSetDevice(s->device));
@@ -1974,6 +2038,7 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
 }
 
 extern "C" int mkb_sim_rearm(mkb_sim* s, const mkb_run_config* r) {
+    NvtxRange nvtx_("mkb_sim_rearm");
     if (!s) return fail(MKB_ERR_STATE, "Simulation not initialized.");
     if (!r) return fail(MKB_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(s->device));

@@ -301,6 +301,29 @@ _PRELUDE = r"""
 #define MKB_ASM_EX2F(y, t) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t))
 #define MKB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
 #define MKB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
+// Streaming kernels: mbarrier + TMA (cp.async.bulk.tensor) and warp shuffles
+#define MKB_SMEM_ADDR(p) ((unsigned int)__cvta_generic_to_shared(p))
+#define MKB_MBAR_INIT(bar, count) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(MKB_SMEM_ADDR(bar)), "r"(count))
+#define MKB_MBAR_FENCE_INIT() asm volatile("fence.mbarrier_init.release.cluster;\n\tfence.proxy.async.shared::cta;" ::: "memory")
+// one arrival that announces `bytes`, then the 2-d box (bw x bh elements) whose
+// first element is (cx, cy) of the tensor `tmap` describes; cells outside the
+// tensor arrive as zeros
+#define MKB_TMA_LOAD_2D(dst, tmap, cx, cy, bar, bw, bh, bytes) do { \
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" \
+                 :: "r"(MKB_SMEM_ADDR(bar)), "r"(bytes) : "memory"); \
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" \
+                 :: "r"(MKB_SMEM_ADDR(dst)), "l"((unsigned long long)(tmap)), "r"(cx), "r"(cy), \
+                    "r"(MKB_SMEM_ADDR(bar)) : "memory"); \
+} while (0)
+#define MKB_MBAR_WAIT(bar, parity) do { \
+    unsigned int done_; \
+    do { \
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" \
+                     : "=r"(done_) : "r"(MKB_SMEM_ADDR(bar)), "r"(parity) : "memory"); \
+    } while (!done_); \
+} while (0)
+#define MKB_SHFL_UP(v, d) __shfl_up_sync(0xffffffffu, (v), (d))
+#define MKB_SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, (v), (d))
 #endif
 
 // Plane k of a cell, from the cell's address in plane 0. (Forms that were
@@ -907,6 +930,7 @@ class KernelSource:
         self.persistent = False
         self.gate_kernel = False        # a second kernel, mkb_gate_step
         self.kernel_flags = 0           # MKB_KERNEL_* of include/myokit_b200.h
+        self.stream_box = (0, 0)        # TMA box (cells, rows) of a streaming kernel
         self.gate_states = []
         self.cells_per_thread = 1
         self.rows_per_thread = 1
@@ -1668,8 +1692,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             q('%s(const __grid_constant__ MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
             q('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
             q('{')
-            q('    __shared__ alignas(128) Real tile[MKB_STAGES][MKB_BH][MKB_BW];')
-            q('    __shared__ alignas(8) unsigned long long full[MKB_STAGES];')
+            q('    // (each stage 128-byte aligned, as the TMA destination must be)')
+            q('    struct alignas(128) MkbStage { Real v[MKB_BH][MKB_BW]; };')
+            q('    __shared__ MkbStage tile[MKB_STAGES];')
+            q('    __shared__ unsigned long long full[MKB_STAGES];')
             q('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
             q('    const unsigned int tid = ty * MKB_BX + tx;')
             q('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
@@ -1693,7 +1719,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             q('            const unsigned int t = blockIdx.x + s * gridDim.x;')
             q('            if (t < n_tiles) {')
             q('                const unsigned int tyb = t / ntx, txb = t - tyb * ntx;')
-            q('                MKB_TMA_LOAD_2D(&tile[s][0][0], tmap, (int)(txb * MKB_TW) - MKB_PAD, (int)(tyb * MKB_TH) - 1,')
+            q('                MKB_TMA_LOAD_2D(&tile[s].v[0][0], tmap, (int)(txb * MKB_TW) - MKB_PAD, (int)(tyb * MKB_TH) - 1,')
             q('                                &full[s], MKB_BW, MKB_BH, (unsigned int)(MKB_BW * MKB_BH * sizeof(Real)));')
             q('            }')
             q('        }')
@@ -1731,7 +1757,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             q('    // this thread\'s patch, the rows above and below it, the cells left and right')
             q('    Real v_up[MKB_CPT], v_dn[MKB_CPT], v_lf[MKB_RPT], v_rt[MKB_RPT];')
             q('    {')
-            q('        const Real (*tl)[MKB_BW] = tile[stg];')
+            q('        const Real (*tl)[MKB_BW] = tile[stg].v;')
             q('        const unsigned int c0 = MKB_PAD + tx * MKB_CPT, r0 = ty * MKB_RPT + 1;')
             q('        mkb_vload<MKB_CPT>(v_up, &tl[r0 - 1][c0], true);')
             q('        mkb_vload<MKB_CPT>(v_dn, &tl[r0 + MKB_RPT][c0], true);')
@@ -1749,7 +1775,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             q('        const unsigned int tn = t + MKB_STAGES * gridDim.x;')
             q('        if (tn < n_tiles) {')
             q('            const unsigned int nyb = tn / ntx, nxb = tn - nyb * ntx;')
-            q('            MKB_TMA_LOAD_2D(&tile[stg][0][0], tmap, (int)(nxb * MKB_TW) - MKB_PAD, (int)(nyb * MKB_TH) - 1,')
+            q('            MKB_TMA_LOAD_2D(&tile[stg].v[0][0], tmap, (int)(nxb * MKB_TW) - MKB_PAD, (int)(nyb * MKB_TH) - 1,')
             q('                            &full[stg], MKB_BW, MKB_BH, (unsigned int)(MKB_BW * MKB_BH * sizeof(Real)));')
             q('        }')
             q('    }')
@@ -1888,11 +1914,18 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('    (void)ix; (void)cid;')
         if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
             q('    const Real vcc = vc[r][c];')
-            q('    // neighbours: registers inside the patch, shared memory on its rim')
-            q('    const Real vxm = (c > 0) ? vc[r][c > 0 ? c - 1 : 0] : col_r[tr][tx];')
-            q('    const Real vxp = (c < MKB_CPT - 1) ? vc[r][c < MKB_CPT - 1 ? c + 1 : 0] : col_l[tr][tx + 2];')
-            q('    const Real vym = (r > 0) ? vc[r > 0 ? r - 1 : 0][c] : row_b[ty][tx * MKB_CPT + c];')
-            q('    const Real vyp = (r < MKB_RPT - 1) ? vc[r < MKB_RPT - 1 ? r + 1 : 0][c] : row_t[ty + 2][tx * MKB_CPT + c];')
+            if stream:
+                q('    // neighbours: registers inside the patch, its rim from the tile / the warp')
+                q('    const Real vxm = (c > 0) ? vc[r][c > 0 ? c - 1 : 0] : v_lf[r];')
+                q('    const Real vxp = (c < MKB_CPT - 1) ? vc[r][c < MKB_CPT - 1 ? c + 1 : 0] : v_rt[r];')
+                q('    const Real vym = (r > 0) ? vc[r > 0 ? r - 1 : 0][c] : v_up[c];')
+                q('    const Real vyp = (r < MKB_RPT - 1) ? vc[r < MKB_RPT - 1 ? r + 1 : 0][c] : v_dn[c];')
+            else:
+                q('    // neighbours: registers inside the patch, shared memory on its rim')
+                q('    const Real vxm = (c > 0) ? vc[r][c > 0 ? c - 1 : 0] : col_r[tr][tx];')
+                q('    const Real vxp = (c < MKB_CPT - 1) ? vc[r][c < MKB_CPT - 1 ? c + 1 : 0] : col_l[tr][tx + 2];')
+                q('    const Real vym = (r > 0) ? vc[r > 0 ? r - 1 : 0][c] : row_b[ty][tx * MKB_CPT + c];')
+                q('    const Real vyp = (r < MKB_RPT - 1) ? vc[r < MKB_RPT - 1 ? r + 1 : 0][c] : row_t[ty + 2][tx * MKB_CPT + c];')
             q('    Real idiff;')
             if diffusion_mode == DIFF_HOMOGENEOUS:
                 q('    // openclsim.cl:401-434 (diff_step); nx >= MKB_CPT > 1 here. Only the')
@@ -1959,6 +1992,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 q('    mkb_vstore<MKB_CPT>(state + %dull * stride + cid0, N%d);'
                   % (var.index(), var.index()))
         q('    }   // rows of this thread')
+        if stream:
+            q('    }   // tiles of this thread block')
         q('}')
         q('')
         options = ['--fmad=true' if fmad else '--fmad=false']
@@ -1968,6 +2003,12 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                           len(fields), diffusion_mode, options)
         ks.cells_per_thread = cpt
         ks.rows_per_thread = rpt
+        if stream:
+            # MKB_KERNEL_STREAM | thread blocks per SM << 8; the TMA box
+            blocks_per_sm = int(min_blocks or 2)
+            ks.kernel_flags = 2 | (blocks_per_sm << 8)
+            pad = 4 if sp else 2
+            ks.stream_box = (bx * cpt + 2 * pad, by * rpt + 2)
         return ks
 
     # ------------------------------------------------------------------

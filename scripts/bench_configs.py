@@ -50,11 +50,13 @@ which = sys.argv[1:] or ['c1', 'c2', 'c4', 'c5']
 if 'c1' in which:
     report('C1 LR91 1-D 128 fp64', workloads.c1_cable(S, 128), 20000)
     report('C1-like LR91 1-D 16384 fp64', workloads.c1_cable(S, 16384), 5000)
-    if os.environ.get('MKB_TEST_EXPERIMENTAL'):
-        # prepared without GPU time left to measure it: all unlogged steps of a chunk in one launch
-        report('C1 LR91 1-D 128 fp64 persistent', workloads.c1_cable(S, 128), 20000, persistent=True)
-        report('C1-like LR91 1-D 1024 fp64 persistent', workloads.c1_cable(S, 1024), 20000, persistent=True)
-        report('C1-like LR91 1-D 1024 fp64', workloads.c1_cable(S, 1024), 20000)
+    # all unlogged steps of a schedule chunk in one launch (one thread block)
+    report('C1 LR91 1-D 128 fp64 persistent', workloads.c1_cable(S, 128), 20000, persistent=True)
+    report('C1 128 persistent + select', workloads.c1_cable(S, 128), 20000, persistent=True, select=True)
+    report('C1 128 persistent + select + estrin', workloads.c1_cable(S, 128), 20000, persistent=True, select=True, fast_exp='estrin')
+    report('C1 128 persistent + select + estrin + div_parallel', workloads.c1_cable(S, 128), 20000, persistent=True, select=True, fast_exp='estrin', div_cubic=False, div_parallel=True)
+    report('C1-like LR91 1-D 1024 fp64 persistent + select', workloads.c1_cable(S, 1024), 20000, persistent=True, select=True)
+    report('C1-like LR91 1-D 1024 fp64', workloads.c1_cable(S, 1024), 20000)
 if 'c2' in which:
     report('C2 LR91 512^2 fp32', workloads.c2_planar(S, 512), 5000)
     report('C2 LR91 512^2 fp32 b32x8', workloads.c2_planar(S, 512), 5000, block=(32, 8))
@@ -69,13 +71,24 @@ if 'c4' in which:
 if 'stencil' in which:
     for prec, name in ((myokit.SINGLE_PRECISION, 'fp32'), (myokit.DOUBLE_PRECISION, 'fp64')):
         rs = 4 if name == 'fp32' else 8
-        for opts in (dict(), dict(block=(128, 2))):
+        variants = [dict(stream=False), dict(stream=True), dict(stream=True, min_blocks=3),
+                    dict(stream=True, min_blocks=4), dict(stream=True, block=(32, 4)),
+                    dict(stream=True, block=(32, 4), min_blocks=4),
+                    dict(stream=True, block=(32, 8), rows_per_thread=2, min_blocks=4),
+                    dict(stream=True, block=(32, 16), rows_per_thread=2, min_blocks=2)]
+        if name == 'fp64':
+            variants += [dict(stream=True, cells_per_thread=4), dict(stream=True, cells_per_thread=4, min_blocks=3)]
+        for opts in variants:
             s = workloads.stencil_only(S, 8192, 4096, precision=prec)
             s.set_kernel_options(**opts)
-            info = s.benchmark_steps(50, warmup=5)
+            try:
+                info = s.benchmark_steps(50, warmup=5)
+            except Exception as e:
+                print('stencil-only %s %s failed: %s' % (name, opts, str(e)[:300]), flush=True)
+                continue
             ms = info['device_ms'] / info['steps']
             gbs = 2 * rs * info['cells'] / ms / 1e6
-            print('stencil-only 8192^2 %s %-22s %8.4f ms/step  %7.1f GB/s  (%.1f%% of 6392.8)' % (
+            print('stencil-only 8192x4096 %s %-60s %8.4f ms/step  %7.1f GB/s  (%.1f%% of 6392.8)' % (
                 name, opts, ms, gbs, 100 * gbs / 6392.8), flush=True)
     s = workloads.stencil_only(S, 8192, precision=myokit.SINGLE_PRECISION, hetero=True)
     info = s.benchmark_steps(50, warmup=5)

@@ -21,5 +21,9 @@ else:
 if os.environ.get('MKB_PROFILE_OPTS'):
     # kernel options of the variant to capture, e.g. "dict(div_cubic=True)"
     s.set_kernel_options(**eval(os.environ['MKB_PROFILE_OPTS']))
+if os.environ.get('MKB_PROFILE_KEYFILE'):
+    # which kernel the capture is of: bench.py trusts the profile only for this key
+    with open(os.environ['MKB_PROFILE_KEYFILE'], 'w') as f:
+        f.write(s.kernel_source().key())
 info = s.benchmark_steps(steps, warmup=3)
 print(name, info)

@@ -14,7 +14,7 @@ import sys
 from collections import Counter, OrderedDict
 
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G = os.path.join(R, 'gpurun_out')
+G = os.path.join(R, 'gpurun_out', os.environ.get('MKB_PROFILE_DIR', ''))
 P = os.path.join(R, 'profiles')
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
 
@@ -156,6 +156,24 @@ def main():
             scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}
             traffic = rd * scale[m['dram__bytes_read.sum'][1]] + wr * scale[m['dram__bytes_write.sum'][1]]
             md.append('| DRAM traffic per launch | %.3f GB |' % (traffic / 1e9))
+            kf = os.path.join(G, 'key_%s.txt' % w)
+            if w == 'c3' and os.path.isfile(kf):
+                # what bench.py reads instead of literals (roofline.traffic, fp64_pipe)
+                fp64 = sum(ops[k] for k in ('DFMA', 'DMUL', 'DADD', 'DSETP'))
+                prof = {
+                    'kernel_key': open(kf).read().strip(),
+                    'workload': title,
+                    'capture': 'ncu --set full --clock-control none, one launch (%s)' % tag,
+                    'instr_per_cell_step': per_warp,
+                    'fp64_instr_per_cell_step': fp64 / nwarps,
+                    'dram_bytes_per_launch': traffic,
+                    'duration_us_under_ncu': t_ms * 1e3,
+                    'registers': int(float(m['launch__registers_per_thread'][0])),
+                    'fp64_pipe_active_pct': float(m['sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'][0]),
+                    'issue_active_pct': float(m['smsp__issue_active.avg.pct_of_peak_sustained_active'][0]),
+                }
+                with open(os.path.join(P, 'c3_kernel_profile.json'), 'w') as f:
+                    json.dump(prof, f, indent=1)
             md.append('| DRAM GB/s under ncu | %.0f |' % (traffic / 1e9 / (t_ms * 1e-3)))
         except Exception:
             pass

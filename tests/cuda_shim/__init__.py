@@ -78,7 +78,7 @@ def schedule(sim, duration, log_interval):
 
 
 def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None,
-                reverse=False):
+                reverse=False, stream_blocks=3):
     """
     Runs ``duration`` on the host. Returns a dict: ``time`` (nt,), ``V``
     (nt, ncells) — V(t) at the logged steps —, ``idiff`` (nt, ncells),
@@ -94,6 +94,8 @@ def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None,
                    'mkb_gate_step' if getattr(src, 'gate_kernel', False) else None)
     lib.shim_set_thread_order(1 if reverse else 0)
     lib.shim_set_persistent(1 if getattr(src, 'persistent', False) else 0)
+    # streaming kernels: a persistent grid of a few blocks walks all tiles
+    lib.shim_set_stream_blocks(stream_blocks if (src.kernel_flags & 2) else 0)
     nx, ny = sim._nx, sim._ny
     if getattr(src, 'persistent', False):
         assert nx <= src.block[0] and ny <= src.block[1]

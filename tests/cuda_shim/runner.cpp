@@ -29,6 +29,7 @@ Fiber* g_cur = nullptr;
 int g_or_acc = 0, g_or_res = 0;
 int g_reverse = 0;
 int g_persistent = 0;
+int g_stream_blocks = 0;     // > 0: persistent-grid streaming kernel, this many blocks
 
 struct Launch {
     MkbGridArgs g;
@@ -118,6 +119,8 @@ extern "C" void shim_set_thread_order(int reverse) { g_reverse = reverse; }
 // persistent kernels: consecutive unlogged steps share one launch (as
 // sim_step_typed groups them); the run length rides in flags >> 8
 extern "C" void shim_set_persistent(int on) { g_persistent = on; }
+extern "C" void shim_set_stream_blocks(int n) { g_stream_blocks = n; }
+double shim_shfl_buf[1024];
 
 extern "C" int shim_run(
     int nx, int ny, int n_state, int i_vm, int n_inter, int n_field, int diffusion_mode,
@@ -196,10 +199,22 @@ extern "C" int shim_run(
     g.pace_x0 = px0; g.pace_x1 = px1; g.pace_y0 = py0; g.pace_y1 = py1;
 
     const unsigned long long cells_x = (unsigned long long)block_x * cpt, cells_y = (unsigned long long)block_y * rpt;
-    const unsigned int gbx = (unsigned int)((nx + cells_x - 1) / cells_x);
+    unsigned int gbx = (unsigned int)((nx + cells_x - 1) / cells_x);
     const unsigned long long by_blocks = (ny + cells_y - 1) / cells_y;
-    const unsigned int gby = (unsigned int)(by_blocks < 32768 ? by_blocks : 32768);
-    const unsigned int gbz = (unsigned int)((by_blocks + gby - 1) / gby);
+    unsigned int gby = (unsigned int)(by_blocks < 32768 ? by_blocks : 32768);
+    unsigned int gbz = (unsigned int)((by_blocks + gby - 1) / gby);
+    if (g_stream_blocks > 0) {
+        // a fixed number of blocks walks all tiles; stand-in tensor maps of the two V planes
+        gbx = (unsigned int)g_stream_blocks; gby = gbz = 1;
+        const unsigned long long planes[2] = {(unsigned long long)(uintptr_t)(state.data() + (size_t)i_vm * stride),
+                                              (unsigned long long)(uintptr_t)v_alt.data()};
+        for (int k = 0; k < 2; k++) {
+            g.tmap[k][0] = planes[k];
+            g.tmap[k][1] = nx;
+            g.tmap[k][2] = ny;
+            g.tmap[k][3] = sizeof(Real);
+        }
+    }
     gridDim.x = gbx; gridDim.y = gby; gridDim.z = gbz;
     blockDim.x = block_x; blockDim.y = block_y; blockDim.z = 1;
 

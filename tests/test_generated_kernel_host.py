@@ -668,3 +668,42 @@ def test_split_gates_with_row_slabs():
     assert out['halo_error'] == 0
     assert np.array_equal(out['V'], one['V'])
     assert np.array_equal(out['state'], one['state'])
+
+
+@pytest.mark.parametrize('precision,nx,ny', [(SP, 140, 37), (DP, 70, 41)])
+@pytest.mark.parametrize('hetero', [False, True])
+def test_streaming_kernel_tma_tiles_equal_oracle(precision, nx, ny, hetero):
+    # kernelgen stream=True: persistent blocks walk tiles; the V tile + halo
+    # arrives by TMA (here: the shim's synchronous box copy with zero fill),
+    # left / right neighbours by warp shuffle. Ragged grids, 3 and 5 resident
+    # blocks, both thread orders: the bits of the oracle.
+    from myokit_b200 import workloads
+
+    def make(cls):
+        return workloads.stencil_only(cls, nx, ny, precision=precision, hetero=hetero)
+    a = make(myokit_b200.SimulationCUDA)
+    a.set_kernel_options(stream=True, fmad=False)
+    src = a.kernel_source()
+    assert src.kernel_flags & 2 and src.block == (32, 8)
+    assert 'MKB_TMA_LOAD_2D' in src.code and '__grid_constant__' in src.code
+    got = cuda_shim.run_on_host(a, 2.5, log_interval=0.5)
+    rev = cuda_shim.run_on_host(a, 2.5, log_interval=0.5, reverse=True, stream_blocks=5)
+    want, wstate = oracle_fields(make(OracleSimulation), 2.5, 0.5, nx, ny,
+                                 ['membrane.V', 'membrane.i_diff'])
+    assert want['membrane.V'].max() > -70
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(rev['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+
+
+def test_streaming_kernel_falls_back_where_tma_cannot_describe_the_grid():
+    from myokit_b200 import workloads
+    # rows that are not 16-byte multiples, 1-d cables: the register-patch path
+    for nx, ny in ((141, 37), (64, 1)):
+        s = workloads.stencil_only(myokit_b200.SimulationCUDA, nx, ny if ny > 1 else None,
+                                   precision=SP) if ny > 1 else None
+        if s is None:
+            continue
+        s.set_kernel_options(stream=True)
+        assert not (s.kernel_source().kernel_flags & 2)

@@ -670,3 +670,65 @@ def test_full_size_blocked_rows_do_not_couple():
     ol, _ = o.run(3, log=['membrane.V'], log_interval=1)
     ref = np.array([ol['%d.membrane.V' % x] for x in range(nx)]).T
     assert np.max(np.abs(V[:, 513, :] - ref)) <= TOL_V
+
+
+@pytest.mark.parametrize('precision,hetero', [(SP, False), (SP, True), (DP, False), (DP, True)])
+def test_streaming_tma_kernel_equals_vector_path_and_oracle(precision, hetero):
+    # kernelgen stream=True: persistent blocks, V tile + halo by TMA
+    # (cp.async.bulk.tensor.2d) through a two-stage mbarrier ring; the same
+    # arithmetic as the register-patch path, so the same bits
+    nx, ny = 264, 77        # ragged in both directions (tiles of 128 x 32 / 64 x 32)
+
+    def make(cls, **opts):
+        s = workloads.stencil_only(cls, nx, ny, precision=precision, hetero=hetero)
+        if opts:
+            s.set_kernel_options(**opts)
+        return s
+    a = make(myokit_b200.SimulationCUDA, stream=True, fmad=False)
+    assert a.kernel_source().kernel_flags & 2
+    b = make(myokit_b200.SimulationCUDA, stream=False, fmad=False)
+    ta, fa = a.run_fields(6, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    tb, fb = b.run_fields(6, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    assert fb['membrane.V'].max() > -70         # the paced edge moved
+    for k in fb:
+        assert np.array_equal(fa[k], fb[k]), k
+    assert np.array_equal(a.state_array(), b.state_array())
+    o = make(OracleSimulation)
+    ol, ostate = o.run(6, log=['engine.time', '5.40.membrane.V', '263.76.membrane.V'],
+                       log_interval=0.5)
+    assert np.array_equal(np.asarray(ol['5.40.membrane.V'], dtype=fa['membrane.V'].dtype),
+                          fa['membrane.V'][:, 40, 5])
+    assert np.array_equal(np.asarray(ostate), a.state_array())
+    # a second run continues on the resident state (graphs, both V planes)
+    ta, fa = a.run_fields(3, ['membrane.V'], log_interval=0.5)
+    tb, fb = b.run_fields(3, ['membrane.V'], log_interval=0.5)
+    assert np.array_equal(fa['membrane.V'], fb['membrane.V'])
+
+
+def test_native_maths_fp32_stays_within_the_activation_time_bar():
+    # native_maths=True (openclsim.py:149-151: native_exp & co, here __expf,
+    # __logf, __fdividef, __powf): no accuracy contract in the reference; the
+    # planar wave must still arrive within one dt of the exact-maths oracle.
+    nx, ny, dt = 96, 24, 0.005
+    keys = ['%d.12.membrane.V' % x for x in range(nx)]
+    logspec = ['engine.time'] + keys
+    m, _ = example()
+    p = myokit.pacing.blocktrain(**PULSE)
+    a = myokit_b200.SimulationCUDA(m, p, ncells=(nx, ny), precision=SP,
+                                   native_maths=True)
+    assert '__expf' in a.kernel_source().code
+    b = OracleSimulation(m, p, ncells=(nx, ny), precision=SP)
+    res = []
+    for s in (a, b):
+        s.set_conductance(10, 10)
+        s.set_paced_cells(nx=5, ny=ny, x=0, y=0)
+        s.set_step_size(dt)
+        r = s.run(22, log=logspec, log_interval=dt)
+        r = r[0] if isinstance(r, tuple) else r
+        res.append(dict((k, np.asarray(v, dtype=np.float64)) for k, v in r.items()))
+    la, lb = res
+    ta = activation_times(la, keys, la['engine.time'])
+    tb = activation_times(lb, keys, lb['engine.time'])
+    assert not np.any(np.isnan(tb))
+    assert np.max(np.abs(ta - tb)) <= dt * 1.0001, np.max(np.abs(ta - tb))
+    assert max_abs_diff(la, lb, keys) < 2.0     # mV, on the upstroke
