@@ -157,9 +157,9 @@ def cpu_baseline(grid, kernel, budget_s=15.0):
     steps = int(max(8, min(2000, budget_s / max(per_step, 1e-6))))
     s = make()
     s.run(steps * 0.005, log=['engine.time'], nthreads=cores)
-    # the native call only: this repo's Python wrapper around the oracle is
-    # not the reference's overhead
-    dt = s.last_run_seconds
+    # the native time-step loop only: this repo's Python wrapper around the
+    # oracle, and its set-up copies, are not the reference's per-step path
+    dt = s.last_loop_seconds
     n_steps = s.last_steps
     value = grid * grid * n_steps / dt
     sample = ('%dx%d crop of the workload (same seeds), %d time steps, %.1f s'
@@ -192,7 +192,7 @@ def run_reference(args, rank, world):
     s.run(max(args.warmup, args.steps, 50) * 0.005, log=['engine.time'],
           nthreads=cores)
     s.run(args.steps * 0.005, log=['engine.time'], nthreads=cores)
-    dt = s.last_run_seconds      # the native call (host loop + kernels) only
+    dt = s.last_loop_seconds     # the native time-step loop (host loop + kernels)
     n_steps = s.last_steps
     value = grid * grid * n_steps / dt
     sample = ('%dx%d crop of the 2048x2048 workload (same seeds), %d time '

@@ -577,6 +577,19 @@ static int grid_for(u64 n) {
     return (int)std::min<u64>(std::max<u64>(b, 1), 148 * 16);
 }
 
+// Host -> device on the simulation's own stream, complete on return. (Not
+// cudaMemcpy: from pageable memory that call may return while the DMA of the
+// staged copy is still in flight, and only the legacy default stream waits for
+// it — the simulation's streams are non-blocking, so a kernel launched on
+// them next could read the destination too early. Found as garbage
+// conductances in a 264 x 77 single-precision run; copies of 64 KiB or less
+// are inline, which is why small grids never showed it.)
+static cudaError_t h2d_sync(mkb_sim* s, void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    return e;
+}
+
 // Uploads a host array in the reference's cell-major layout into SoA planes:
 // 64 MiB chunks through two device staging buffers on the launching stream,
 // one synchronisation at the end. From pinned host memory (mkb_host_alloc) the
@@ -678,12 +691,12 @@ template <typename TH, typename TR>
 static int upload_convert(mkb_sim* s, const void* host, u64 count, TR* d) {
     if (count == 0) return MKB_OK;
     if (sizeof(TH) == sizeof(TR)) {
-        CUDA_TRY(cudaMemcpy(d, host, count * sizeof(TR), cudaMemcpyHostToDevice));
+        CUDA_TRY(h2d_sync(s, d, host, count * sizeof(TR)));
         return MKB_OK;
     }
     TH* stage = nullptr;
     CUDA_TRY(cudaMalloc(&stage, count * sizeof(TH)));
-    cudaError_t e = cudaMemcpy(stage, host, count * sizeof(TH), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpyAsync(stage, host, count * sizeof(TH), cudaMemcpyHostToDevice, s->stream);
     if (e == cudaSuccess) {
         k_convert<TH, TR><<<grid_for(count), 256, 0, s->stream>>>(stage, d, count);
         s->launches++;
@@ -795,10 +808,9 @@ static int sim_init_typed(mkb_sim* s, const mkb_sim_config* c) {
         CUDA_TRY(cudaMalloc(&s->d_csr_row, (s->n + 1) * sizeof(u64)));
         CUDA_TRY(cudaMalloc(&s->d_csr_col, (2 * ne + 1) * sizeof(unsigned int)));
         CUDA_TRY(cudaMalloc(&s->d_csr_g, (2 * ne + 1) * sizeof(TR)));
-        CUDA_TRY(cudaMemcpy(s->d_csr_row, row.data(), (s->n + 1) * sizeof(u64), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(s->d_csr_col, col.data(), (2 * ne + 1) * sizeof(unsigned int),
-                            cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(s->d_csr_g, g.data(), (2 * ne + 1) * sizeof(TR), cudaMemcpyHostToDevice));
+        CUDA_TRY(h2d_sync(s, s->d_csr_row, row.data(), (s->n + 1) * sizeof(u64)));
+        CUDA_TRY(h2d_sync(s, s->d_csr_col, col.data(), (2 * ne + 1) * sizeof(unsigned int)));
+        CUDA_TRY(h2d_sync(s, s->d_csr_g, g.data(), (2 * ne + 1) * sizeof(TR)));
     }
     return MKB_OK;
 }
@@ -1199,7 +1211,7 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
                 if (cid >= cell0 && cid - cell0 < s->n) mask[cid - cell0] = 1;
             }
             INIT_CUDA(cudaMalloc(&s->d_mask, s->n));
-            INIT_CUDA(cudaMemcpy(s->d_mask, mask.data(), s->n, cudaMemcpyHostToDevice));
+            INIT_CUDA(h2d_sync(s, s->d_mask, mask.data(), s->n));
         }
     }
 
@@ -2003,11 +2015,11 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
         }
         const size_t np = flag_ptrs.size();
         CUDA_TRY(cudaMalloc(&s->d_peer_flags, np * sizeof(unsigned int*)));
-        CUDA_TRY(cudaMemcpy(s->d_peer_flags, flag_ptrs.data(), np * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+        CUDA_TRY(h2d_sync(s, s->d_peer_flags, flag_ptrs.data(), np * sizeof(unsigned int*)));
         CUDA_TRY(cudaMalloc(&s->d_peer_base, np * sizeof(void*)));
-        CUDA_TRY(cudaMemcpy(s->d_peer_base, bases.data(), np * sizeof(void*), cudaMemcpyHostToDevice));
+        CUDA_TRY(h2d_sync(s, s->d_peer_base, bases.data(), np * sizeof(void*)));
         CUDA_TRY(cudaMalloc(&s->d_peer_n_ghost, np * sizeof(u64)));
-        CUDA_TRY(cudaMemcpy(s->d_peer_n_ghost, counts.data(), np * sizeof(u64), cudaMemcpyHostToDevice));
+        CUDA_TRY(h2d_sync(s, s->d_peer_n_ghost, counts.data(), np * sizeof(u64)));
         CUDA_TRY(cudaMalloc(&s->d_push_done, sizeof(unsigned int)));
         CUDA_TRY(cudaMemset(s->d_push_done, 0, sizeof(unsigned int)));
         s->n_export = exp_src.size();
@@ -2015,9 +2027,9 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
             CUDA_TRY(cudaMalloc(&s->d_exp_src, s->n_export * sizeof(u64)));
             CUDA_TRY(cudaMalloc(&s->d_exp_slot, s->n_export * sizeof(u64)));
             CUDA_TRY(cudaMalloc(&s->d_exp_peer, s->n_export * sizeof(unsigned int)));
-            CUDA_TRY(cudaMemcpy(s->d_exp_src, exp_src.data(), s->n_export * sizeof(u64), cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMemcpy(s->d_exp_slot, exp_slot.data(), s->n_export * sizeof(u64), cudaMemcpyHostToDevice));
-            CUDA_TRY(cudaMemcpy(s->d_exp_peer, exp_peer.data(), s->n_export * sizeof(unsigned int), cudaMemcpyHostToDevice));
+            CUDA_TRY(h2d_sync(s, s->d_exp_src, exp_src.data(), s->n_export * sizeof(u64)));
+            CUDA_TRY(h2d_sync(s, s->d_exp_slot, exp_slot.data(), s->n_export * sizeof(u64)));
+            CUDA_TRY(h2d_sync(s, s->d_exp_peer, exp_peer.data(), s->n_export * sizeof(unsigned int)));
         }
     }
     s->n_import = n_import;
@@ -2026,7 +2038,7 @@ extern "C" int mkb_sim_ghost_connect(mkb_sim* s, uint32_t n_flags, uint32_t n_pe
             if (import_flags[k] >= n_flags) return fail(MKB_ERR_INVALID, "import flag out of range");
         }
         CUDA_TRY(cudaMalloc(&s->d_import, n_import * sizeof(unsigned int)));
-        CUDA_TRY(cudaMemcpy(s->d_import, import_flags, n_import * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        CUDA_TRY(h2d_sync(s, s->d_import, import_flags, n_import * sizeof(unsigned int)));
         // the step kernel itself waits for these flags (no separate launch)
         s->grid.ghost_flags = (const unsigned int*)(s->d_xchg + ghost_flags_offset(s->n_ghost, s->rs));
         s->grid.ghost_import = s->d_import;

@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -265,6 +266,18 @@ int oracle_real_size(void) { return (int)sizeof(Real); }
  * log_out: [max_rows * n_log] doubles.
  * Returns 0, or a negative pacing error flag, or 1 if log_out overflowed.
  */
+/* Wall-clock seconds the last oracle_run spent in its time-step loop
+ * (sim_step's loop, openclsim.c:1051-1178), without set-up and state copies:
+ * what bench.py's CPU arms report, so that a 20-step call and a 900-step call
+ * measure the same thing. */
+static double g_loop_seconds = 0;
+double oracle_loop_seconds(void) { return g_loop_seconds; }
+static double o_now(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 int oracle_run(
     size_t nx, size_t ny, int diffusion_mode,
     double gx_in, double gy_in,
@@ -339,6 +352,7 @@ int oracle_run(
     inext_log = 0;
     tnext_log = tmin;
 
+    const double t_loop0 = o_now();
     while (1) {
         int logging_condition, intermediary_step = 0;
         long ic;
@@ -459,6 +473,7 @@ int oracle_run(
         /* openclsim.c:1162 */
         if (engine_time >= tmax || halt) break;
     }
+    g_loop_seconds = o_now() - t_loop0;
 
     /* Final state: openclsim.c:1185-1190 */
     for (i = 0; i < n * N_STATE; i++) state_io[i] = (double)state[i];

@@ -179,6 +179,7 @@ class OracleSimulation:
             self._model.initial_values(True), dtype=np.float64), self._n)
         self.last_steps = 0
         self.last_run_seconds = 0.0     # wall clock of the native run call
+        self.last_loop_seconds = 0.0    # ... of its time-step loop alone
         self.last_halted = False
 
     # -- setters (subset of openclsim.py:1286-1715) --------------------------
@@ -441,6 +442,11 @@ class OracleSimulation:
             ctypes.byref(halted), ctypes.byref(tfinal),
             ctypes.c_int(nthreads))
         self.last_run_seconds = time.perf_counter() - t_call
+        try:
+            lib.oracle_loop_seconds.restype = ctypes.c_double
+            self.last_loop_seconds = float(lib.oracle_loop_seconds())
+        except AttributeError:      # a library built before the timer existed
+            self.last_loop_seconds = self.last_run_seconds
         if rc < 0:
             raise RuntimeError('Oracle pacing error %d' % rc)
         if rc > 0:

@@ -684,7 +684,7 @@ def test_streaming_kernel_tma_tiles_equal_oracle(precision, nx, ny, hetero):
     a = make(myokit_b200.SimulationCUDA)
     a.set_kernel_options(stream=True, fmad=False)
     src = a.kernel_source()
-    assert src.kernel_flags & 2 and src.block == (32, 8)
+    assert src.kernel_flags & 2 and src.block == ((32, 4) if precision == SP else (32, 16))
     assert 'MKB_TMA_LOAD_2D' in src.code and '__grid_constant__' in src.code
     got = cuda_shim.run_on_host(a, 2.5, log_interval=0.5)
     rev = cuda_shim.run_on_host(a, 2.5, log_interval=0.5, reverse=True, stream_blocks=5)
