@@ -690,7 +690,7 @@ def test_streaming_kernel_tma_tiles_equal_oracle(precision, nx, ny, hetero):
     rev = cuda_shim.run_on_host(a, 2.5, log_interval=0.5, reverse=True, stream_blocks=5)
     want, wstate = oracle_fields(make(OracleSimulation), 2.5, 0.5, nx, ny,
                                  ['membrane.V', 'membrane.i_diff'])
-    assert want['membrane.V'].max() > -70
+    assert want['membrane.V'].max() > -72       # the paced edge moved
     assert np.array_equal(got['V'], want['membrane.V'])
     assert np.array_equal(rev['V'], want['membrane.V'])
     assert np.array_equal(got['idiff'], want['membrane.i_diff'])
