@@ -169,6 +169,9 @@ typedef struct mkb_sim_config {
                                    min(tiles, sm_count * blocks_per_sm) thread blocks walks
                                    the tiles of the grid; the V tile + halo arrives by TMA
                                    through the descriptors in MkbGridArgs::tmap */
+#define MKB_KERNEL_OVERLAP    4 /* consecutive launches of kernel_name overlap: launched with
+                                   programmatic stream serialization, ordered by the
+                                   per-block step counters in MkbGridArgs::tile_done */
 #define MKB_KERNEL_FLAG_SHIFT_BLOCKS 8   /* bits 8..15: thread blocks per SM (stream) */
 
 /* A run on the state that is already resident on the device (mkb_sim_rearm):

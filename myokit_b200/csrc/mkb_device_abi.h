@@ -103,6 +103,11 @@ struct MkbGridArgs {
     const void* junction_v1;
     double jg;
     unsigned long long jx, jy0, jn, joff, jstride;
+    /* Kernels whose consecutive steps overlap (kernelgen overlap=True): one
+     * counter per thread block of the launch grid, [row block][column block]:
+     * the last step that block has completed (stores released). Zeroed when
+     * a run starts counting its steps from 1. Null otherwise. */
+    unsigned int* tile_done;
     /* Streaming kernels (kernelgen stream=True): TMA descriptors
      * (cuTensorMapEncodeTiled) of the two membrane-potential planes as 2-d
      * tensors [ny][nx] with the box the kernel was generated for: tmap[0] the

@@ -158,9 +158,12 @@ template <typename TR>
 __global__ void k_push_ghosts(const TR* __restrict__ v, const u64* __restrict__ src,
                               const u64* __restrict__ slot, const unsigned int* __restrict__ peer,
                               u64 n, void* const* peer_base, const u64* __restrict__ peer_n_ghost,
-                              unsigned int* const* flags, unsigned int n_peers, unsigned int step,
-                              unsigned int* done) {
+                              unsigned int* const* flags, unsigned int n_peers, unsigned int step_arg,
+                              const MkbStepParams* __restrict__ sp, unsigned int* done) {
     __shared__ bool last;
+    // the step this push delivers for: the one after the step record `sp` (so
+    // that the launch can sit in a replayed CUDA graph), or `step_arg`
+    const unsigned int step = sp ? sp->step + 1u : step_arg;
     const u64 plane = step % 3u;
     u64 e = blockIdx.x * (u64)blockDim.x + threadIdx.x;
     for (; e < n; e += (u64)gridDim.x * blockDim.x) {
@@ -450,6 +453,9 @@ struct mkb_sim {
     bool halo_live = false;             // exchange block consistent with step_index (see arm_run)
     bool halo_connected = false;        // halo_connect / ghost_connect + first seed done
     bool state_replaced = false;        // mkb_sim_set_state since the last run
+    bool overlap = false;               // MKB_KERNEL_OVERLAP: step kernels launched with PDL
+    unsigned int* d_tile_done = nullptr;
+    size_t n_tiles = 0;
 
     // partitioned connection graphs: ghost cells (multi-GPU)
     u64 n_ghost = 0;
@@ -557,6 +563,7 @@ static void sim_destroy(mkb_sim* s) {
     if (s->ev_rows) cudaEventDestroy(s->ev_rows);
     if (s->ev_t0) cudaEventDestroy(s->ev_t0);
     if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    if (s->d_tile_done) cudaFree(s->d_tile_done);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->side) cudaStreamDestroy(s->side);
     if (s->lib) cudaLibraryUnload(s->lib);
@@ -1029,7 +1036,13 @@ static int arm_run(mkb_sim* s, const mkb_run_config* r) {
     // on every neighbour (the last step kernel delivered them), so a re-armed
     // run continues the exchange protocol where it stopped — no flag reset,
     // no barrier, no re-seed.
-    if (!s->halo_live) s->step_index = 0;
+    if (!s->halo_live) {
+        s->step_index = 0;
+        // (stream order: after everything of the previous run, before the first step)
+        if (s->d_tile_done) {
+            CUDA_TRY(cudaMemsetAsync(s->d_tile_done, 0, s->n_tiles * sizeof(unsigned int), s->stream));
+        }
+    }
     s->issued = 0;
     s->throttle_count = 0;
     s->ring_chunk = 0;
@@ -1339,6 +1352,18 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
         }
     }
 
+    s->overlap = (c->kernel_flags & MKB_KERNEL_OVERLAP) != 0;
+    if (s->overlap) {
+        if (s->kern2 || s->persistent || (c->kernel_flags & MKB_KERNEL_STREAM)) {
+            sim_destroy(s);
+            return fail(MKB_ERR_INVALID, "Overlapping steps need a single ordinary step kernel.");
+        }
+        s->n_tiles = (size_t)s->launch_grid.x * s->launch_grid.y * s->launch_grid.z;
+        INIT_CUDA(cudaMalloc(&s->d_tile_done, s->n_tiles * sizeof(unsigned int)));
+        INIT_CUDA(cudaMemsetAsync(s->d_tile_done, 0, s->n_tiles * sizeof(unsigned int), s->stream));
+        g.tile_done = s->d_tile_done;
+    }
+
     // Logging, pacing and schedule of the first run
     {
         mkb_run_config r;
@@ -1467,17 +1492,40 @@ static size_t ghost_flags_offset(u64 n_ghost, size_t rs) {
 // Pushes V(t) of the exported cells into the peers' slot for `step` and raises
 // the flags to `step` (seeding uses step = 1 with the current V plane).
 template <typename TR>
-static int ghost_push(mkb_sim* s, const TR* v, unsigned int step) {
+static int ghost_push(mkb_sim* s, const TR* v, unsigned int step, const MkbStepParams* sp = nullptr) {
     if (s->gpeers.empty()) return MKB_OK;
     u64 blocks = (s->n_export + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 4) blocks = 148 * 4;
     k_push_ghosts<TR><<<(unsigned int)blocks, 256, 0, s->stream>>>(
         v, s->d_exp_src, s->d_exp_slot, s->d_exp_peer, s->n_export, s->d_peer_base,
-        s->d_peer_n_ghost, s->d_peer_flags, (unsigned int)s->gpeers.size(), step, s->d_push_done);
+        s->d_peer_n_ghost, s->d_peer_flags, (unsigned int)s->gpeers.size(), step, sp, s->d_push_done);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return MKB_OK;
+}
+
+// One step-kernel launch. Overlapping kernels carry the programmatic-stream-
+// serialization attribute: the launch may begin while the previous kernel in
+// the stream is still running (once all its blocks have started); the blocks
+// order themselves through MkbGridArgs::tile_done. Captured into a graph the
+// attribute becomes a programmatic dependency edge.
+static cudaError_t launch_step(mkb_sim* s, cudaKernel_t kern, void** args) {
+    if (!s->overlap) {
+        return cudaLaunchKernel((const void*)kern, s->launch_grid, s->launch_block, args, 0, s->stream);
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = s->launch_grid;
+    cfg.blockDim = s->launch_block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, (const void*)kern, args);
 }
 
 // Builds (once per slot and entry parity) the graph
@@ -1504,9 +1552,15 @@ static int graph_get(mkb_sim* s, int slot, int parity, cudaGraphExec_t* out) {
             TR* v_out = plane_ptr<TR>(s, par ? vm_plane : s->plane_alt_v);
             const MkbStepParams* sp = gs.d_params + j;
             void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
-            e = cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0, s->stream);
+            e = launch_step(s, s->kern, args);
             if (e == cudaSuccess && s->kern2) {
                 e = cudaLaunchKernel((const void*)s->kern2, s->launch_grid, s->launch_block, args, 0, s->stream);
+            }
+            if (e == cudaSuccess && !s->gpeers.empty()) {
+                // partitioned graphs: V(t + dt) of the exported cells -> the peers'
+                // slot for the next step (the push reads its step number from sp)
+                if (ghost_push<TR>(s, v_out, 0u, sp)) e = cudaErrorUnknown;
+                s->launches--;      // counted when the graph is launched
             }
             par ^= 1;
         }
@@ -1591,7 +1645,7 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
         s->ring_chunk++;
 
         for (size_t i = 0; i < s->recs.size(); i++) {
-            if (s->use_graphs && !s->ghosts_connected && !s->partner && !s->persistent &&
+            if (s->use_graphs && !s->partner && !s->persistent &&
                 i + kGraphSteps <= s->recs.size()) {
                 bool plain = true;
                 for (int j = 0; j < kGraphSteps && plain; j++) plain = !s->recs[i + j].logging;
@@ -1612,7 +1666,7 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
                     gs.pending = true;
                     s->graph_seq++;
                     s->graph_launches++;
-                    s->launches += (s->kern2 ? 2 : 1) * kGraphSteps;
+                    s->launches += ((s->kern2 ? 2 : 1) + (s->gpeers.empty() ? 0 : 1)) * kGraphSteps;
                     s->steps += kGraphSteps;
                     s->issued += kGraphSteps;
                     i += kGraphSteps - 1;       // parity unchanged: kGraphSteps is even
@@ -1664,8 +1718,7 @@ static int sim_step_typed(mkb_sim* s, bool drain = true) {
             // fused diffusion + cell step: states -> t + dt (openclsim.c:1066-1096)
             const MkbStepParams* sp = dring + i;
             void* args[] = {(void*)&s->grid, (void*)&sp, (void*)&v_in, (void*)&v_out};
-            CUDA_TRY(cudaLaunchKernel((const void*)s->kern, s->launch_grid, s->launch_block, args, 0,
-                                      s->stream));
+            CUDA_TRY(launch_step(s, s->kern, args));
             if (s->kern2) {
                 // gates: reads V(t) (v_in) and the states only it updates
                 CUDA_TRY(cudaLaunchKernel((const void*)s->kern2, s->launch_grid, s->launch_block, args, 0,

@@ -326,6 +326,49 @@ _PRELUDE = r"""
 #define MKB_SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, (v), (d))
 #endif
 
+// Overlapping consecutive steps (option overlap). A step kernel normally starts
+// when the previous one has drained: every SM then idles through the tail of
+// the last wave — about half a thread's latency (27 us for the 48-state
+// model) per step, 2 % of a 2048^2 step but 12 % of a 256-row slab's. Kernels
+// generated with MKB_OVERLAP_STEPS are launched with programmatic stream
+// serialization: each block lets the next kernel start launching as soon as
+// it runs itself (griddepcontrol.launch_dependents), and orders itself
+// against the previous step by data instead of by kernel boundary: it waits
+// until its own tile and its four neighbours have published step - 1 in
+// MkbGridArgs::tile_done (their V(t) rows are then written, and they have
+// finished reading the V plane this block is about to overwrite), and
+// publishes `step` behind a device-scope release when its stores are done.
+// All earlier blocks are resident or finished whenever a block waits (the
+// next grid only launches once every block of this one has started), so the
+// waits cannot deadlock. Loads of data another step wrote bypass L1
+// (ld.global.cg): the previous kernel may still be running on this SM.
+#ifndef MKB_OVERLAP_STEPS
+#define MKB_OVERLAP_STEPS 0
+#endif
+#if MKB_OVERLAP_STEPS
+#define MKB_LD(p) __ldcg(p)
+#else
+#define MKB_LD(p) (*(p))
+#endif
+#ifndef MKB_PDL_TRIGGER
+#define MKB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+__device__ __forceinline__ void mkb_wait_tile(const unsigned int* flag, unsigned int want, unsigned int* error) {
+    unsigned int seen, spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen >= want) break;
+        __nanosleep(spins < 64 ? 20 : 100);
+        if (++spins > 20000000u) {      // ~2 s: surface as an error, never hang the GPU
+            if (error) atomicExch(error, 2u);
+            break;
+        }
+    }
+}
+__device__ __forceinline__ void mkb_publish_tile(unsigned int* flag, unsigned int step) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(step) : "memory");
+}
+#endif
+
 // Plane k of a cell, from the cell's address in plane 0. (Forms that were
 // tried to get below two integer instructions per access and did not: a 32-bit
 // stride, which the compiler turns into the same chains of 64-bit additions,
@@ -955,7 +998,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              const_div=True, slab_lean=False, div_parallel=False,
              junction=None, persistent=False, split_gates=False,
              div_cubic=False, prefetch=None, debug_mem=None,
-             fast_libm=False, select=False, exp_scale='mul', stream=False):
+             fast_libm=False, select=False, exp_scale='mul', stream=False,
+             overlap=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -1070,7 +1114,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         w._fast_libm = bool(fast_libm) and not sp
         w._select = select if select == 'cheap' else bool(select)
     w._pow_multiply = bool(pow_multiply)
-    math_defines = '#define MKB_EXP_SCALE_ADD %d\n#define MKB_FAST_LIBM %d\n#define MKB_EXP_FN %s' % (
+    math_defines = '#define MKB_OVERLAP_STEPS @OVERLAP@\n#define MKB_EXP_SCALE_ADD %d\n#define MKB_FAST_LIBM %d\n#define MKB_EXP_FN %s' % (
         1 if exp_scale == 'add' else 0,
         1 if (fast_libm and not sp and not native_maths) else 0,
         getattr(w, '_fast_exp', None) if (getattr(w, '_fast_exp', None)
@@ -1101,6 +1145,18 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     # grids whose rows are 16-byte multiples, one warp across a tile row
     stream = bool(stream) and cpt > 1 and diffusion_mode in (
         DIFF_HOMOGENEOUS, DIFF_FIELD) and bx == 32 and not stab
+
+    # Consecutive steps overlap (see MKB_OVERLAP in the prelude): scalar path
+    # on regular grids only
+    overlap = bool(overlap) and cpt == 1 and diffusion_mode in (
+        DIFF_HOMOGENEOUS, DIFF_FIELD) and not (junction or persistent
+                                               or split_gates or debug_mem)
+
+    # Consecutive steps overlap (see MKB_OVERLAP_STEPS in the prelude): scalar
+    # path on regular grids only
+    overlap = bool(overlap) and cpt == 1 and diffusion_mode in (
+        DIFF_HOMOGENEOUS, DIFF_FIELD) and not (junction or persistent
+                                               or split_gates or debug_mem)
 
     if junction not in (None, 'fiber', 'tissue'):
         raise ValueError('junction must be None, "fiber" or "tissue".')
@@ -1213,7 +1269,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         k = var.index()
         if k == i_vm:
             return '    const Real %s = vc;' % v(var)
-        src = 'MKB_AT(state_c, %d)' % k
+        src = 'MKB_LD(&MKB_AT(state_c, %d))' % k
         if debug_mem:
             src = 'MKB_AT(state + (cid & 255ull), %d)' % k
         if guarded:
@@ -1500,7 +1556,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
         q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
         q('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
-        q(math_defines)
+        q(math_defines.replace('@OVERLAP@', '0'))
         q(_PRELUDE)
         if pooled and w._pool:
             q('__constant__ double mkb_k[%d] = {' % len(w._pool))
@@ -1665,7 +1721,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         q('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
         q('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
         q('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
-        q(math_defines)
+        q(math_defines.replace('@OVERLAP@', '0'))
         q(_PRELUDE)
         q(_VECTOR_PRELUDE)
         if pooled and w._pool:
@@ -2029,7 +2085,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('#define MKB_DIV_INT_CHECK %d' % (1 if div_int_check else 0))
     p('#define MKB_DIV_PARALLEL %d' % (1 if div_parallel else 0))
     p('#define MKB_DIV_CUBIC %d' % (1 if div_cubic else 0))
-    p(math_defines)
+    p(math_defines.replace('@OVERLAP@', '1' if overlap else '0'))
     p(_PRELUDE)
     if pooled and w._pool:
         p('// Model constants (double precision), in order of first use')
@@ -2075,6 +2131,22 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    }')
     else:
         p('    const unsigned int iy = byr * MKB_BY + ty;')
+    if overlap:
+        p('    // Steps overlap: the next kernel may start launching now; this block')
+        p('    // waits for step - 1 of its own tile and its four neighbours.')
+        p('    MKB_PDL_TRIGGER();')
+        p('    const unsigned int tile_row = %s;' % ('byb' if slab else 'byr'))
+        p('    {')
+        p('        const unsigned int t5 = ty * MKB_BX + tx;')
+        p('        if (t5 < 5u) {')
+        p('            const int nbx_ = (int)bxb + (t5 == 1u ? -1 : (t5 == 2u ? 1 : 0));')
+        p('            const int nby_ = (int)tile_row + (t5 == 3u ? -1 : (t5 == 4u ? 1 : 0));')
+        p('            if (nbx_ >= 0 && nbx_ < (int)gridDim.x && nby_ >= 0 && nby_ < (int)nby)')
+        p('                mkb_wait_tile(g.tile_done + (unsigned int)nby_ * gridDim.x + (unsigned int)nbx_,')
+        p('                              sp->step - 1u, g.halo_error);')
+        p('        }')
+        p('        __syncthreads();')
+        p('    }')
     if partitioned:
         p('    // Ghost cells: V(t) of this step must have arrived from every')
         p('    // exporting GPU before any thread of this block gathers it.')
@@ -2101,7 +2173,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    (void)time; (void)pace_in; (void)store_aux; (void)v_in; (void)v_out;')
     p('')
     if diffusion:
-        p('    const Real vc = active ? v_in[cid] : (Real)0;')
+        p('    const Real vc = active ? MKB_LD(v_in + cid) : (Real)0;')
     if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
         p('    const unsigned int iyg = iy + (unsigned int)g.iy_offset;  // global row')
         p('    const unsigned int nyg = (unsigned int)g.ny_global;')
@@ -2129,7 +2201,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         for var in states:
             if var.index() != i_vm and var not in early_states and var not in gate_set_unused:
                 p('        MKB_PREFETCH_%s(&MKB_AT(state_c, %d));'
-                  % ('L1' if prefetch == 'l1' else 'L2', var.index()))
+                  % ('L1' if (prefetch == 'l1' and not overlap) else 'L2', var.index()))
         p('    }')
     p('')
 
@@ -2142,12 +2214,12 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    // column is the halo slot of its neighbour, written below)')
         p('    if (active) tile[ty + 1][tx + 1] = vc;')
         p('    if (active) {')
-        p('        if (tx == 0) tile[ty + 1][0] = (ix > 0) ? v_in[cid - 1] : vc;')
+        p('        if (tx == 0) tile[ty + 1][0] = (ix > 0) ? MKB_LD(v_in + cid - 1) : vc;')
         p('        if (tx == MKB_BX - 1 || ix == nx - 1)')
-        p('            tile[ty + 1][tx + 2] = (ix < nx - 1) ? v_in[cid + 1] : vc;')
+        p('            tile[ty + 1][tx + 2] = (ix < nx - 1) ? MKB_LD(v_in + cid + 1) : vc;')
         p('        if (ty == 0) {')
         p('            Real vn = vc;')
-        p('            if (iy > 0) vn = v_in[cid - nx];')
+        p('            if (iy > 0) vn = MKB_LD(v_in + cid - nx);')
         if slab:
             p('            else if (iyg > 0 && g.halo_lo) vn = __ldcg((const Real*)g.halo_lo + (step % 3u) * nx + ix);')
         else:
@@ -2156,7 +2228,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('        }')
         p('        if (ty == MKB_BY - 1 || iy == ny - 1) {')
         p('            Real vn = vc;')
-        p('            if (iy < ny - 1) vn = v_in[cid + nx];')
+        p('            if (iy < ny - 1) vn = MKB_LD(v_in + cid + nx);')
         if slab:
             p('            else if (iyg < nyg - 1 && g.halo_hi) vn = __ldcg((const Real*)g.halo_hi + (step % 3u) * nx + ix);')
         else:
@@ -2291,6 +2363,25 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('            if (send_hi) *((volatile unsigned int*)g.peer_hi_flag_lo + bxb) = step + 1u;')
         p('        }')
         p('    }')
+    if overlap:
+        p('    // This tile has taken its step: stores first (barrier of the threads')
+        p('    // still here, device-scope release), then the flag. Coordinates are')
+        p('    // read again rather than kept in registers across the model.')
+        p('    __syncthreads();')
+        p('    {')
+        p('        unsigned int tx_, ty_;')
+        p('        MKB_ASM_SREG(tx_, "tid.x"); MKB_ASM_SREG(ty_, "tid.y");')
+        p('        if (tx_ == 0 && ty_ == 0) {')
+        p('            unsigned int bx_, by_, bz_, gy_, gx_;')
+        p('            MKB_ASM_SREG(bx_, "ctaid.x"); MKB_ASM_SREG(by_, "ctaid.y"); MKB_ASM_SREG(bz_, "ctaid.z");')
+        p('            MKB_ASM_SREG(gy_, "nctaid.y"); MKB_ASM_SREG(gx_, "nctaid.x");')
+        p('            unsigned int row_ = by_ + bz_ * gy_;')
+        if slab:
+            p('            const unsigned int nby_ = ((unsigned int)g.ny + MKB_BY - 1) / MKB_BY;')
+            p('            row_ = (row_ == 0) ? 0 : ((row_ == 1) ? nby_ - 1 : row_ - 1);')
+        p('            mkb_publish_tile(g.tile_done + row_ * gx_ + bx_, *(const volatile unsigned int*)&sp->step);')
+        p('        }')
+        p('    }')
     p('}')
     p('')
     if gate_states:
@@ -2338,4 +2429,6 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                       len(fields), diffusion_mode, options)
     ks.gate_kernel = bool(gate_states)
     ks.gate_states = [x.qname() for x in gate_states]
+    if overlap:
+        ks.kernel_flags |= 4            # MKB_KERNEL_OVERLAP
     return ks

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Runs on an N-GPU box (gpurun --gpus N): multi-GPU tests on distinct devices, the bench at N (and below), slab overhead.
 N=${1:-2}
+ONLY=${2:-"1 2 4 8"}   # which GPU counts to bench
 O=gpurun_out/r02
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
@@ -8,7 +9,7 @@ nvidia-smi -L | head -8
 timeout 300 python -m pytest tests/test_multigpu_gpu.py -q -m gpu 2>&1 | tail -3 | tee $O/multigpu_tests_n$N.log
 port=29700
 for n in $(seq 1 8); do
-  if [ $n -le $N ] && { [ $n = 1 ] || [ $n = 2 ] || [ $n = 4 ] || [ $n = 8 ]; }; then
+  if [ $n -le $N ] && [[ " $ONLY " == *" $n "* ]]; then
     port=$((port + 1))
     if [ $n = 1 ]; then
       timeout 400 python bench.py --steps 20 --warmup 3 --no-cpu 2>$O/scale_n$n.err | tail -1 > $O/scale_n$n.json
@@ -30,7 +31,7 @@ PY
   fi
 done
 # what a slab costs beyond its cells: the same rows unsharded on one GPU
-python - <<'PY' 2>&1 | grep -v Warn
+[ -n "$SKIP_SINGLE" ] || python - <<'PY' 2>&1 | grep -v Warn
 import sys; sys.path.insert(0, '.')
 import myokit_b200
 from myokit_b200 import workloads

@@ -216,6 +216,10 @@ extern "C" int shim_run(
         }
     }
     gridDim.x = gbx; gridDim.y = gby; gridDim.z = gbz;
+    // kernels whose steps overlap on the GPU: per-block step counters (here every
+    // wait finds its flag set, which the shim checks)
+    std::vector<unsigned int> tile_done((size_t)gbx * gby * gbz, 0u);
+    g.tile_done = tile_done.data();
     blockDim.x = block_x; blockDim.y = block_y; blockDim.z = 1;
 
     std::vector<Fiber> fibers((size_t)block_x * block_y);
@@ -304,6 +308,7 @@ struct Slab {
     std::vector<Real> state, v_alt, idiff, inter, field, gxf, gyf;
     std::vector<unsigned char> mask;
     std::vector<char> xchg;
+    std::vector<unsigned int> tile_done;
     MkbGridArgs g;
 };
 
@@ -441,6 +446,8 @@ extern "C" int shim_run_slabs(
             gridDim.x = (unsigned int)nbx;
             gridDim.y = (unsigned int)(by_blocks < 32768 ? by_blocks : 32768);
             gridDim.z = (unsigned int)((by_blocks + gridDim.y - 1) / gridDim.y);
+            if (s.tile_done.empty()) s.tile_done.assign((size_t)gridDim.x * gridDim.y * gridDim.z, 0u);
+            s.g.tile_done = s.tile_done.data();
             g_launch.g = s.g;
             g_launch.sp = &sp;
             g_launch.v_in = v_in;
