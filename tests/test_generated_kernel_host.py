@@ -588,8 +588,10 @@ def test_persistent_kernel_limits_and_name():
     g.set_kernel_options(persistent=True)
     with pytest.raises(ValueError):
         g.kernel_source()
-    # the default stays the one-step kernel
+    # grids of up to 128 cells take it by default, larger ones the one-step kernel
     d = myokit_b200.SimulationCUDA(m, None, ncells=128, precision=DP)
+    assert d.kernel_source().kernel_name == 'mkb_cell_step_persistent'
+    d = myokit_b200.SimulationCUDA(m, None, ncells=129, precision=DP)
     assert d.kernel_source().kernel_name == 'mkb_cell_step'
 
 

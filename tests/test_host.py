@@ -214,7 +214,7 @@ def test_generated_source_follows_reference_arithmetic():
     s = variants()['1d_fp64']
     # tiny models default to several cells per thread with vector accesses;
     # any model can ask for it
-    s.set_kernel_options(cells_per_thread=2)
+    s.set_kernel_options(cells_per_thread=2, persistent=False)
     code = s.kernel_source().code
     assert '#define MKB_CPT 2' in code
     assert 'mkb_vload<MKB_CPT>(S1[r], state + 1ull * stride + cid0, active);' in code
@@ -260,6 +260,7 @@ def test_generated_source_follows_reference_arithmetic():
 def test_logged_intermediaries_are_stored_only_on_logged_steps():
     m, p, _ = myokit.load('example')
     s = myokit_b200.SimulationCUDA(m, p, ncells=8, precision=DP)
+    s.set_kernel_options(persistent=False)
     src = s.kernel_source([s._model.get('ica.ICa')])
     assert src.n_inter == 1
     assert 'if (store_aux) MKB_AT(inter_c, 0) = V_ICa;' \
