@@ -1110,11 +1110,6 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     s->ny = c->ny;
     s->n = c->nx * c->ny;
     s->stride = (s->n + 31) / 32 * 32;
-    if (const char* pad = getenv("MKB_STRIDE_PAD")) {
-        // experiment: planes a power of two apart (2048^2, 8192^2 cells) all start in
-        // the same memory channel; a pad of some 128-byte lines staggers them
-        s->stride += (u64)strtoull(pad, nullptr, 10) / 32 * 32;
-    }
     s->block_x = c->block_x;
     s->block_y = c->block_y;
     s->cpt = c->cells_per_thread > 1 ? c->cells_per_thread : 1;

@@ -659,7 +659,7 @@ __device__ __forceinline__ double mkb_exp_tab(double x) {
 // latencies. These have no branches, handle special operands with selects,
 // and use fewer integer instructions. Polynomials: scripts/gen_libm_coeffs.py.
 // Accuracy (tests/test_prelude_math_host.py, _gpu.py): sqrt <= 0.5 ulp + 2^-20,
-// log <= 1 ulp, cos, acos <= 1.5 ulp, pow <= 3 + |y ln x| ulp.
+// log <= 1 ulp, cos, acos <= 1.5 ulp, pow <= 2 + 1.5 |y ln x| ulp.
 // ---------------------------------------------------------------------------
 
 // sqrt: reciprocal-square-root seed (>= 20 bits), one coupled Newton step on
@@ -784,7 +784,7 @@ __device__ __forceinline__ double mkb_acos(double x) {
 
 // pow for exponents that are not small integer literals: exp(y log x), the
 // product clamped to +-1024 so that 0^y and overflow come out as 0 / inf.
-// Error <= 3 + |y ln x| ulp (OpenCL allows its pow 16 ulp). A negative base
+// Error <= 2 + 1.5 |y ln x| ulp (OpenCL allows its pow 16 ulp). A negative base
 // gives NaN also for integer-valued y (integer literals never get here: they
 // are multiplication chains), and 0^0 is NaN.
 #ifndef MKB_EXP_FN

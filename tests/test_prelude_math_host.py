@@ -165,7 +165,7 @@ def test_pow_through_exp_and_log():
         want = mp.power(mp.mpf(float(xi)), mp.mpf(float(yi)))
         ulp = mp.mpf(float(np.spacing(float(want))))
         err = float(abs(mp.mpf(float(gi)) - want) / ulp)
-        worst = max(worst, err / (3.0 + abs(yi * np.log(xi))))
+        worst = max(worst, err / (2.0 + 1.5 * abs(yi * np.log(xi))))
     assert worst <= 1.0, worst
     # 0^y, overflow and underflow, NaN
     got = call_host(lib, 'pow', np.array([0.0, 0.0, 10.0, 10.0, np.nan, 2.0]),
