@@ -40,3 +40,9 @@ for ny in (1024, 512, 256):
     i = s.benchmark_steps(40, warmup=10)
     print('single GPU, 2048 x %d unsharded: %.4f ms/step' % (ny, i['device_ms'] / i['steps']))
 PY
+# the other BASELINE configurations, sharded (device-resident timing)
+if [ -n "$WITH_CONFIGS" ]; then
+  port=$((port + 1))
+  timeout 300 $TR --nproc-per-node $N --master-port $port scripts/bench_configs.py c4 mesh c5 2>$O/configs_n$N.err | grep "GPUs\]" | tee $O/configs_n$N.txt
+  timeout 300 python scripts/bench_configs.py c4 mesh c5 2>/dev/null | grep -v Warn | grep "cell-steps" | tee $O/configs_n1.txt
+fi
