@@ -639,3 +639,43 @@ def test_command_line(tmp_path, monkeypatch, capsys):
     out = capsys.readouterr().out
     assert 'Device 1: B200' in out and '(selected)' in out
     assert 'Multiprocessors   : 148' in out
+
+
+def test_host_state_stays_one_cell_until_cells_differ():
+    # the initial state is the model's, for every cell: no n_cells-long array
+    # exists (an 8192 x 8192 grid would need 25.8 GB of host memory for it)
+    # until a caller asks for one or changes a single cell
+    m, p, _ = myokit.load('example')
+    n = m.count_states()
+    s = myokit_b200.SimulationCUDA(m, p, ncells=(5, 4), precision=DP)
+    assert s._state_full is None and s._default_full is None
+    init = list(m.initial_values(True))
+    assert s.state(3, 2) == init and s.default_state(0, 0) == init
+    assert s._state_full is None                    # single-cell queries do not tile it
+    s.set_state([float(k) for k in range(n)])       # one cell's values for all
+    assert s._state_full is None and s.state(4, 3) == [float(k) for k in range(n)]
+    s.reset()
+    assert s._state_full is None and s.state(1, 1) == init
+    # one cell differs: now there is an array, in the reference's layout
+    s.set_state([9.0] * n, 2, 1)
+    assert s._state_full is not None
+    full = s.state_array()
+    assert full.shape == (5 * 4 * n,)
+    assert list(full[(2 + 1 * 5) * n:(3 + 1 * 5) * n]) == [9.0] * n
+    assert list(full[:n]) == init
+    # the simulation's own array handed back is adopted, not copied
+    mine = s.state_array(copy=False)
+    mine[0] = -1.0
+    s.set_state(mine)
+    assert s.state_array(copy=False) is mine and s.state(0, 0)[0] == -1.0
+    # a full vector from the caller is copied
+    other = np.zeros(5 * 4 * n)
+    s.set_state(other)
+    other[0] = 7.0
+    assert s.state(0, 0)[0] == 0.0
+    # default state follows the same rules
+    s.set_default_state([1.0] * n)
+    assert s._default_full is None and s.default_state(4, 3) == [1.0] * n
+    s.set_default_state([2.0] * n, 0, 0)
+    assert s.default_state(0, 0) == [2.0] * n and s.default_state(1, 0) == [1.0] * n
+    assert len(s.default_state()) == 5 * 4 * n

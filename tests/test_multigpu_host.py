@@ -26,6 +26,10 @@ WORKER = textwrap.dedent('''
     got = comm.allgather(('rank', comm.rank, b'x' * 64))
     assert [g[1] for g in got] == [0, 1]
     comm.barrier()
+    # NaN-halt agreement: one small all-reduce over the host group
+    assert comm.any(False) is False
+    assert comm.any(comm.rank == 1) is True
+    # set_state on this rank's own array is adopted, a uniform state stays one cell's values
 
     m, p, _ = myokit.load('example')
     nx, ny = 6, 5
@@ -41,6 +45,13 @@ WORKER = textwrap.dedent('''
     s.set_state(full)
     want = full.reshape(ny, nx, n)[y0:y0 + sny].reshape(-1)
     assert np.array_equal(s.state_array(), want)
+    mine = s.state_array(copy=False)
+    s.set_state(mine)                       # our own array handed back: no copy
+    assert s.state_array(copy=False) is mine
+    u1 = myokit_b200.SimulationCUDA(m, p, ncells=(nx, ny), precision=myokit.DOUBLE_PRECISION, comm=comm)
+    assert u1._state_full is None and len(u1._state_cell) == n      # uniform: never tiled
+    u1.set_state(list(range(n)))
+    assert u1._state_full is None and u1.state(2, y0) == list(map(float, range(n)))
     # single-cell access is global-indexed; remote cells raise
     own = (2, y0)
     other = (2, rows[1 - comm.rank][0])
