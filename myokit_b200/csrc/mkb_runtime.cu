@@ -453,6 +453,8 @@ struct mkb_sim {
     bool halo_live = false;             // exchange block consistent with step_index (see arm_run)
     bool halo_connected = false;        // halo_connect / ghost_connect + first seed done
     bool state_replaced = false;        // mkb_sim_set_state since the last run
+    void* d_stage[2] = {nullptr, nullptr};  // state up / download staging (kept: cudaMalloc and
+    size_t stage_bytes = 0;                 // cudaFree per transfer cost ms and synchronise the device)
     bool overlap = false;               // MKB_KERNEL_OVERLAP: step kernels launched with PDL
     unsigned int* d_tile_done = nullptr;
     size_t n_tiles = 0;
@@ -564,6 +566,8 @@ static void sim_destroy(mkb_sim* s) {
     if (s->ev_t0) cudaEventDestroy(s->ev_t0);
     if (s->ev_t1) cudaEventDestroy(s->ev_t1);
     if (s->d_tile_done) cudaFree(s->d_tile_done);
+    if (s->d_stage[0]) cudaFree(s->d_stage[0]);
+    if (s->d_stage[1]) cudaFree(s->d_stage[1]);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->side) cudaStreamDestroy(s->side);
     if (s->lib) cudaLibraryUnload(s->lib);
@@ -591,6 +595,25 @@ static int grid_for(u64 n) {
 // them next could read the destination too early. Found as garbage
 // conductances in a 264 x 77 single-precision run; copies of 64 KiB or less
 // are inline, which is why small grids never showed it.)
+// Two device staging buffers of at least `bytes` each, kept with the simulation.
+static cudaError_t stage_buffers(mkb_sim* s, size_t bytes, int count) {
+    if (s->stage_bytes < bytes) {
+        for (int i = 0; i < 2; i++) {
+            if (s->d_stage[i]) cudaFree(s->d_stage[i]);
+            s->d_stage[i] = nullptr;
+        }
+        s->stage_bytes = 0;
+    }
+    for (int i = 0; i < count; i++) {
+        if (!s->d_stage[i]) {
+            cudaError_t e = cudaMalloc(&s->d_stage[i], bytes);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    if (s->stage_bytes < bytes) s->stage_bytes = bytes;
+    return cudaSuccess;
+}
+
 static cudaError_t h2d_sync(mkb_sim* s, void* dst, const void* src, size_t bytes) {
     cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
@@ -608,16 +631,10 @@ static int upload_aos(mkb_sim* s, const void* host, TR* planes, int nvar) {
     if (nvar == 0) return MKB_OK;
     const u64 chunk_cells = std::max<u64>(1, (64ull << 20) / ((u64)nvar * sizeof(TH)));
     const u64 cap = std::min<u64>(chunk_cells, s->n);
-    TH* d_stage[2] = {nullptr, nullptr};
     const int nbuf = (cap < s->n) ? 2 : 1;
-    for (int i = 0; i < nbuf; i++) {
-        cudaError_t e = cudaMalloc(&d_stage[i], cap * nvar * sizeof(TH));
-        if (e != cudaSuccess) {
-            cudaFree(d_stage[0]);
-            return fail(MKB_ERR_CUDA, "state upload failed: %s", cudaGetErrorString(e));
-        }
-    }
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = stage_buffers(s, cap * nvar * sizeof(TH), nbuf);
+    if (e != cudaSuccess) return fail(MKB_ERR_CUDA, "state upload failed: %s", cudaGetErrorString(e));
+    TH* d_stage[2] = {(TH*)s->d_stage[0], (TH*)s->d_stage[1]};
     int b = 0;
     for (u64 c0 = 0; c0 < s->n && e == cudaSuccess; c0 += cap, b = (b + 1) % nbuf) {
         const u64 nc = std::min<u64>(cap, s->n - c0);
@@ -631,8 +648,6 @@ static int upload_aos(mkb_sim* s, const void* host, TR* planes, int nvar) {
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_stage[0]);
-    cudaFree(d_stage[1]);
     if (e != cudaSuccess) return fail(MKB_ERR_CUDA, "state upload failed: %s", cudaGetErrorString(e));
     return MKB_OK;
 }
@@ -662,15 +677,10 @@ static int download_aos(mkb_sim* s, void* host) {
     const int nvar = s->n_state;
     const u64 chunk_cells = std::max<u64>(1, (64ull << 20) / ((u64)nvar * sizeof(TH)));
     const u64 cap = std::min<u64>(chunk_cells, s->n);
-    TH* d_stage[2] = {nullptr, nullptr};
     const int nbuf = (cap < s->n) ? 2 : 1;
-    for (int i = 0; i < nbuf; i++) {
-        cudaError_t e = cudaMalloc(&d_stage[i], cap * nvar * sizeof(TH));
-        if (e != cudaSuccess) {
-            cudaFree(d_stage[0]);
-            return fail(MKB_ERR_CUDA, "state download failed: %s", cudaGetErrorString(e));
-        }
-    }
+    cudaError_t e0 = stage_buffers(s, cap * nvar * sizeof(TH), nbuf);
+    if (e0 != cudaSuccess) return fail(MKB_ERR_CUDA, "state download failed: %s", cudaGetErrorString(e0));
+    TH* d_stage[2] = {(TH*)s->d_stage[0], (TH*)s->d_stage[1]};
     const TR* planes = plane_ptr<TR>(s, 0);
     const TR* v_cur = plane_ptr<TR>(s, s->parity ? s->plane_alt_v : (u64)std::max(s->i_vm, 0));
     cudaError_t e = cudaSuccess;
@@ -687,8 +697,6 @@ static int download_aos(mkb_sim* s, void* host) {
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_stage[0]);
-    cudaFree(d_stage[1]);
     if (e != cudaSuccess) return fail(MKB_ERR_CUDA, "state download failed: %s", cudaGetErrorString(e));
     return MKB_OK;
 }

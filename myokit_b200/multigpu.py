@@ -54,6 +54,7 @@ class TorchComm:
         self._torch = torch
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
+        self._nccl_group = None
         if host_group is None:
             if dist.get_backend(group) == 'gloo':
                 host_group = group
@@ -61,6 +62,10 @@ class TorchComm:
                 ranks = (None if group is None
                          else dist.get_process_group_ranks(group))
                 host_group = dist.new_group(ranks=ranks, backend='gloo')
+                if dist.get_backend(group) == 'nccl' and torch.cuda.is_available():
+                    # one-word agreements go over NVLink: ~50 us instead of
+                    # the ~0.4 ms of a gloo all-reduce among 8 processes
+                    self._nccl_group = (group,)
         self._group = host_group
 
     def allgather(self, obj):
@@ -70,7 +75,13 @@ class TorchComm:
 
     def any(self, flag):
         """True on every rank if ``flag`` is true on any."""
-        t = self._torch.tensor([1 if flag else 0], dtype=self._torch.int32)
+        torch = self._torch
+        if self._nccl_group is not None:
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device='cuda')
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX,
+                                  group=self._nccl_group[0])
+            return bool(t.item())
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32)
         self._dist.all_reduce(t, op=self._dist.ReduceOp.MAX, group=self._group)
         return bool(t.item())
 
