@@ -1074,6 +1074,27 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         time of a step goes: ``'l1'`` reads every state but V from one of
         256 cells (always a cache hit: the kernel without its load latency),
         ``'l1ns'`` also predicates every state store off.
+    ``fast_libm``
+        In-line branch-free double-precision ``sqrt`` / ``log`` / ``cos`` /
+        ``acos`` / general ``pow`` (``mkb_sqrt`` ... in the prelude) instead
+        of libdevice's, whose internal branches cut the kernel body into
+        short scheduling regions.
+    ``select``
+        Conditional expressions evaluate both arms and select (``True``), or
+        only where no arm holds an exp / log / pow / trig call (``'cheap'``).
+    ``exp_scale``
+        ``'mul'`` (default): ``mkb_exp_*`` apply 2^n with a multiplication,
+        +inf / 0 outside the double range; ``'add'``: exponent-field add,
+        saturating.
+    ``stream``
+        Vector path fed by TMA: persistent blocks walk tiles, the V tile and
+        its halo arrive through ``cp.async.bulk.tensor.2d`` into a two-stage
+        mbarrier ring (2-d grids on one GPU whose rows are 16-byte multiples,
+        ``block[0] == 32``).
+    ``overlap``
+        Consecutive steps overlap: programmatic dependent launch plus
+        per-tile step counters (``MkbGridArgs::tile_done``) instead of the
+        kernel boundary; scalar path on regular grids.
     ``div_cubic``
         ``mkb_div`` with one third-order refinement of the reciprocal and no
         residual correction: 4 FP64 instructions instead of 6, IEEE results
