@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MKB_ABI_VERSION 4
+#define MKB_ABI_VERSION 5
 
 /* Error codes */
 #define MKB_OK               0
@@ -160,6 +160,9 @@ typedef struct mkb_sim_config {
     int kernel_flags;           /* MKB_KERNEL_* */
     int stream_box_w, stream_box_h; /* MKB_KERNEL_STREAM: the TMA box (cells, rows) the
                                        kernel loads per tile, halo included */
+    uint64_t kernel_stride;     /* 0, or the plane stride (elements) the kernel was
+                                   compiled for: nx * ny rounded up to 32. Anything
+                                   else is refused (the kernel would trap) */
 } mkb_sim_config;
 
 /* kernel_flags */

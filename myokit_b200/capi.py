@@ -15,7 +15,7 @@ c_u64 = ctypes.c_uint64
 c_i64 = ctypes.c_int64
 c_vp = ctypes.c_void_p
 
-MKB_ABI_VERSION = 4
+MKB_ABI_VERSION = 5
 MKB_OK = 0
 MKB_ERR_INVALID = -1
 MKB_ERR_CUDA = -2
@@ -83,6 +83,7 @@ class SimConfig(ctypes.Structure):
         ('second_kernel_name', ctypes.c_char_p),
         ('kernel_flags', ctypes.c_int),
         ('stream_box_w', ctypes.c_int), ('stream_box_h', ctypes.c_int),
+        ('kernel_stride', c_u64),
     ]
 
 

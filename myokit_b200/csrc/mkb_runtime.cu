@@ -1118,6 +1118,12 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
     s->ny = c->ny;
     s->n = c->nx * c->ny;
     s->stride = (s->n + 31) / 32 * 32;
+    if (c->kernel_stride && c->kernel_stride != s->stride) {
+        const u64 want = s->stride;
+        delete s;
+        return fail(MKB_ERR_INVALID, "The kernel was compiled for a plane stride of %llu elements; this grid needs %llu.",
+                    (unsigned long long)c->kernel_stride, (unsigned long long)want);
+    }
     s->block_x = c->block_x;
     s->block_y = c->block_y;
     s->cpt = c->cells_per_thread > 1 ? c->cells_per_thread : 1;

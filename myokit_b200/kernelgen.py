@@ -324,6 +324,10 @@ _PRELUDE = r"""
 } while (0)
 #define MKB_SHFL_UP(v, d) __shfl_up_sync(0xffffffffu, (v), (d))
 #define MKB_SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, (v), (d))
+// max(min(a, b), 0) in one instruction (VIMNMX.RELU)
+#define MKB_MIN_RELU(d, a, b) asm("min.relu.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b))
+// Kernels generated for one plane stride (option plane_stride) refuse any other
+#define MKB_STRIDE_MISMATCH() __trap()
 #endif
 
 // Overlapping consecutive steps (option overlap). A step kernel normally starts
@@ -369,11 +373,16 @@ __device__ __forceinline__ void mkb_publish_tile(unsigned int* flag, unsigned in
 }
 #endif
 
-// Plane k of a cell, from the cell's address in plane 0. (Forms that were
-// tried to get below two integer instructions per access and did not: a 32-bit
-// stride, which the compiler turns into the same chains of 64-bit additions,
-// and an inline mad.wide.u32, which ptxas splits into a uniform multiply and
-// the same additions.)
+// Plane k of a cell, from the cell's address in plane 0. With the plane
+// stride as a run-time value every access costs three integer instructions
+// (IMAD.WIDE.U32 + IMAD + IADD for the 64 x 64-bit product; a 32-bit stride
+// and an inline mad.wide.u32 were tried: ptxas knows the stride to be uniform
+// and turns both into a uniform multiply, a copy to ordinary registers and a
+// 64-bit addition in two halves, no fewer). Kernels are compiled per
+// simulation anyway, so the main kernel takes the stride as a compile-time
+// constant (option plane_stride): the access is then base + constant, two
+// instructions, and the stride, its multiples and their copies leave the
+// register file: 640 of the 4200 instructions of the 48-state kernel.
 #define MKB_AT(base, k) ((base)[(unsigned long long)(k) * stride])
 
 // Conditional expression with both arms evaluated (function arguments are),
@@ -455,17 +464,30 @@ __device__ __forceinline__ double mkb_div(double a, double b) {
     // (relative error e^3 < 2^-60 from the >= 20-bit seed), then the product:
     // 4 FP64 instructions instead of 6, no residual correction and therefore
     // no NaN from inf - inf for an infinite dividend. A divisor of 0 or inf
-    // gives a seed of inf / 0 and e = NaN; the seed's exponent field (all ones
-    // / all zeros) is tested on the integer pipe and the correction factor is
-    // then replaced by a finite number (one 32-bit select on its high word),
-    // so r stays inf / 0 and a * r is the IEEE quotient (a / 0 = inf,
-    // a / inf = 0, 0 / 0 = NaN). Error <= 1.5 ulp of the quotient (two
-    // roundings: reciprocal and product; reciprocals 1 / b: <= 1 ulp);
-    // denormal divisors count as 0 (rcp.approx.ftz).
+    // gives a seed of inf / 0 and e = NaN (either sign) or inf. The correction
+    // factor e + e^2 is then replaced by a finite number with ONE instruction
+    // on the otherwise idle FP32 pipe: its high word, read as a float, is a
+    // float NaN exactly when the double is NaN or inf (exponent field all
+    // ones), and fminf(x, 1.0f) returns 1.0f for a NaN x and x itself — same
+    // bits — for every other value a correction can take (|e + e^2| < 2^-19:
+    // the float reading is below 1.0f; flush-to-zero only concerns doubles
+    // below 2^-1015, and an exact zero stays zero). So r stays inf / 0 and
+    // a * r is the IEEE quotient (a / 0 = inf, a / inf = 0, 0 / 0 = NaN).
+    // (Option div_int_check: the first form of this test, on the seed's
+    // exponent field with the integer pipe — add, and, compare, select: 4
+    // issue slots per division; kept for comparison.)
+    // Error <= 1.5 ulp of the quotient (two roundings: reciprocal and product;
+    // reciprocals 1 / b: <= 1 ulp); denormal divisors count as 0
+    // (rcp.approx.ftz).
     double e2 = fma(e, e, e);
+#if MKB_DIV_INT_CHECK
     const unsigned int rh = (unsigned int)__double2hiint(r);
     const bool special = ((rh + 0x00100000u) & 0x7fe00000u) == 0u;
     e2 = __hiloint2double(special ? 0x3ff00000 : __double2hiint(e2), __double2loint(e2));
+#else
+    e2 = __hiloint2double(__float_as_int(fminf(__int_as_float(__double2hiint(e2)), 1.0f)),
+                          __double2loint(e2));
+#endif
     r = fma(r, e2, r);
     return a * r;
 #endif
@@ -534,9 +556,20 @@ __device__ __forceinline__ double mkb_exp_apply(double p, int n) {
 #endif
 }
 __device__ __forceinline__ double mkb_exp_poly(double x) {
-    double t = fma(x, mkb_exp_c[0], mkb_exp_c[1]);
+#if MKB_EXP_SCALE_ADD
+    double t = fma(x, mkb_exp_c[0], 6755399441055744.0);
     const int n = __double2loint(t);
-    t -= mkb_exp_c[1];
+    t -= 6755399441055744.0;
+#else
+    // The rounding shift carries the exponent bias: the low word of t is
+    // n + 1023, which ONE min-with-relu clamps to [0, 2047] = the exponent
+    // fields of 0 and +inf (see mkb_exp_scale; its clamp was two instructions
+    // and the bias a third).
+    double t = fma(x, mkb_exp_c[0], 6755399441056767.0);     // 1.5 * 2^52 + 1023
+    int nb;
+    MKB_MIN_RELU(nb, __double2loint(t), 2047);
+    t -= 6755399441056767.0;
+#endif
     double r = fma(t, mkb_exp_c[2], x);
     r = fma(t, mkb_exp_c[3], r);
     double p = mkb_exp_c[4];
@@ -544,7 +577,11 @@ __device__ __forceinline__ double mkb_exp_poly(double x) {
     for (int k = 5; k < 14; k++) p = fma(p, r, mkb_exp_c[k]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
+#if MKB_EXP_SCALE_ADD
     return mkb_exp_apply(p, n);
+#else
+    return p * __hiloint2double(nb << 20, 0);
+#endif
 }
 
 // Single precision (option fast_exp = 'ex2'): expf(x) = 2^t with t = x log2(e)
@@ -981,6 +1018,7 @@ class KernelSource:
         self.gate_states = []
         self.cells_per_thread = 1
         self.rows_per_thread = 1
+        self.plane_stride = 0           # elements; 0: any (read from MkbGridArgs)
 
     def key(self):
         h = hashlib.sha256()
@@ -999,7 +1037,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              junction=None, persistent=False, split_gates=False,
              div_cubic=False, prefetch=None, debug_mem=None,
              fast_libm=False, select=False, exp_scale='mul', stream=False,
-             overlap=False):
+             overlap=False, plane_stride=None):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -1095,6 +1133,11 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         Consecutive steps overlap: programmatic dependent launch plus
         per-tile step counters (``MkbGridArgs::tile_done``) instead of the
         kernel boundary; scalar path on regular grids.
+    ``plane_stride``
+        The plane stride (elements) as a compile-time constant of the main
+        kernel: plane addresses become base + constant. The kernel traps on
+        any other ``MkbGridArgs::stride``; ``KernelSource.plane_stride``
+        tells the runtime (``mkb_sim_config::kernel_stride``).
     ``div_cubic``
         ``mkb_div`` with one third-order refinement of the reciprocal and no
         residual correction: 4 FP64 instructions instead of 6, IEEE results
@@ -2118,6 +2161,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     if min_blocks:
         p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY, %d)'
           % int(min_blocks))
+    elif max_registers:
+        # (ptxas ignores --maxrregcount for kernels with launch bounds, and
+        # derives only 128 / 96 / 80 ... registers from a block count)
+        p('extern "C" __global__ void __maxnreg__(%d)' % int(max_registers))
     else:
         p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
     p('%s(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
@@ -2128,7 +2175,12 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    // grid is (column blocks, row blocks mod 32768, row blocks / 32768).')
     p('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
     p('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
-    p('    const unsigned long long stride = g.stride;')
+    if plane_stride:
+        p('    // compiled for this plane stride (see MKB_AT)')
+        p('    constexpr unsigned long long stride = %dull;' % int(plane_stride))
+        p('    if (g.stride != stride) { MKB_STRIDE_MISMATCH(); return; }')
+    else:
+        p('    const unsigned long long stride = g.stride;')
     p('    const unsigned int nby = (ny + MKB_BY - 1) / MKB_BY;')
     p('    const unsigned int byr = blockIdx.y + blockIdx.z * gridDim.y;')
     p('    if (byr >= nby) return;')
@@ -2452,4 +2504,5 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     ks.gate_states = [x.qname() for x in gate_states]
     if overlap:
         ks.kernel_flags |= 4            # MKB_KERNEL_OVERLAP
+    ks.plane_stride = int(plane_stride or 0)
     return ks

@@ -13,6 +13,7 @@ steps = int(os.environ.get('SWEEP_STEPS', '20'))
 B3 = dict(div_cubic=True, fast_exp='stab', fast_libm=False, select=False)
 OLD = dict(div_cubic=False, fast_libm=False, select=False)
 LM = dict(select=False)
+ND = dict(block=(128, 2), min_blocks=2, load_ahead=24, prefetch='l1', select=False)
 
 
 def also(base, **kw):
@@ -152,6 +153,37 @@ SETS = {
         ('128x4 mb1 la24', also(LM, prefetch='l1', load_ahead=24, block=(128, 4), min_blocks=1, max_registers=128)),
         ('128x2 la24 (diag. l1)', also(LM, prefetch='l1', load_ahead=24, block=(128, 2), debug_mem='l1')),
     ],
+    # round 2, last pass: the plane stride as a compile-time constant and the
+    # one-instruction special-divisor test (4217 -> 3578 SASS instructions)
+    'r3a': [
+        ('r2 default (run-time stride, int check)', also(ND, plane_stride=False, div_int_check=True)),
+        ('fminf test only', also(ND, plane_stride=False)),
+        ('const stride only', also(ND, div_int_check=True)),
+        ('NEW default', dict(ND)),
+        ('new 64x4', also(ND, block=(64, 4))),
+        ('new 256x1', also(ND, block=(256, 1))),
+        ('new 128x1 mb4', also(ND, block=(128, 1), min_blocks=4)),
+        ('new 64x3 (112 regs)', also(ND, block=(64, 3), min_blocks=None, max_registers=112)),
+        ('new 64x1 (112 regs)', also(ND, block=(64, 1), min_blocks=None, max_registers=112)),
+        ('new select 64x3 (112 regs)', also(ND, select=True, block=(64, 3), min_blocks=None, max_registers=112)),
+        ('new 128x1 mb5 (96 regs)', also(ND, block=(128, 1), min_blocks=5)),
+        ('new la16', also(ND, load_ahead=16)),
+        ('new la20', also(ND, load_ahead=20)),
+        ('new la28', also(ND, load_ahead=28)),
+        ('new la32', also(ND, load_ahead=32)),
+        ('new la40', also(ND, load_ahead=40)),
+        ('new no prefetch', also(ND, prefetch=None)),
+        ('new pf-l2', also(ND, prefetch='l2')),
+        ('new select', also(ND, select=True)),
+        ('new select la8', also(ND, select=True, load_ahead=8)),
+        ('new select 128x1 mb3 (168)', also(ND, select=True, block=(128, 1), min_blocks=3, max_registers=168)),
+        ('new select 64x3 mb2 (168)', also(ND, select=True, block=(64, 3), min_blocks=2, max_registers=168)),
+        ('new 128x1 mb3 (168)', also(ND, block=(128, 1), min_blocks=3, max_registers=168)),
+        ('new cheap-select', also(ND, select='cheap')),
+        ('new exp-add', also(ND, exp_scale='add')),
+        ('new estrin', also(ND, fast_exp='estrin')),
+        ('new (diag. l1)', also(ND, debug_mem='l1')),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -167,7 +199,8 @@ for name, opts in variants:
         block=(64, 4), min_blocks=2, max_registers=0, load_ahead=32, prefetch=None,
         div_cubic=True, fast_libm=True, select=True,
         fast_exp='poly', split_gates=False, div_parallel=False,
-        const_div=True, fmad=True, debug_mem=None, exp_scale='mul'), **opts))
+        const_div=True, fmad=True, debug_mem=None, exp_scale='mul',
+        plane_stride=True, div_int_check=False), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:

@@ -172,7 +172,9 @@ def run_slabs_on_host(make, n_slabs, duration, log_interval=1.0, options=None,
     ``halo_error``.
     """
     from myokit_b200 import multigpu
-    options = options or {}
+    # one host library serves every slab: the kernel reads its plane stride at
+    # run time (on a GPU each rank compiles for its own)
+    options = dict(options or {}, plane_stride=False)
     whole = make(None)
     whole.set_kernel_options(**options)
     box = {}
@@ -253,7 +255,7 @@ def run_parts_on_host(make, n_parts, duration, log_interval=1.0, options=None,
     (nt, ncells, global cell order), ``idiff``, ``state``, ``halo_error``.
     """
     from myokit_b200 import multigpu
-    options = options or {}
+    options = dict(options or {}, plane_stride=False)     # (as in run_slabs_on_host)
     ranks = [None] * n_parts
 
     def work(comm):
