@@ -160,6 +160,7 @@ typedef struct mkb_sim_config {
     int kernel_flags;           /* MKB_KERNEL_* */
     int stream_box_w, stream_box_h; /* MKB_KERNEL_STREAM: the TMA box (cells, rows) the
                                        kernel loads per tile, halo included */
+    int kernel_smem_bytes;      /* MKB_KERNEL_STAGE: dynamic shared memory per thread block */
     uint64_t kernel_stride;     /* 0, or the plane stride (elements) the kernel was
                                    compiled for: nx * ny rounded up to 32. Anything
                                    else is refused (the kernel would trap) */
@@ -175,6 +176,10 @@ typedef struct mkb_sim_config {
 #define MKB_KERNEL_OVERLAP    4 /* consecutive launches of kernel_name overlap: launched with
                                    programmatic stream serialization, ordered by the
                                    per-block step counters in MkbGridArgs::tile_done */
+#define MKB_KERNEL_STAGE      8 /* kernel_name stages its thread block's tile of every state
+                                   plane in `kernel_smem_bytes` of dynamic shared memory by
+                                   TMA, through the 3-d descriptor MkbGridArgs::tmap_state
+                                   ([plane][row][column], box block_x x block_y x 1) */
 #define MKB_KERNEL_FLAG_SHIFT_BLOCKS 8   /* bits 8..15: thread blocks per SM (stream) */
 
 /* A run on the state that is already resident on the device (mkb_sim_rearm):

@@ -83,12 +83,15 @@ class SimConfig(ctypes.Structure):
         ('second_kernel_name', ctypes.c_char_p),
         ('kernel_flags', ctypes.c_int),
         ('stream_box_w', ctypes.c_int), ('stream_box_h', ctypes.c_int),
+        ('kernel_smem_bytes', ctypes.c_int),
         ('kernel_stride', c_u64),
     ]
 
 
 KERNEL_PERSISTENT = 1
 KERNEL_STREAM = 2
+KERNEL_OVERLAP = 4
+KERNEL_STAGE = 8
 
 
 class RunConfig(ctypes.Structure):

@@ -114,6 +114,11 @@ struct MkbGridArgs {
      * plane inside `state`, tmap[1] the second V plane. A kernel that uses them
      * declares its grid argument __grid_constant__. Zero elsewhere. */
     alignas(64) unsigned long long tmap[2][16];
+    /* Staged kernels (kernelgen stage=True): TMA descriptor of the state
+     * planes as a 3-d tensor [n_state][ny][nx] (strides: row nx, plane
+     * `stride`) with a box of one thread-block tile of one plane. Loads fill
+     * cells outside the grid with zeros, stores clip them. Zero elsewhere. */
+    alignas(64) unsigned long long tmap_state[16];
 };
 
 #endif

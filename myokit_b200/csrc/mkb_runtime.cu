@@ -393,6 +393,7 @@ struct mkb_sim {
     int parity = 0;                     // 0: V(t) in plane i_vm, 1: in plane alt_v
     MkbGridArgs grid{};
     dim3 launch_grid, launch_block;
+    unsigned int smem_bytes = 0;        // dynamic shared memory of the step kernel (staged kernels)
 
     // schedule (openclsim.c globals :84-211)
     double tmin = 0, tmax = 0, default_dt = 0, log_interval = 1;
@@ -1366,6 +1367,58 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
         }
     }
 
+    if (c->kernel_flags & MKB_KERNEL_STAGE) {
+        // Staged kernel: the state planes as one 3-d tensor [plane][row][column]
+        // with a box of one thread-block tile of one plane; the kernel asks for
+        // kernel_smem_bytes of dynamic shared memory (above the 48 KiB default:
+        // opt in).
+        if (s->persistent || (c->kernel_flags & MKB_KERNEL_STREAM) || s->cpt != 1 || s->rpt != 1 ||
+            c->kernel_smem_bytes <= 0 || (s->nx * s->rs) % 16 != 0 || (s->block_x * s->rs) % 16 != 0 ||
+            s->block_x > 256 || s->block_y > 256) {
+            sim_destroy(s);
+            return fail(MKB_ERR_INVALID, "Staged kernel: rows of %llu cells / a tile of %d x %d cannot be described "
+                                         "to the TMA unit (16-byte multiples, at most 256 per side), or the kernel "
+                                         "form does not stage its states.",
+                        (unsigned long long)s->nx, s->block_x, s->block_y);
+        }
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        INIT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            sim_destroy(s);
+            return fail(MKB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        }
+        static_assert(sizeof(CUtensorMap) == sizeof(g.tmap_state), "tensor map size");
+        const cuuint64_t dims[3] = {s->nx, s->ny, (cuuint64_t)s->n_state};
+        const cuuint64_t strides[2] = {s->nx * s->rs, s->stride * s->rs};
+        const cuuint32_t box[3] = {(cuuint32_t)s->block_x, (cuuint32_t)s->block_y, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ((encode_fn)fn)(
+            (CUtensorMap*)g.tmap_state, s->rs == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+            3, s->d_planes, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            sim_destroy(s);
+            return fail(MKB_ERR_CUDA, "cuTensorMapEncodeTiled (state planes) failed (%d)", (int)r);
+        }
+        s->smem_bytes = (unsigned int)c->kernel_smem_bytes;
+        cudaError_t ea = cudaFuncSetAttribute((const void*)s->kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)s->smem_bytes);
+        if (ea != cudaSuccess) {
+            sim_destroy(s);
+            return fail(MKB_ERR_CUDA, "Staged kernel: %u bytes of shared memory per block refused (%s).",
+                        s->smem_bytes, cudaGetErrorName(ea));
+        }
+        // (all of the SM's shared memory for the two resident blocks)
+        cudaFuncSetAttribute((const void*)s->kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    }
+
     s->overlap = (c->kernel_flags & MKB_KERNEL_OVERLAP) != 0;
     if (s->overlap) {
         if (s->kern2 || s->persistent || (c->kernel_flags & MKB_KERNEL_STREAM)) {
@@ -1525,14 +1578,15 @@ static int ghost_push(mkb_sim* s, const TR* v, unsigned int step, const MkbStepP
 // order themselves through MkbGridArgs::tile_done. Captured into a graph the
 // attribute becomes a programmatic dependency edge.
 static cudaError_t launch_step(mkb_sim* s, cudaKernel_t kern, void** args) {
+    const unsigned int smem = (kern == s->kern) ? s->smem_bytes : 0u;
     if (!s->overlap) {
-        return cudaLaunchKernel((const void*)kern, s->launch_grid, s->launch_block, args, 0, s->stream);
+        return cudaLaunchKernel((const void*)kern, s->launch_grid, s->launch_block, args, smem, s->stream);
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = s->launch_grid;
     cfg.blockDim = s->launch_block;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

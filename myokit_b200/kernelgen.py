@@ -324,6 +324,30 @@ _PRELUDE = r"""
 } while (0)
 #define MKB_SHFL_UP(v, d) __shfl_up_sync(0xffffffffu, (v), (d))
 #define MKB_SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, (v), (d))
+// Staged kernels (option stage): the thread block's tile of every state plane
+// travels HBM <-> shared memory by TMA, one box of (MKB_BX, MKB_BY, 1 plane)
+// per instruction, through the 3-d descriptor MkbGridArgs::tmap_state
+// ([plane][row][column]); cells outside the grid arrive as zeros and are not
+// written back.
+#define MKB_STAGE_DECL(bytes) extern __shared__ __align__(128) unsigned char mkb_stage_mem[]
+#define MKB_SYNCWARP() __syncwarp()
+#define MKB_MBAR_EXPECT_TX(bar, bytes) \
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" \
+                 :: "r"(MKB_SMEM_ADDR(bar)), "r"(bytes) : "memory")
+#define MKB_TMA_LOAD_3D(dst, tmap, cx, cy, cz, bar) \
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" \
+                 :: "r"(MKB_SMEM_ADDR(dst)), "l"((unsigned long long)(tmap)), "r"(cx), "r"(cy), "r"(cz), \
+                    "r"(MKB_SMEM_ADDR(bar)) : "memory")
+#define MKB_TMA_STORE_3D(tmap, cx, cy, cz, src) \
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" \
+                 :: "l"((unsigned long long)(tmap)), "r"(cx), "r"(cy), "r"(cz), "r"(MKB_SMEM_ADDR(src)) : "memory")
+// commit the stores issued so far and wait until they have been performed
+#define MKB_TMA_STORE_FINISH() \
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory")
+// shared-memory writes of this thread become visible to the TMA unit
+#define MKB_FENCE_ASYNC_SMEM() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
+// global writes of the TMA unit observed through a flag become visible to later TMA reads
+#define MKB_FENCE_ASYNC_GLOBAL() asm volatile("fence.proxy.async.global;" ::: "memory")
 // max(min(a, b), 0) in one instruction (VIMNMX.RELU)
 #define MKB_MIN_RELU(d, a, b) asm("min.relu.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b))
 // Kernels generated for one plane stride (option plane_stride) refuse any other
@@ -1019,6 +1043,7 @@ class KernelSource:
         self.cells_per_thread = 1
         self.rows_per_thread = 1
         self.plane_stride = 0           # elements; 0: any (read from MkbGridArgs)
+        self.smem_bytes = 0             # dynamic shared memory per block (staged kernels)
 
     def key(self):
         h = hashlib.sha256()
@@ -1037,7 +1062,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              junction=None, persistent=False, split_gates=False,
              div_cubic=False, prefetch=None, debug_mem=None,
              fast_libm=False, select=False, exp_scale='mul', stream=False,
-             overlap=False, plane_stride=None):
+             overlap=False, plane_stride=None, stage=False,
+             stage_group=8):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -1210,17 +1236,22 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     stream = bool(stream) and cpt > 1 and diffusion_mode in (
         DIFF_HOMOGENEOUS, DIFF_FIELD) and bx == 32 and not stab
 
-    # Consecutive steps overlap (see MKB_OVERLAP in the prelude): scalar path
-    # on regular grids only
-    overlap = bool(overlap) and cpt == 1 and diffusion_mode in (
-        DIFF_HOMOGENEOUS, DIFF_FIELD) and not (junction or persistent
-                                               or split_gates or debug_mem)
-
     # Consecutive steps overlap (see MKB_OVERLAP_STEPS in the prelude): scalar
     # path on regular grids only
     overlap = bool(overlap) and cpt == 1 and diffusion_mode in (
         DIFF_HOMOGENEOUS, DIFF_FIELD) and not (junction or persistent
                                                or split_gates or debug_mem)
+
+    # States staged in shared memory by TMA (see the main kernel's prologue):
+    # scalar path, regular grids and uncoupled cells; the caller checks that
+    # rows are 16-byte multiples (the descriptor's strides)
+    rs_ = 4 if sp else 8
+    stage = (bool(stage) and cpt == 1 and lazy_state and not (
+        persistent or split_gates or debug_mem or junction or stab)
+        and diffusion_mode != DIFF_CONNECTIONS
+        and (bx * rs_) % 16 == 0 and (bx * by * rs_) % 128 == 0
+        and bx <= 256 and by <= 256)
+    stage_group = max(int(stage_group or 8), 1)
 
     if junction not in (None, 'fiber', 'tissue'):
         raise ValueError('junction must be None, "fiber" or "tissue".')
@@ -1329,10 +1360,21 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     state_set = set(states)
     inter_index = dict((var, k) for k, var in enumerate(inter_log))
 
+    stage_slot = {}         # state -> slot in the staged tile (option stage)
+    stage_waited = set()    # arrival groups already waited for
+
     def state_load(var, guarded=False):
         k = var.index()
         if k == i_vm:
             return '    const Real %s = vc;' % v(var)
+        if var in stage_slot:
+            j = stage_slot[var]
+            lines = []
+            if j // stage_group not in stage_waited:
+                stage_waited.add(j // stage_group)
+                lines.append('    MKB_MBAR_WAIT(&stage_bar[%d], 0u);' % (j // stage_group))
+            lines.append('    const Real %s = stage_c[%d * MKB_STAGE_TILE];' % (v(var), j))
+            return '\n'.join(lines)
         src = 'MKB_LD(&MKB_AT(state_c, %d))' % k
         if debug_mem:
             src = 'MKB_AT(state + (cid & 255ull), %d)' % k
@@ -1378,6 +1420,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 '    }' % rhs)
         if k == i_vm:
             return '    v_out[cid] = %s;' % rhs
+        if var in stage_slot:
+            return '    stage_c[%d * MKB_STAGE_TILE] = %s;' % (stage_slot[var], rhs)
         if debug_mem == 'l1ns':
             return '    { const Real vnew = %s; if (dt < (Real)0) MKB_AT(state_c, %d) = vnew; }' % (rhs, k)
         return '    MKB_AT(state_c, %d) = %s;' % (k, rhs)
@@ -1501,6 +1545,10 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 first_use.setdefault(var, len(todo))
         order = sorted([x for x in states if x in first_use],
                        key=lambda x: (first_use[x], x.index()))
+        if stage:
+            for var in order:
+                if var.index() != i_vm:
+                    stage_slot[var] = len(stage_slot)
         loaded = set()
         have = set()
         done = set(gate_set)    # updated by mkb_gate_step, if any
@@ -1529,7 +1577,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                     body.append(state_update(var))
                     done.add(var)
 
-        emit_loads(ahead, early, True)
+        # (staged states are read from shared memory: after the tile barrier)
+        emit_loads(ahead, body if stage else early, True)
         early_states = set(loaded)
         gate_set_unused = set(x for x in gate_set if x not in first_use)
         for i, (name, eq) in enumerate(todo):
@@ -2158,6 +2207,19 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('    %r,' % x)
         p('};')
         p('')
+    stage_head = ((len(stage_slot) + stage_group - 1) // stage_group * 8 + 127) // 128 * 128
+    if stage and stage_slot:
+        slot_plane_ = [None] * len(stage_slot)
+        for var, j in stage_slot.items():
+            slot_plane_[j] = var.index()
+        p('// Staged states: slot -> state plane, in order of first use')
+        p('#define MKB_STAGE_TILE (MKB_BX * MKB_BY)')
+        p('#define MKB_STAGE_LANES %d' % min(32, bx * by))
+        p('#define MKB_STAGE_HEAD %d    // the arrival barriers' % stage_head)
+        p('#define MKB_STAGE_BYTES %d' % (stage_head + len(stage_slot) * bx * by * rs_))
+        p('__constant__ unsigned short mkb_stage_plane[%d] = {%s};'
+          % (len(slot_plane_), ', '.join(str(x) for x in slot_plane_)))
+        p('')
     if min_blocks:
         p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY, %d)'
           % int(min_blocks))
@@ -2167,7 +2229,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('extern "C" __global__ void __maxnreg__(%d)' % int(max_registers))
     else:
         p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY)')
-    p('%s(const MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
+    p('%s(const %sMkbGridArgs g, const MkbStepParams* __restrict__ sp,'
+      % (KERNEL_NAME, '__grid_constant__ ' if stage else ''))
     p('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
     p('{')
     p('    // 32-bit indices (64-bit integer arithmetic is emulated on the GPU);')
@@ -2231,6 +2294,44 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('        }')
         p('        __syncthreads();')
         p('    }')
+    n_slots = len(stage_slot)
+    n_groups = (n_slots + stage_group - 1) // stage_group
+    if stage and n_slots:
+        slot_plane = [None] * n_slots
+        for var, j in stage_slot.items():
+            slot_plane[j] = var.index()
+        p('    // Staged states: the tile of every state plane but V arrives in shared')
+        p('    // memory by TMA, one box per plane, in the order the equations first')
+        p('    // need them; %d arrival barriers of %d planes each. The first warp'
+          % (n_groups, stage_group))
+        p('    // issues everything now; a thread reads and updates only its own')
+        p('    // element of each plane, and the tiles go back by TMA at the end.')
+        p('    MKB_STAGE_DECL(MKB_STAGE_BYTES);')
+        p('    unsigned long long* const stage_bar = (unsigned long long*)mkb_stage_mem;')
+        p('    Real* const stage_base = (Real*)(mkb_stage_mem + MKB_STAGE_HEAD);')
+        p('    Real* const stage_c = stage_base + ty * MKB_BX + tx;')
+        p('    {')
+        p('        const unsigned int t_ = ty * MKB_BX + tx;')
+        p('        if (t_ < MKB_STAGE_LANES) {')
+        p('            if (t_ == 0) {')
+        p('                for (int k_ = 0; k_ < %d; k_++) MKB_MBAR_INIT(&stage_bar[k_], 1);' % n_groups)
+        p('                MKB_MBAR_FENCE_INIT();')
+        for gi in range(n_groups):
+            cnt = min(stage_group, n_slots - gi * stage_group)
+            p('                MKB_MBAR_EXPECT_TX(&stage_bar[%d], %du * MKB_STAGE_TILE * (unsigned int)sizeof(Real));'
+              % (gi, cnt))
+        p('            }')
+        p('            MKB_SYNCWARP();')
+        if overlap:
+            p('            // (the tiles were written by the TMA unit of the previous step,')
+            p('            // which this block has just observed through tile_done)')
+            p('            MKB_FENCE_ASYNC_GLOBAL();')
+        p('            for (unsigned int j_ = t_; j_ < %du; j_ += MKB_STAGE_LANES)' % n_slots)
+        p('                MKB_TMA_LOAD_3D(stage_base + j_ * MKB_STAGE_TILE, g.tmap_state,')
+        p('                                (int)(ix - tx), (int)(iy - ty), (int)mkb_stage_plane[j_],')
+        p('                                &stage_bar[j_ / %du]);' % stage_group)
+        p('        }')
+        p('    }')
     p('    const bool active = (ix < nx) && (iy < ny);')
     p('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
     p('    Real* const state = (Real*)g.state;')
@@ -2268,7 +2369,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    // Loads issued ahead of use: fields and the first states')
     for line in early:
         p(line)
-    if prefetch and lazy_state:
+    if prefetch and lazy_state and not stage:
         p('    // The other states: only prefetched here, loaded where they are used')
         p('    if (active) {')
         for var in states:
@@ -2381,6 +2482,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         if stab:
             p('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
             p('    __syncthreads();')
+        elif stage and n_slots:
+            p('    __syncthreads();    // the arrival barriers are initialised')
         p('    if (!active) return;')
     p('')
 
@@ -2405,6 +2508,38 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('')
     for line in body:
         p(line)
+
+    def stage_epilogue():
+        if not (stage and n_slots):
+            return
+        p('    // Staged states go back: every writer makes its shared-memory stores')
+        p('    // visible to the TMA unit, the threads still here meet, and one thread')
+        p('    // issues a box per plane and waits until they have been written')
+        p('    // (cells outside the grid are clipped). Coordinates are read again.')
+        p('    MKB_FENCE_ASYNC_SMEM();')
+        p('    __syncthreads();')
+        p('    {')
+        p('        unsigned int tx_, ty_;')
+        p('        MKB_ASM_SREG(tx_, "tid.x"); MKB_ASM_SREG(ty_, "tid.y");')
+        p('        if (tx_ == 0 && ty_ == 0) {')
+        p('            unsigned int bx_, by_, bz_, gy_;')
+        p('            MKB_ASM_SREG(bx_, "ctaid.x"); MKB_ASM_SREG(by_, "ctaid.y"); MKB_ASM_SREG(bz_, "ctaid.z");')
+        p('            MKB_ASM_SREG(gy_, "nctaid.y");')
+        p('            unsigned int row_ = by_ + bz_ * gy_;')
+        if slab:
+            p('            const unsigned int nby_ = ((unsigned int)g.ny + MKB_BY - 1) / MKB_BY;')
+            p('            row_ = (row_ == 0) ? 0 : ((row_ == 1) ? nby_ - 1 : row_ - 1);')
+        p('            Real* const base_ = (Real*)(mkb_stage_mem + MKB_STAGE_HEAD);')
+        p('            for (unsigned int j_ = 0; j_ < %du; j_++)' % n_slots)
+        p('                MKB_TMA_STORE_3D(g.tmap_state, (int)(bx_ * MKB_BX), (int)(row_ * MKB_BY),')
+        p('                                 (int)mkb_stage_plane[j_], base_ + j_ * MKB_STAGE_TILE);')
+        p('            MKB_TMA_STORE_FINISH();')
+        if overlap:
+            p('            MKB_FENCE_ASYNC_GLOBAL();')
+        p('        }')
+        p('    }')
+    if not (slab and not slab_lean):
+        stage_epilogue()
     if slab and slab_lean:
         p('    // Publish the boundary rows: data first, then (after a system-scope')
         p('    // fence by every writer and a barrier of the threads still here)')
@@ -2424,6 +2559,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    }')
     elif slab:
         p('    }   // active')
+        stage_epilogue()
         p('    // Publish the boundary rows: data first, then (after a system-scope')
         p('    // fence by every writer and a CTA barrier) the arrival flag.')
         p('    const bool send_lo = (byb == 0) && g.peer_lo_halo_hi;')
@@ -2505,4 +2641,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     if overlap:
         ks.kernel_flags |= 4            # MKB_KERNEL_OVERLAP
     ks.plane_stride = int(plane_stride or 0)
+    if stage and stage_slot:
+        ks.kernel_flags |= 8            # MKB_KERNEL_STAGE
+        ks.smem_bytes = stage_head + len(stage_slot) * bx * by * rs_
     return ks

@@ -184,6 +184,32 @@ SETS = {
         ('new estrin', also(ND, fast_exp='estrin')),
         ('new (diag. l1)', also(ND, debug_mem='l1')),
     ],
+    # staged states: tiles of every state plane through shared memory by TMA
+    'r3b': [
+        ('NEW default', dict(ND)),
+        ('stage la24', also(ND, stage=True)),
+        ('stage la8', also(ND, stage=True, load_ahead=8)),
+        ('stage la4', also(ND, stage=True, load_ahead=4)),
+        ('stage la2', also(ND, stage=True, load_ahead=2)),
+        ('stage la1', also(ND, stage=True, load_ahead=1)),
+        ('stage la4 groups of 4', also(ND, stage=True, load_ahead=4, stage_group=4)),
+        ('stage la4 groups of 16', also(ND, stage=True, load_ahead=4, stage_group=16)),
+        ('stage la4 one group', also(ND, stage=True, load_ahead=4, stage_group=64)),
+        ('stage la4 64x4', also(ND, stage=True, load_ahead=4, block=(64, 4))),
+        ('stage la4 256x1', also(ND, stage=True, load_ahead=4, block=(256, 1))),
+        ('stage la4 128x1 mb4', also(ND, stage=True, load_ahead=4, block=(128, 1), min_blocks=4)),
+        ('stage la4 64x2 mb4', also(ND, stage=True, load_ahead=4, block=(64, 2), min_blocks=4)),
+        ('stage la4 select', also(ND, stage=True, load_ahead=4, select=True)),
+        ('stage la8 select', also(ND, stage=True, load_ahead=8, select=True)),
+        ('stage la4 cheap-select', also(ND, stage=True, load_ahead=4, select='cheap')),
+        ('stage la4 128x1 mb3 (168)', also(ND, stage=True, load_ahead=4, block=(128, 1), min_blocks=3, max_registers=168)),
+        ('stage la4 select 128x1 mb3 (168)', also(ND, stage=True, load_ahead=4, select=True, block=(128, 1), min_blocks=3, max_registers=168)),
+        ('stage la4 128x1 mb5 (96)', also(ND, stage=True, load_ahead=4, block=(128, 1), min_blocks=5)),
+        ('stage la4 estrin', also(ND, stage=True, load_ahead=4, fast_exp='estrin')),
+        ('stage la4 exp-add', also(ND, stage=True, load_ahead=4, exp_scale='add')),
+        ('stage la4 overlap', also(ND, stage=True, load_ahead=4, overlap=True)),
+        ('overlap (no stage)', also(ND, overlap=True)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -200,7 +226,8 @@ for name, opts in variants:
         div_cubic=True, fast_libm=True, select=True,
         fast_exp='poly', split_gates=False, div_parallel=False,
         const_div=True, fmad=True, debug_mem=None, exp_scale='mul',
-        plane_stride=True, div_int_check=False), **opts))
+        plane_stride=True, div_int_check=False, stage=False, stage_group=8,
+        overlap=False), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:

@@ -192,6 +192,11 @@ extern "C" int shim_run(
     g.nx = nx;
     g.ny = ny;
     g.stride = stride;
+    // stand-in descriptor of the state planes (staged kernels)
+    g.tmap_state[0] = (unsigned long long)(uintptr_t)state.data();
+    g.tmap_state[1] = nx; g.tmap_state[2] = ny; g.tmap_state[3] = sizeof(Real);
+    g.tmap_state[4] = stride; g.tmap_state[5] = (unsigned long long)n_state;
+    g.tmap_state[6] = (unsigned long long)block_x; g.tmap_state[7] = (unsigned long long)block_y;
     g.iy_offset = 0;
     g.ny_global = ny;
     g.gx = gx;
@@ -376,6 +381,10 @@ extern "C" int shim_run_slabs(
         g.nx = nx;
         g.ny = s.ny;
         g.stride = s.stride;
+        g.tmap_state[0] = (unsigned long long)(uintptr_t)s.state.data();
+        g.tmap_state[1] = nx; g.tmap_state[2] = s.ny; g.tmap_state[3] = sizeof(Real);
+        g.tmap_state[4] = s.stride; g.tmap_state[5] = (unsigned long long)n_state;
+        g.tmap_state[6] = (unsigned long long)block_x; g.tmap_state[7] = (unsigned long long)block_y;
         g.iy_offset = s.iy0;
         g.ny_global = ny;
         g.gx = gx;

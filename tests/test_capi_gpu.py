@@ -53,6 +53,7 @@ def test_c_abi_end_to_end_fp32_host_buffers():
     cfg.kernel_flags = src.kernel_flags      # (what kind of kernel the generator made)
     cfg.stream_box_w, cfg.stream_box_h = src.stream_box
     cfg.kernel_stride = src.plane_stride     # (0, or the stride it was compiled for)
+    cfg.kernel_smem_bytes = src.smem_bytes   # (staged kernels)
     cfg.block_x, cfg.block_y = src.block
     cfg.cells_per_thread = src.cells_per_thread
     cfg.rows_per_thread = src.rows_per_thread

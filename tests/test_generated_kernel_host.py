@@ -709,3 +709,82 @@ def test_streaming_kernel_falls_back_where_tma_cannot_describe_the_grid():
             continue
         s.set_kernel_options(stream=True)
         assert not (s.kernel_source().kernel_flags & 2)
+
+
+# ---------------------------------------------------------------------------
+# Staged states (option stage): every state plane's tile through shared memory
+# by TMA — on the host the shim's synchronous box copies — must not change a bit
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('block,nx,ny', [((8, 4), 12, 9), ((16, 2), 16, 4), ((8, 2), 10, 5)])
+def test_staged_states_equal_oracle_bit_for_bit(block, nx, ny):
+    def make(cls):
+        return workloads.c3_hetero(cls, nx=nx, ny=ny)
+    opts = dict(EXACT, block=block, stage=True, load_ahead=2, stage_group=5)
+    a = make(myokit_b200.SimulationCUDA)
+    a.set_kernel_options(**opts)
+    src = a.kernel_source()
+    assert src.kernel_flags & 8 and src.smem_bytes > 0
+    assert 'MKB_TMA_LOAD_3D' in src.code and 'MKB_PREFETCH_L1(&' not in src.code
+    got, want, wstate = both(make, opts, 3.0, 0.5, nx, ny)
+    assert want['membrane.V'].max() > 0
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+    # last-to-first thread order: the same bits
+    b = make(myokit_b200.SimulationCUDA)
+    b.set_kernel_options(**opts)
+    rev = cuda_shim.run_on_host(b, 3.0, log_interval=0.5, reverse=True)
+    assert np.array_equal(rev['state'], got['state'])
+
+
+def test_staged_states_uncoupled_cells_and_default_arithmetic():
+    m, p, _ = myokit.load('example')
+
+    def make(cls):
+        s = cls(m, p, ncells=24, diffusion=False, precision=DP, rl=True)
+        s.set_field('ina.gNa', np.linspace(8, 16, 24))
+        return s
+    opts = dict(EXACT, block=(16, 1), stage=True)
+    a = make(myokit_b200.SimulationCUDA)
+    a.set_kernel_options(**opts)
+    assert a.kernel_source().kernel_flags & 8
+    got = cuda_shim.run_on_host(a, 2.0, log_interval=0.5)
+    log, ostate = make(OracleSimulation).run(2.0, log=['engine.time'], log_interval=0.5)
+    assert np.array_equal(got['state'].ravel(), np.asarray(ostate))
+    # the rewrites the bench runs with (in-line division, exp, libm): the fp64 bar
+    def make3(cls):
+        return workloads.c3_hetero(cls, nx=12, ny=9)
+    got, want, wstate = both(make3, dict(block=(8, 4), stage=True), 3.0, 0.5, 12, 9)
+    assert np.max(np.abs(got['V'] - want['membrane.V'])) < 1e-9
+
+
+def test_staged_states_fall_back_where_tma_cannot_describe_the_rows():
+    # rows of 11 doubles are not 16-byte multiples; connection graphs and the
+    # register-patch path do not stage
+    s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=11, ny=4)
+    s.set_kernel_options(stage=True, block=(8, 4))
+    src = s.kernel_source()
+    assert not (src.kernel_flags & 8) and src.smem_bytes == 0
+    m, p, _ = myokit.load('example')
+    c = myokit_b200.SimulationCUDA(m, p, ncells=16, precision=DP)
+    c.set_connections([(i, i + 1, 5.0) for i in range(15)])
+    c.set_kernel_options(stage=True)
+    assert not (c.kernel_source().kernel_flags & 8)
+
+
+@pytest.mark.parametrize('lean', [False, True], ids=['slab', 'slab_lean'])
+def test_staged_states_row_slabs_equal_the_whole_grid(lean):
+    def make(comm):
+        kw = {} if comm is None else dict(comm=comm)
+        return workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=12, ny=11, **kw)
+    opts = dict(EXACT, block=(8, 4))
+    whole = make(None)
+    whole.set_kernel_options(**opts)
+    one = cuda_shim.run_on_host(whole, 3.0, log_interval=0.5)
+    for reverse in (False, True):
+        out = cuda_shim.run_slabs_on_host(
+            make, 3, 3.0, 0.5, dict(opts, slab_lean=lean, stage=True, overlap=True),
+            reverse=reverse)
+        assert out['halo_error'] == 0
+        assert np.array_equal(out['V'], one['V'])
+        assert np.array_equal(out['state'], one['state'])

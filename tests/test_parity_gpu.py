@@ -732,3 +732,70 @@ def test_native_maths_fp32_stays_within_the_activation_time_bar():
     assert not np.any(np.isnan(tb))
     assert np.max(np.abs(ta - tb)) <= dt * 1.0001, np.max(np.abs(ta - tb))
     assert max_abs_diff(la, lb, keys) < 2.0     # mV, on the upstroke
+
+
+@pytest.mark.parametrize('overlap', [False, True], ids=['serial', 'overlap'])
+def test_staged_states_by_tma_equal_the_plain_kernel_and_oracle(overlap):
+    # kernelgen stage=True: every state plane's tile travels HBM <-> shared
+    # memory by TMA (cp.async.bulk.tensor.3d, one box per plane, arrival
+    # barriers in order of first use); the arithmetic and its order are those
+    # of the plain kernel, so the bits are too. 200 x 37 under 128 x 2 tiles:
+    # partial tiles in both directions (zero fill on load, clipped on store).
+    nx, ny = 200, 37
+
+    def make(cls, **opts):
+        s = workloads.c3_hetero(cls, nx=nx, ny=ny)
+        if opts:
+            s.set_kernel_options(**opts)
+        return s
+    a = make(myokit_b200.SimulationCUDA, stage=True, load_ahead=4, overlap=overlap)
+    src = a.kernel_source()
+    assert src.kernel_flags & 8 and src.smem_bytes > 48 * 1024
+    b = make(myokit_b200.SimulationCUDA, stage=False, overlap=False)
+    assert not (b.kernel_source().kernel_flags & 8)
+    ta, fa = a.run_fields(4, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    tb, fb = b.run_fields(4, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    assert fb['membrane.V'].max() > 0           # the paced edge fired
+    for k in fb:
+        assert np.array_equal(fa[k], fb[k]), k
+    assert np.array_equal(a.state_array(), b.state_array())
+    # a second run continues on the resident state (CUDA graphs, both V planes)
+    ta, fa = a.run_fields(2, ['membrane.V'], log_interval=0.5)
+    tb, fb = b.run_fields(2, ['membrane.V'], log_interval=0.5)
+    assert np.array_equal(fa['membrane.V'], fb['membrane.V'])
+    assert np.array_equal(a.state_array(), b.state_array())
+    # and the oracle (in-line division / exp / libm: the fp64 bar)
+    o = make(OracleSimulation)
+    ol, ostate = o.run(6, log=['engine.time'], log_interval=1)
+    ostate = np.asarray(ostate)
+    rel = np.abs(a.state_array() - ostate) / (np.abs(ostate) + 1e-12)
+    assert rel.max() <= 1e-6
+
+
+def test_staged_states_uncoupled_and_cable():
+    # no diffusion (every state in place, no V planes) and a 1-d cable
+    m, p, _ = myokit.load('example')
+
+    def pop(cls, **opts):
+        s = cls(m, p, ncells=1000, diffusion=False, precision=DP, rl=True)
+        s.set_field('ina.gNa', np.linspace(8, 16, 1000))
+        if opts:
+            s.set_kernel_options(**opts)
+        return s
+    a = pop(myokit_b200.SimulationCUDA, stage=True)
+    assert a.kernel_source().kernel_flags & 8
+    b = pop(myokit_b200.SimulationCUDA, stage=False)
+    a.run(5, log=myokit.LOG_NONE)
+    b.run(5, log=myokit.LOG_NONE)
+    assert np.array_equal(a.state_array(), b.state_array())
+
+    def cable(cls, **opts):
+        s = workloads.c1_cable(cls, 512)
+        s.set_kernel_options(persistent=False, **opts)
+        return s
+    a = cable(myokit_b200.SimulationCUDA, stage=True)
+    assert a.kernel_source().kernel_flags & 8
+    b = cable(myokit_b200.SimulationCUDA, stage=False)
+    a.run(5, log=myokit.LOG_NONE)
+    b.run(5, log=myokit.LOG_NONE)
+    assert np.array_equal(a.state_array(), b.state_array())
