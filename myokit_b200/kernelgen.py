@@ -344,6 +344,9 @@ _PRELUDE = r"""
 // commit the stores issued so far and wait until they have been performed
 #define MKB_TMA_STORE_FINISH() \
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory")
+// commit, and wait only until the shared memory has been read
+#define MKB_TMA_STORE_READ_DONE() \
+    asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory")
 // shared-memory writes of this thread become visible to the TMA unit
 #define MKB_FENCE_ASYNC_SMEM() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
 // global writes of the TMA unit observed through a flag become visible to later TMA reads
@@ -1251,7 +1254,22 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         and diffusion_mode != DIFF_CONNECTIONS
         and (bx * rs_) % 16 == 0 and (bx * by * rs_) % 128 == 0
         and bx <= 256 and by <= 256)
-    stage_group = max(int(stage_group or 8), 1)
+    if isinstance(stage_group, (tuple, list)):
+        # explicit group sizes; the last group takes what is left
+        stage_sizes = [max(int(x), 1) for x in stage_group]
+    else:
+        stage_sizes = None
+        stage_group = max(int(stage_group or 8), 1)
+
+    def stage_group_of(j):
+        if stage_sizes is None:
+            return j // stage_group
+        at = 0
+        for gi, n in enumerate(stage_sizes):
+            at += n
+            if j < at:
+                return gi
+        return len(stage_sizes)
 
     if junction not in (None, 'fiber', 'tissue'):
         raise ValueError('junction must be None, "fiber" or "tissue".')
@@ -1370,9 +1388,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         if var in stage_slot:
             j = stage_slot[var]
             lines = []
-            if j // stage_group not in stage_waited:
-                stage_waited.add(j // stage_group)
-                lines.append('    MKB_MBAR_WAIT(&stage_bar[%d], 0u);' % (j // stage_group))
+            if stage_group_of(j) not in stage_waited:
+                stage_waited.add(stage_group_of(j))
+                lines.append('    MKB_MBAR_WAIT(&stage_bar[%d], 0u);' % stage_group_of(j))
             lines.append('    const Real %s = stage_c[%d * MKB_STAGE_TILE];' % (v(var), j))
             return '\n'.join(lines)
         src = 'MKB_LD(&MKB_AT(state_c, %d))' % k
@@ -2207,18 +2225,20 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('    %r,' % x)
         p('};')
         p('')
-    stage_head = ((len(stage_slot) + stage_group - 1) // stage_group * 8 + 127) // 128 * 128
+    stage_head = ((stage_group_of(max(len(stage_slot) - 1, 0)) + 1) * 8 + 127) // 128 * 128
     if stage and stage_slot:
         slot_plane_ = [None] * len(stage_slot)
         for var, j in stage_slot.items():
             slot_plane_[j] = var.index()
         p('// Staged states: slot -> state plane, in order of first use')
         p('#define MKB_STAGE_TILE (MKB_BX * MKB_BY)')
-        p('#define MKB_STAGE_LANES %d' % min(32, bx * by))
+        p('#define MKB_STAGE_WARPS %d' % ((bx * by + 31) // 32))
         p('#define MKB_STAGE_HEAD %d    // the arrival barriers' % stage_head)
         p('#define MKB_STAGE_BYTES %d' % (stage_head + len(stage_slot) * bx * by * rs_))
         p('__constant__ unsigned short mkb_stage_plane[%d] = {%s};'
           % (len(slot_plane_), ', '.join(str(x) for x in slot_plane_)))
+        p('__constant__ unsigned char mkb_stage_group[%d] = {%s};'
+          % (len(slot_plane_), ', '.join(str(stage_group_of(j)) for j in range(len(slot_plane_)))))
         p('')
     if min_blocks:
         p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY, %d)'
@@ -2295,41 +2315,38 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('        __syncthreads();')
         p('    }')
     n_slots = len(stage_slot)
-    n_groups = (n_slots + stage_group - 1) // stage_group
+    group_of_slot = [stage_group_of(j) for j in range(n_slots)]
+    n_groups = (max(group_of_slot) + 1) if n_slots else 0
     if stage and n_slots:
-        slot_plane = [None] * n_slots
-        for var, j in stage_slot.items():
-            slot_plane[j] = var.index()
         p('    // Staged states: the tile of every state plane but V arrives in shared')
         p('    // memory by TMA, one box per plane, in the order the equations first')
-        p('    // need them; %d arrival barriers of %d planes each. The first warp'
-          % (n_groups, stage_group))
-        p('    // issues everything now; a thread reads and updates only its own')
-        p('    // element of each plane, and the tiles go back by TMA at the end.')
+        p('    // need them, announced on %d arrival barrier(s). One thread sets the' % n_groups)
+        p('    // barriers up, then the first lane of every warp issues its share of')
+        p('    // the boxes; a thread reads and updates only its own element of each')
+        p('    // plane, and the tiles go back by TMA at the end.')
         p('    MKB_STAGE_DECL(MKB_STAGE_BYTES);')
         p('    unsigned long long* const stage_bar = (unsigned long long*)mkb_stage_mem;')
         p('    Real* const stage_base = (Real*)(mkb_stage_mem + MKB_STAGE_HEAD);')
         p('    Real* const stage_c = stage_base + ty * MKB_BX + tx;')
         p('    {')
         p('        const unsigned int t_ = ty * MKB_BX + tx;')
-        p('        if (t_ < MKB_STAGE_LANES) {')
-        p('            if (t_ == 0) {')
-        p('                for (int k_ = 0; k_ < %d; k_++) MKB_MBAR_INIT(&stage_bar[k_], 1);' % n_groups)
-        p('                MKB_MBAR_FENCE_INIT();')
+        p('        if (t_ == 0) {')
+        p('            for (int k_ = 0; k_ < %d; k_++) MKB_MBAR_INIT(&stage_bar[k_], 1);' % n_groups)
+        p('            MKB_MBAR_FENCE_INIT();')
         for gi in range(n_groups):
-            cnt = min(stage_group, n_slots - gi * stage_group)
-            p('                MKB_MBAR_EXPECT_TX(&stage_bar[%d], %du * MKB_STAGE_TILE * (unsigned int)sizeof(Real));'
-              % (gi, cnt))
-        p('            }')
-        p('            MKB_SYNCWARP();')
+            p('            MKB_MBAR_EXPECT_TX(&stage_bar[%d], %du * MKB_STAGE_TILE * (unsigned int)sizeof(Real));'
+              % (gi, group_of_slot.count(gi)))
+        p('        }')
+        p('        __syncthreads();')
+        p('        if ((t_ & 31u) == 0u) {')
         if overlap:
             p('            // (the tiles were written by the TMA unit of the previous step,')
             p('            // which this block has just observed through tile_done)')
             p('            MKB_FENCE_ASYNC_GLOBAL();')
-        p('            for (unsigned int j_ = t_; j_ < %du; j_ += MKB_STAGE_LANES)' % n_slots)
+        p('            for (unsigned int j_ = t_ >> 5; j_ < %du; j_ += MKB_STAGE_WARPS)' % n_slots)
         p('                MKB_TMA_LOAD_3D(stage_base + j_ * MKB_STAGE_TILE, g.tmap_state,')
         p('                                (int)(ix - tx), (int)(iy - ty), (int)mkb_stage_plane[j_],')
-        p('                                &stage_bar[j_ / %du]);' % stage_group)
+        p('                                &stage_bar[mkb_stage_group[j_]]);')
         p('        }')
         p('    }')
     p('    const bool active = (ix < nx) && (iy < ny);')
@@ -2521,7 +2538,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    {')
         p('        unsigned int tx_, ty_;')
         p('        MKB_ASM_SREG(tx_, "tid.x"); MKB_ASM_SREG(ty_, "tid.y");')
-        p('        if (tx_ == 0 && ty_ == 0) {')
+        p('        const unsigned int t_ = ty_ * MKB_BX + tx_;')
+        p('        if ((t_ & 31u) == 0u) {')
         p('            unsigned int bx_, by_, bz_, gy_;')
         p('            MKB_ASM_SREG(bx_, "ctaid.x"); MKB_ASM_SREG(by_, "ctaid.y"); MKB_ASM_SREG(bz_, "ctaid.z");')
         p('            MKB_ASM_SREG(gy_, "nctaid.y");')
@@ -2529,13 +2547,26 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         if slab:
             p('            const unsigned int nby_ = ((unsigned int)g.ny + MKB_BY - 1) / MKB_BY;')
             p('            row_ = (row_ == 0) ? 0 : ((row_ == 1) ? nby_ - 1 : row_ - 1);')
-        p('            Real* const base_ = (Real*)(mkb_stage_mem + MKB_STAGE_HEAD);')
-        p('            for (unsigned int j_ = 0; j_ < %du; j_++)' % n_slots)
-        p('                MKB_TMA_STORE_3D(g.tmap_state, (int)(bx_ * MKB_BX), (int)(row_ * MKB_BY),')
-        p('                                 (int)mkb_stage_plane[j_], base_ + j_ * MKB_STAGE_TILE);')
-        p('            MKB_TMA_STORE_FINISH();')
+        p('            // a tile inside the grid: every warp is still here and takes its')
+        p('            // share; a tile across the rim: thread (0, 0), which always is')
+        p('            const bool full_ = (bx_ + 1u) * MKB_BX <= (unsigned int)g.nx')
+        p('                && (row_ + 1u) * MKB_BY <= (unsigned int)g.ny;')
+        p('            const unsigned int j0_ = full_ ? (t_ >> 5) : 0u, dj_ = full_ ? MKB_STAGE_WARPS : 1u;')
+        p('            if (full_ || t_ == 0u) {')
+        p('                Real* const base_ = (Real*)(mkb_stage_mem + MKB_STAGE_HEAD);')
+        p('                for (unsigned int j_ = j0_; j_ < %du; j_ += dj_)' % n_slots)
+        p('                    MKB_TMA_STORE_3D(g.tmap_state, (int)(bx_ * MKB_BX), (int)(row_ * MKB_BY),')
+        p('                                     (int)mkb_stage_plane[j_], base_ + j_ * MKB_STAGE_TILE);')
         if overlap:
-            p('            MKB_FENCE_ASYNC_GLOBAL();')
+            p('                // (written, and visible to the next step\'s TMA loads, before')
+            p('                // the tile is published)')
+            p('                MKB_TMA_STORE_FINISH();')
+            p('                MKB_FENCE_ASYNC_GLOBAL();')
+        else:
+            p('                // (the shared memory has been read; the kernel boundary')
+            p('                // completes the writes)')
+            p('                MKB_TMA_STORE_READ_DONE();')
+        p('            }')
         p('        }')
         p('    }')
     if not (slab and not slab_lean):

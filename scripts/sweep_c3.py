@@ -14,6 +14,7 @@ B3 = dict(div_cubic=True, fast_exp='stab', fast_libm=False, select=False)
 OLD = dict(div_cubic=False, fast_libm=False, select=False)
 LM = dict(select=False)
 ND = dict(block=(128, 2), min_blocks=2, load_ahead=24, prefetch='l1', select=False)
+ST = dict(ND, stage=True, stage_group=64)
 
 
 def also(base, **kw):
@@ -210,6 +211,28 @@ SETS = {
         ('stage la4 overlap', also(ND, stage=True, load_ahead=4, overlap=True)),
         ('overlap (no stage)', also(ND, overlap=True)),
     ],
+    'r3c': [
+        ('NEW default', dict(ND)),
+        ('NEW default, 300 steps', also(ND, _steps=300)),
+        ('stage one group la4', also(ST, load_ahead=4)),
+        ('stage one group la4, 300 steps', also(ST, load_ahead=4, _steps=300)),
+        ('stage one group la2', also(ST, load_ahead=2)),
+        ('stage one group la8', also(ST, load_ahead=8)),
+        ('stage one group la24', also(ST, load_ahead=24)),
+        ('stage 8 + rest la4', also(ST, load_ahead=4, stage_group=(8,))),
+        ('stage 8 + rest la8', also(ST, load_ahead=8, stage_group=(8,))),
+        ('stage 16 + rest la4', also(ST, load_ahead=4, stage_group=(16,))),
+        ('stage 4 + 12 + rest la4', also(ST, load_ahead=4, stage_group=(4, 12))),
+        ('stage one group la4 cheap-select', also(ST, load_ahead=4, select='cheap')),
+        ('stage one group la8 cheap-select', also(ST, load_ahead=8, select='cheap')),
+        ('stage 8 + rest la4 cheap-select', also(ST, load_ahead=4, stage_group=(8,), select='cheap')),
+        ('stage one group la8 select', also(ST, load_ahead=8, select=True)),
+        ('stage one group la4 64x4', also(ST, load_ahead=4, block=(64, 4))),
+        ('stage one group la4 256x1', also(ST, load_ahead=4, block=(256, 1))),
+        ('stage one group la4 64x2 mb4', also(ST, load_ahead=4, block=(64, 2), min_blocks=4)),
+        ('stage one group la4 overlap', also(ST, load_ahead=4, overlap=True)),
+        ('stage one group la4 exp-add', also(ST, load_ahead=4, exp_scale='add')),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -218,6 +241,8 @@ s = None
 for name, opts in variants:
     if only and only not in name:
         continue
+    opts = dict(opts)
+    nsteps = opts.pop('_steps', steps)
     if s is None or not gpu:
         s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=grid if gpu else 16)
     # one simulation, re-optioned: the state stays in HBM across variants
@@ -241,7 +266,7 @@ for name, opts in variants:
         name, m.group(1) if m else '?', '/'.join(sp.groups()) if sp else '?')
     if gpu:
         try:
-            info = s.benchmark_steps(steps, warmup=3)
+            info = s.benchmark_steps(nsteps, warmup=3)
             ms = info['device_ms'] / info['steps']
             line += '  %.4f ms/step  %.3e cell-steps/s' % (ms, grid * grid / ms * 1e3)
         except Exception as e:
