@@ -1393,7 +1393,8 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
             return fail(MKB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
         }
         static_assert(sizeof(CUtensorMap) == sizeof(g.tmap_state), "tensor map size");
-        const cuuint64_t dims[3] = {s->nx, s->ny, (cuuint64_t)s->n_state};
+        // (n_state planes and the second V plane right behind them, for L2 prefetches)
+        const cuuint64_t dims[3] = {s->nx, s->ny, (cuuint64_t)s->n_state + (s->i_vm >= 0 ? 1u : 0u)};
         const cuuint64_t strides[2] = {s->nx * s->rs, s->stride * s->rs};
         const cuuint32_t box[3] = {(cuuint32_t)s->block_x, (cuuint32_t)s->block_y, 1};
         const cuuint32_t estr[3] = {1, 1, 1};

@@ -344,6 +344,11 @@ _PRELUDE = r"""
 // commit the stores issued so far and wait until they have been performed
 #define MKB_TMA_STORE_FINISH() \
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group 0;" ::: "memory")
+// the same box only as far as L2 (no destination): a hint
+#define MKB_TMA_PREFETCH_3D(tmap, cx, cy, cz) \
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" \
+                 :: "l"((unsigned long long)(tmap)), "r"(cx), "r"(cy), "r"(cz) : "memory")
+#define MKB_NSM(v) asm("mov.u32 %0, %%nsmid;" : "=r"(v))
 // commit, and wait only until the shared memory has been read
 #define MKB_TMA_STORE_READ_DONE() \
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory")
@@ -1066,7 +1071,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              div_cubic=False, prefetch=None, debug_mem=None,
              fast_libm=False, select=False, exp_scale='mul', stream=False,
              overlap=False, plane_stride=None, stage=False,
-             stage_group=8):
+             stage_group=8, stage_store=True, prefetch_next=None):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -1438,7 +1443,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
                 '    }' % rhs)
         if k == i_vm:
             return '    v_out[cid] = %s;' % rhs
-        if var in stage_slot:
+        if var in stage_slot and stage_store:
             return '    stage_c[%d * MKB_STAGE_TILE] = %s;' % (stage_slot[var], rhs)
         if debug_mem == 'l1ns':
             return '    { const Real vnew = %s; if (dt < (Real)0) MKB_AT(state_c, %d) = vnew; }' % (rhs, k)
@@ -1599,9 +1604,14 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         emit_loads(ahead, body if stage else early, True)
         early_states = set(loaded)
         gate_set_unused = set(x for x in gate_set if x not in first_use)
+        next_at = None
+        if stage and prefetch_next:
+            next_at = min(max(int(float(prefetch_next) * len(todo)), 0), len(todo) - 1)
         for i, (name, eq) in enumerate(todo):
             if name:
                 body.append('    // Component: %s' % name)
+            if i == next_at:
+                body.append('@PREFETCH_NEXT@')
             emit_loads(i + ahead, body, False)
             var = eq.lhs.var()
             body.append('    const Real %s = %s;' % (v(eq.lhs), w.ex(eq.rhs)))
@@ -2386,6 +2396,23 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     p('    // Loads issued ahead of use: fields and the first states')
     for line in early:
         p(line)
+    if stage and prefetch_next and diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD) and (
+            fields or diffusion_mode == DIFF_FIELD):
+        p('    // Hint (see the tile prefetch further down): conductances and fields of')
+        p('    // the cells whose blocks start a wave from now, as far as L2')
+        p('    {')
+        p('        unsigned int nsm_;')
+        p('        MKB_NSM(nsm_);')
+        p('        const unsigned int r_ = ((nsm_ * %du + gridDim.x - 1u) / gridDim.x) * MKB_BY;'
+          % int(min_blocks or 2))
+        p('        if (active && iy + r_ < ny) {')
+        if diffusion_mode == DIFF_FIELD:
+            p('            if (ix < nx - 1) MKB_PREFETCH_L2(gxf + (cid - iy) + (unsigned long long)r_ * (nx - 1));')
+            p('            MKB_PREFETCH_L2(gyf + cid + (unsigned long long)r_ * nx);')
+        for k in range(len(fields)):
+            p('            MKB_PREFETCH_L2(&MKB_AT(field_c, %d) + (unsigned long long)r_ * nx);' % k)
+        p('        }')
+        p('    }')
     if prefetch and lazy_state and not stage:
         p('    // The other states: only prefetched here, loaded where they are used')
         p('    if (active) {')
@@ -2524,10 +2551,39 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p(line)
     p('')
     for line in body:
+        if line == '@PREFETCH_NEXT@':
+            # The thread blocks that start when this wave retires find their
+            # tiles in L2: about a quarter of a warp's residence was the wait
+            # for its first loads from HBM (ncu, profiles/r03_summary.md). The
+            # grid is handed out in launch order, x fastest: the tile a wave
+            # ahead is `resident blocks / column blocks` block rows down.
+            p('    // Hint: bring the tiles of the blocks that start a wave from now as far as L2')
+            p('    {')
+            p('        unsigned int tx_, ty_;')
+            p('        MKB_ASM_SREG(tx_, "tid.x"); MKB_ASM_SREG(ty_, "tid.y");')
+            p('        const unsigned int t_ = ty_ * MKB_BX + tx_;')
+            p('        if ((t_ & 31u) == 0u) {')
+            p('            unsigned int bx_, by_, bz_, gy_, gx_, nsm_;')
+            p('            MKB_ASM_SREG(bx_, "ctaid.x"); MKB_ASM_SREG(by_, "ctaid.y"); MKB_ASM_SREG(bz_, "ctaid.z");')
+            p('            MKB_ASM_SREG(gy_, "nctaid.y"); MKB_ASM_SREG(gx_, "nctaid.x");')
+            p('            MKB_NSM(nsm_);')
+            p('            const unsigned int row_ = by_ + bz_ * gy_ + (nsm_ * %du + gx_ - 1u) / gx_;'
+              % int(min_blocks or 2))
+            p('            const int x_ = (int)(bx_ * MKB_BX), y_ = (int)(row_ * MKB_BY);')
+            p('            for (unsigned int j_ = t_ >> 5; j_ < %du; j_ += MKB_STAGE_WARPS)' % n_slots)
+            p('                MKB_TMA_PREFETCH_3D(g.tmap_state, x_, y_, (int)mkb_stage_plane[j_]);')
+            if diffusion and i_vm >= 0:
+                p('            // (V(t): the plane inside `state`, or the second V plane behind the states)')
+                p('            if (t_ == 0u) MKB_TMA_PREFETCH_3D(g.tmap_state, x_, y_,')
+                p('                (v_in == (const Real*)g.state + %dull * stride) ? %d : %d);'
+                  % (i_vm, i_vm, n_state))
+            p('        }')
+            p('    }')
+            continue
         p(line)
 
     def stage_epilogue():
-        if not (stage and n_slots):
+        if not (stage and n_slots and stage_store):
             return
         p('    // Staged states go back: every writer makes its shared-memory stores')
         p('    // visible to the TMA unit, the threads still here meet, and one thread')

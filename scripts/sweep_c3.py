@@ -15,6 +15,7 @@ OLD = dict(div_cubic=False, fast_libm=False, select=False)
 LM = dict(select=False)
 ND = dict(block=(128, 2), min_blocks=2, load_ahead=24, prefetch='l1', select=False)
 ST = dict(ND, stage=True, stage_group=64)
+SB = dict(ND, stage=True, stage_group=(8,), load_ahead=4, select='cheap')
 
 
 def also(base, **kw):
@@ -233,6 +234,23 @@ SETS = {
         ('stage one group la4 overlap', also(ST, load_ahead=4, overlap=True)),
         ('stage one group la4 exp-add', also(ST, load_ahead=4, exp_scale='add')),
     ],
+    'r3d': [
+        ('NEW default', dict(ND)),
+        ('stage 8+ la4 cheap', dict(SB)),
+        ('stage 8+ la4 cheap next .3', also(SB, prefetch_next=0.3)),
+        ('stage 8+ la4 cheap next .5', also(SB, prefetch_next=0.5)),
+        ('stage 8+ la4 cheap next .7', also(SB, prefetch_next=0.7)),
+        ('stage 8+ la4 cheap next .9', also(SB, prefetch_next=0.9)),
+        ('stage 8+ la4 cheap next .01', also(SB, prefetch_next=0.01)),
+        ('stage 8+ la4 cheap, direct stores', also(SB, stage_store=False)),
+        ('stage 8+ la4 cheap, direct stores, next .5', also(SB, stage_store=False, prefetch_next=0.5)),
+        ('stage 8+ la8 cheap next .5', also(SB, load_ahead=8, prefetch_next=0.5)),
+        ('stage 8+ la4 next .5', also(SB, select=False, prefetch_next=0.5)),
+        ('stage 4+12+ la4 cheap next .5', also(SB, stage_group=(4, 12), prefetch_next=0.5)),
+        ('stage one group la8 next .5', also(ST, load_ahead=8, prefetch_next=0.5)),
+        ('stage 8+ la4 cheap next .5, 300 steps', also(SB, prefetch_next=0.5, _steps=300)),
+        ('stage 8+ la4 cheap next .5 overlap', also(SB, prefetch_next=0.5, overlap=True)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -252,7 +270,7 @@ for name, opts in variants:
         fast_exp='poly', split_gates=False, div_parallel=False,
         const_div=True, fmad=True, debug_mem=None, exp_scale='mul',
         plane_stride=True, div_int_check=False, stage=False, stage_group=8,
-        overlap=False), **opts))
+        overlap=False, stage_store=True, prefetch_next=None), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:

@@ -788,3 +788,27 @@ def test_staged_states_row_slabs_equal_the_whole_grid(lean):
         assert out['halo_error'] == 0
         assert np.array_equal(out['V'], one['V'])
         assert np.array_equal(out['state'], one['state'])
+
+
+@pytest.mark.parametrize('extra', [
+    dict(stage_store=False),
+    dict(prefetch_next=0.5, stage_group=(3, 6)),
+    dict(stage_store=False, prefetch_next=0.3, select='cheap'),
+], ids=['direct_stores', 'next_wave_prefetch', 'both'])
+def test_staged_states_variants_bit_for_bit(extra):
+    # results written straight to HBM instead of through the staged tile; L2
+    # hints for the next wave's tiles (no effect on results)
+    def make(cls):
+        return workloads.c3_hetero(cls, nx=12, ny=9)
+    opts = dict(EXACT, block=(8, 4), stage=True, load_ahead=2, **extra)
+    a = make(myokit_b200.SimulationCUDA)
+    a.set_kernel_options(**opts)
+    src = a.kernel_source()
+    assert src.kernel_flags & 8
+    if 'prefetch_next' in extra:
+        assert 'MKB_TMA_PREFETCH_3D(g.tmap_state' in src.code
+    if extra.get('stage_store') is False:
+        assert 'MKB_TMA_STORE_3D(g.tmap_state' not in src.code
+    got, want, wstate = both(make, opts, 3.0, 0.5, 12, 9)
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['state'].ravel(), wstate)
