@@ -1022,12 +1022,45 @@ def default_options(precision, n_state):
                 load_ahead=24 if big else 32,
                 prefetch='l1' if big else None,
                 slab_lean=True,
+                # large models: every state plane's tile through shared memory
+                # by TMA where the grid allows (profiles/r03_sweeps.md: 0.707
+                # -> 0.652 ms on C3; SimulationCUDA.kernel_source then also
+                # loads 4 equations ahead and takes select='cheap')
+                stage=big,
+                stage_group=(8,),
                 # small models: vector path, TMA-fed where the grid allows
                 # (stencil-only on 8192 x 4096: 92-97 % of the measured copy
                 # bandwidth in double precision against 69 % without)
                 stream=n_state <= 4,
                 cells_per_thread=2 if n_state <= 4 else 1,
                 rows_per_thread=4 if n_state <= 4 else 1)
+
+
+# Shared memory two resident thread blocks of a staged kernel may take together
+# (227 KiB per SM less the V tile, the exp table and the per-block reserve)
+STAGE_SMEM_LIMIT = 106 * 1024
+
+
+def stage_applies(precision, n_state, block, diffusion_mode, nx, cells_per_thread=1,
+                  persistent=False, split_gates=False, junction=None,
+                  debug_mem=None, fast_exp=None, lazy_state=True, **ignored):
+    """
+    True if :func:`generate` can stage the states of this configuration in
+    shared memory (option ``stage``): scalar path on a regular grid or
+    uncoupled cells, rows and tile rows that are 16-byte multiples (the TMA
+    descriptor's strides and box), and a tile of all state planes small enough
+    for two resident thread blocks per SM.
+    """
+    rs = 4 if precision == myokit.SINGLE_PRECISION else 8
+    bx, by = block
+    return bool(
+        (cells_per_thread or 1) == 1 and lazy_state
+        and not (persistent or split_gates or junction or debug_mem)
+        and fast_exp != 'stab'
+        and diffusion_mode != DIFF_CONNECTIONS
+        and (nx * rs) % 16 == 0 and (bx * rs) % 16 == 0
+        and (bx * by * rs) % 128 == 0 and bx <= 256 and by <= 256
+        and n_state * bx * by * rs + 128 <= STAGE_SMEM_LIMIT)
 
 
 class KernelSource:

@@ -251,6 +251,15 @@ SETS = {
         ('stage 8+ la4 cheap next .5, 300 steps', also(SB, prefetch_next=0.5, _steps=300)),
         ('stage 8+ la4 cheap next .5 overlap', also(SB, prefetch_next=0.5, overlap=True)),
     ],
+    # small grids (SWEEP_GRID=768: the cells of a 2048 x 256 slab): overlapping steps x staging
+    'r3e': [
+        ('plain', also(ND, _steps=200)),
+        ('plain overlap', also(ND, overlap=True, _steps=200)),
+        ('stage', also(SB, _steps=200)),
+        ('stage overlap', also(SB, overlap=True, _steps=200)),
+        ('stage overlap direct stores', also(SB, overlap=True, stage_store=False, _steps=200)),
+        ('stage one group la8 overlap', also(ST, load_ahead=8, overlap=True, _steps=200)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
