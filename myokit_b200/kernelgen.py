@@ -2360,7 +2360,9 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
     n_slots = len(stage_slot)
     group_of_slot = [stage_group_of(j) for j in range(n_slots)]
     n_groups = (max(group_of_slot) + 1) if n_slots else 0
-    if stage and n_slots:
+    def stage_prologue():
+        if not (stage and n_slots):
+            return
         p('    // Staged states: the tile of every state plane but V arrives in shared')
         p('    // memory by TMA, one box per plane, in the order the equations first')
         p('    // need them, announced on %d arrival barrier(s). One thread sets the' % n_groups)
@@ -2463,30 +2465,51 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    __shared__ Real tile[MKB_BY + 2][MKB_BX + 2];')
         p('    // (only cells of the grid: the slot of a thread beyond the last row or')
         p('    // column is the halo slot of its neighbour, written below)')
-        p('    if (active) tile[ty + 1][tx + 1] = vc;')
-        p('    if (active) {')
-        p('        if (tx == 0) tile[ty + 1][0] = (ix > 0) ? MKB_LD(v_in + cid - 1) : vc;')
-        p('        if (tx == MKB_BX - 1 || ix == nx - 1)')
-        p('            tile[ty + 1][tx + 2] = (ix < nx - 1) ? MKB_LD(v_in + cid + 1) : vc;')
-        p('        if (ty == 0) {')
-        p('            Real vn = vc;')
-        p('            if (iy > 0) vn = MKB_LD(v_in + cid - nx);')
-        if slab:
-            p('            else if (iyg > 0 && g.halo_lo) vn = __ldcg((const Real*)g.halo_lo + (step % 3u) * nx + ix);')
+        lo_src = ('__ldcg((const Real*)g.halo_lo + (step % 3u) * nx + ix)' if slab
+                  else '((const Real*)g.halo_lo)[ix]')
+        hi_src = ('__ldcg((const Real*)g.halo_hi + (step % 3u) * nx + ix)' if slab
+                  else '((const Real*)g.halo_hi)[ix]')
+        if stage and n_slots:
+            # every load from HBM is in flight before the block meets to set
+            # up the arrival barriers; the tile is written after
+            p('    const bool rim_l = active && tx == 0, rim_r = active && (tx == MKB_BX - 1 || ix == nx - 1);')
+            p('    const bool rim_u = active && ty == 0, rim_d = active && (ty == MKB_BY - 1 || iy == ny - 1);')
+            p('    Real vrl = vc, vrr = vc, vru = vc, vrd = vc;')
+            p('    if (rim_l && ix > 0) vrl = MKB_LD(v_in + cid - 1);')
+            p('    if (rim_r && ix < nx - 1) vrr = MKB_LD(v_in + cid + 1);')
+            p('    if (rim_u) {')
+            p('        if (iy > 0) vru = MKB_LD(v_in + cid - nx);')
+            p('        else if (iyg > 0 && g.halo_lo) vru = %s;' % lo_src)
+            p('    }')
+            p('    if (rim_d) {')
+            p('        if (iy < ny - 1) vrd = MKB_LD(v_in + cid + nx);')
+            p('        else if (iyg < nyg - 1 && g.halo_hi) vrd = %s;' % hi_src)
+            p('    }')
+            stage_prologue()
+            p('    if (active) tile[ty + 1][tx + 1] = vc;')
+            p('    if (rim_l) tile[ty + 1][0] = vrl;')
+            p('    if (rim_r) tile[ty + 1][tx + 2] = vrr;')
+            p('    if (rim_u) tile[0][tx + 1] = vru;')
+            p('    if (rim_d) tile[ty + 2][tx + 1] = vrd;')
         else:
-            p('            else if (iyg > 0 && g.halo_lo) vn = ((const Real*)g.halo_lo)[ix];')
-        p('            tile[0][tx + 1] = vn;')
-        p('        }')
-        p('        if (ty == MKB_BY - 1 || iy == ny - 1) {')
-        p('            Real vn = vc;')
-        p('            if (iy < ny - 1) vn = MKB_LD(v_in + cid + nx);')
-        if slab:
-            p('            else if (iyg < nyg - 1 && g.halo_hi) vn = __ldcg((const Real*)g.halo_hi + (step % 3u) * nx + ix);')
-        else:
-            p('            else if (iyg < nyg - 1 && g.halo_hi) vn = ((const Real*)g.halo_hi)[ix];')
-        p('            tile[ty + 2][tx + 1] = vn;')
-        p('        }')
-        p('    }')
+            p('    if (active) tile[ty + 1][tx + 1] = vc;')
+            p('    if (active) {')
+            p('        if (tx == 0) tile[ty + 1][0] = (ix > 0) ? MKB_LD(v_in + cid - 1) : vc;')
+            p('        if (tx == MKB_BX - 1 || ix == nx - 1)')
+            p('            tile[ty + 1][tx + 2] = (ix < nx - 1) ? MKB_LD(v_in + cid + 1) : vc;')
+            p('        if (ty == 0) {')
+            p('            Real vn = vc;')
+            p('            if (iy > 0) vn = MKB_LD(v_in + cid - nx);')
+            p('            else if (iyg > 0 && g.halo_lo) vn = %s;' % lo_src)
+            p('            tile[0][tx + 1] = vn;')
+            p('        }')
+            p('        if (ty == MKB_BY - 1 || iy == ny - 1) {')
+            p('            Real vn = vc;')
+            p('            if (iy < ny - 1) vn = MKB_LD(v_in + cid + nx);')
+            p('            else if (iyg < nyg - 1 && g.halo_hi) vn = %s;' % hi_src)
+            p('            tile[ty + 2][tx + 1] = vn;')
+            p('        }')
+            p('    }')
         if stab:
             p('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
         p('    __syncthreads();')
@@ -2560,7 +2583,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('    MKB_EXP_TABLE_INIT(ty * MKB_BX + tx, MKB_BX * MKB_BY);')
             p('    __syncthreads();')
         elif stage and n_slots:
-            p('    __syncthreads();    // the arrival barriers are initialised')
+            stage_prologue()
         p('    if (!active) return;')
     p('')
 

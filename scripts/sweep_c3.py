@@ -260,6 +260,21 @@ SETS = {
         ('stage overlap direct stores', also(SB, overlap=True, stage_store=False, _steps=200)),
         ('stage one group la8 overlap', also(ST, load_ahead=8, overlap=True, _steps=200)),
     ],
+    # V and conductance loads issued before the staging barrier
+    'r3f': [
+        ('stage 8+ la4 cheap', dict(SB)),
+        ('stage 8+ la4 cheap (again)', dict(SB)),
+        ('stage 4+ la4 cheap', also(SB, stage_group=(4,))),
+        ('stage 16+ la4 cheap', also(SB, stage_group=(16,))),
+        ('stage 4+12+ la4 cheap', also(SB, stage_group=(4, 12))),
+        ('stage one group la4 cheap', also(SB, stage_group=64)),
+        ('stage 8+ la2 cheap', also(SB, load_ahead=2)),
+        ('stage 8+ la8 cheap', also(SB, load_ahead=8)),
+        ('stage 8+ la4', also(SB, select=False)),
+        ('stage 8+ la4 cheap 64x4', also(SB, block=(64, 4))),
+        ('stage 8+ la4 cheap 256x1', also(SB, block=(256, 1))),
+        ('stage 8+ la4 cheap direct stores', also(SB, stage_store=False)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
