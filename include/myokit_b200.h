@@ -180,7 +180,10 @@ typedef struct mkb_sim_config {
                                    plane in `kernel_smem_bytes` of dynamic shared memory by
                                    TMA, through the 3-d descriptor MkbGridArgs::tmap_state
                                    ([plane][row][column], box block_x x block_y x 1) */
-#define MKB_KERNEL_FLAG_SHIFT_BLOCKS 8   /* bits 8..15: thread blocks per SM (stream) */
+#define MKB_KERNEL_TILE_LOOP 16 /* with MKB_KERNEL_STAGE: a fixed grid of
+                                   min(tiles, sm_count * blocks_per_sm) thread blocks, block b
+                                   taking tiles b, b + grid, ... (x fastest) */
+#define MKB_KERNEL_FLAG_SHIFT_BLOCKS 8   /* bits 8..15: thread blocks per SM (stream, tile loop) */
 
 /* A run on the state that is already resident on the device (mkb_sim_rearm):
  * the time span, step size, protocol and log selection of mkb_sim_config. */

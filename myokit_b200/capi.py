@@ -92,6 +92,7 @@ KERNEL_PERSISTENT = 1
 KERNEL_STREAM = 2
 KERNEL_OVERLAP = 4
 KERNEL_STAGE = 8
+KERNEL_TILE_LOOP = 16
 
 
 class RunConfig(ctypes.Structure):

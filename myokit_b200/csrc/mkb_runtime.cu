@@ -1415,6 +1415,13 @@ extern "C" int mkb_sim_init(const mkb_sim_config* c, mkb_sim** out) {
             return fail(MKB_ERR_CUDA, "Staged kernel: %u bytes of shared memory per block refused (%s).",
                         s->smem_bytes, cudaGetErrorName(ea));
         }
+        if (c->kernel_flags & MKB_KERNEL_TILE_LOOP) {
+            int sms = 0;
+            INIT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+            const u64 per_sm = std::max<u64>(1, ((u64)c->kernel_flags >> MKB_KERNEL_FLAG_SHIFT_BLOCKS) & 0xff);
+            const u64 tiles = ((s->nx + s->block_x - 1) / s->block_x) * ((s->ny + s->block_y - 1) / s->block_y);
+            s->launch_grid = dim3((unsigned int)std::min<u64>(tiles, (u64)sms * per_sm), 1, 1);
+        }
         // (all of the SM's shared memory for the two resident blocks)
         cudaFuncSetAttribute((const void*)s->kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);

@@ -349,6 +349,14 @@ _PRELUDE = r"""
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" \
                  :: "l"((unsigned long long)(tmap)), "r"(cx), "r"(cy), "r"(cz) : "memory")
 #define MKB_NSM(v) asm("mov.u32 %0, %%nsmid;" : "=r"(v))
+// tile-loop kernels: commit / wait separately; per-thread asynchronous copies
+// (LDGSTS) of the next tile's membrane potentials
+#define MKB_TMA_STORE_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
+#define MKB_TMA_STORE_READ_WAIT() asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory")
+#define MKB_CP_ASYNC(dst, src) \
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" \
+                 :: "r"(MKB_SMEM_ADDR(dst)), "l"(src), "n"(sizeof(Real)) : "memory")
+#define MKB_CP_ASYNC_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 // commit, and wait only until the shared memory has been read
 #define MKB_TMA_STORE_READ_DONE() \
     asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory")
@@ -1093,6 +1101,263 @@ class KernelSource:
         return h.hexdigest()
 
 
+def _emit_tile_loop(p, L):
+    """
+    The staged kernel as a loop over tiles (option ``tile_loop``): a fixed grid
+    of ``SMs x blocks per SM`` thread blocks, block b taking tiles b, b + grid,
+    ... in launch order. What a one-tile block waits for at its start — its
+    first loads from HBM, about a third of a warp's residence (ncu,
+    profiles/r03_summary.md) — is requested one tile ahead instead:
+
+    * while tile i is computed, the membrane potentials of tile i + grid (own
+      cell and rim, per thread, LDGSTS) and the ``stage_early`` state planes
+      its equations need first (TMA) travel into the second of two small
+      buffers;
+    * the other state planes of tile i + grid are requested as soon as the
+      TMA stores of tile i have read the main buffer, and arrive while the
+      block works on the early planes;
+    * the diffusion current is formed where the equations first use it (the
+      update of V, at the end), so its conductances are loaded late and never
+      waited for at the top.
+
+    Same arithmetic in the same order as the one-tile kernel: same bits.
+    ``L`` is the local namespace of :func:`generate`.
+    """
+    bx, by = L['bx'], L['by']
+    stage_slot, stage_sizes = L['stage_slot'], L['stage_sizes']
+    diffusion_mode, diffusion = L['diffusion_mode'], L['diffusion']
+    fields, consts, body = L['fields'], L['consts'], L['body']
+    plane_stride, min_blocks = L['plane_stride'], L['min_blocks']
+    paced_list, i_vm, n_state = L['paced_list'], L['i_vm'], L['n_state']
+    load_ahead = max(int(L['load_ahead']), 0)
+    n_slots = len(stage_slot)
+    ne = min(stage_sizes[0], n_slots)
+    nm = n_slots - ne
+    grid = diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD)
+    p('#define MKB_STAGE_EARLY %d' % ne)
+    p('#define MKB_STAGE_AT(j) (*((j) < MKB_STAGE_EARLY ? early_c + (j) * MKB_STAGE_TILE'
+      ' : main_c + ((j) - MKB_STAGE_EARLY) * MKB_STAGE_TILE))')
+    p('#define MKB_STAGE_WAIT(k) do { if ((k) == 0) MKB_MBAR_WAIT(&stage_bar[1 + pb_], pe_);'
+      ' else MKB_MBAR_WAIT(&stage_bar[0], pm_); } while (0)')
+    p('')
+    p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY, %d)' % int(min_blocks or 2))
+    p('%s(const __grid_constant__ MkbGridArgs g, const MkbStepParams* __restrict__ sp,' % KERNEL_NAME)
+    p('    const Real* __restrict__ v_in, Real* __restrict__ v_out)')
+    p('{')
+    p('    const unsigned int tx = threadIdx.x, ty = threadIdx.y;')
+    p('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+    if plane_stride:
+        p('    constexpr unsigned long long stride = %dull;' % int(plane_stride))
+        p('    if (g.stride != stride) { MKB_STRIDE_MISMATCH(); return; }')
+    else:
+        p('    const unsigned long long stride = g.stride;')
+    p('    const unsigned int nbx = (nx + MKB_BX - 1) / MKB_BX;')
+    p('    const unsigned int ntiles = nbx * ((ny + MKB_BY - 1) / MKB_BY);')
+    p('    if (blockIdx.x >= ntiles) return;')
+    p('    const unsigned int t_ = ty * MKB_BX + tx;')
+    p('    const bool lane0_ = (t_ & 31u) == 0u;')
+    p('    Real* const state = (Real*)g.state;')
+    p('    // Per-step scalars, cast like openclsim.c:1063,1148,1155')
+    p('    const Real time = (Real)sp->time;')
+    p('    const Real dt = (Real)sp->dt;')
+    p('    const Real pace_in = (Real)sp->pace;')
+    p('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
+    p('    (void)time; (void)pace_in; (void)store_aux; (void)v_in; (void)v_out; (void)stride; (void)state;')
+    p('    // Shared memory: arrival barriers (main, early[2]); the main buffer (%d' % nm)
+    p('    // state planes of this tile); two early buffers (%d planes each: this' % ne)
+    p('    // tile\'s and the next one\'s); two V tiles with their rims.')
+    p('    MKB_STAGE_DECL(MKB_LOOP_BYTES);')
+    p('    unsigned long long* const stage_bar = (unsigned long long*)mkb_stage_mem;')
+    p('    Real* const main_base = (Real*)(mkb_stage_mem + 128);')
+    p('    Real* const early_base = main_base + %d * MKB_STAGE_TILE;' % nm)
+    if grid:
+        p('    __shared__ Real tile2[2][MKB_BY + 2][MKB_BX + 2];')
+    p('    if (t_ == 0) {')
+    p('        for (int k_ = 0; k_ < 3; k_++) MKB_MBAR_INIT(&stage_bar[k_], MKB_STAGE_WARPS);')
+    p('        MKB_MBAR_FENCE_INIT();')
+    p('    }')
+    p('    __syncthreads();')
+
+    def request_early(tile, buf):
+        # V of the tile (own cell and rim) by per-thread asynchronous copies,
+        # its early planes by TMA, into buffer `buf`
+        p('        {')
+        p('            const unsigned int byr_ = %s / nbx, bxb_ = %s - byr_ * nbx;' % (tile, tile))
+        if grid:
+            p('            const unsigned int ix_ = bxb_ * MKB_BX + tx, iy_ = byr_ * MKB_BY + ty;')
+            p('            if (ix_ < nx && iy_ < ny) {')
+            p('                const Real* const vs_ = v_in + ((unsigned long long)iy_ * nx + ix_);')
+            p('                Real (*const tl_)[MKB_BX + 2] = tile2[%s];' % buf)
+            p('                MKB_CP_ASYNC(&tl_[ty + 1][tx + 1], vs_);')
+            p('                // (a rim slot outside the grid takes the cell\'s own V and is never used)')
+            p('                if (tx == 0) MKB_CP_ASYNC(&tl_[ty + 1][0], (ix_ > 0) ? vs_ - 1 : vs_);')
+            p('                if (tx == MKB_BX - 1 || ix_ == nx - 1)')
+            p('                    MKB_CP_ASYNC(&tl_[ty + 1][tx + 2], (ix_ < nx - 1) ? vs_ + 1 : vs_);')
+            p('                if (ty == 0) {')
+            p('                    const Real* src_ = vs_;')
+            p('                    if (iy_ > 0) src_ = vs_ - nx;')
+            p('                    else if (g.iy_offset > 0 && g.halo_lo) src_ = (const Real*)g.halo_lo + ix_;')
+            p('                    MKB_CP_ASYNC(&tl_[0][tx + 1], src_);')
+            p('                }')
+            p('                if (ty == MKB_BY - 1 || iy_ == ny - 1) {')
+            p('                    const Real* src_ = vs_;')
+            p('                    if (iy_ < ny - 1) src_ = vs_ + nx;')
+            p('                    else if (g.iy_offset + iy_ < g.ny_global - 1 && g.halo_hi) src_ = (const Real*)g.halo_hi + ix_;')
+            p('                    MKB_CP_ASYNC(&tl_[ty + 2][tx + 1], src_);')
+            p('                }')
+            p('            }')
+        p('            if (lane0_) {')
+        p('                unsigned int n_ = 0;')
+        p('                for (unsigned int j_ = t_ >> 5; j_ < %du; j_ += MKB_STAGE_WARPS) n_++;' % ne)
+        p('                MKB_MBAR_EXPECT_TX(&stage_bar[1 + %s], n_ * MKB_STAGE_TILE * (unsigned int)sizeof(Real));' % buf)
+        p('                for (unsigned int j_ = t_ >> 5; j_ < %du; j_ += MKB_STAGE_WARPS)' % ne)
+        p('                    MKB_TMA_LOAD_3D(early_base + (%s * %du + j_) * MKB_STAGE_TILE, g.tmap_state,' % (buf, ne))
+        p('                                    (int)(bxb_ * MKB_BX), (int)(byr_ * MKB_BY), (int)mkb_stage_plane[j_],')
+        p('                                    &stage_bar[1 + %s]);' % buf)
+        p('            }')
+        p('        }')
+
+    p('    // the first tile\'s early data')
+    p('    {')
+    request_early('blockIdx.x', '0u')
+    p('    }')
+    p('    unsigned int it_ = 0;')
+    p('    for (unsigned int tile_ = blockIdx.x; tile_ < ntiles; tile_ += gridDim.x, it_++) {')
+    p('        // buffer and barrier phases of this tile')
+    p('        const unsigned int pb_ = it_ & 1u, pm_ = it_ & 1u, pe_ = (it_ >> 1) & 1u;')
+    p('        const unsigned int byr = tile_ / nbx, bxb = tile_ - byr * nbx;')
+    p('        const unsigned int ix = bxb * MKB_BX + tx, iy = byr * MKB_BY + ty;')
+    p('        const bool active = (ix < nx) && (iy < ny);')
+    p('        const unsigned long long cid = (unsigned long long)iy * nx + ix;')
+    p('        Real* const state_c = state + cid;')
+    p('        const Real* const field_c = (const Real*)g.field + cid;')
+    p('        Real* const inter_c = (Real*)g.inter + cid;')
+    p('        (void)state_c; (void)field_c; (void)inter_c;')
+    p('        Real* const main_c = main_base + t_;')
+    p('        Real* const early_c = early_base + pb_ * %du * MKB_STAGE_TILE + t_;' % ne)
+    p('        (void)main_c; (void)early_c;')
+    p('        // This thread\'s copies of V have landed; the stores of the previous tile')
+    p('        // have read the buffers; then the block meets.')
+    p('        MKB_CP_ASYNC_WAIT();')
+    p('        if (lane0_) MKB_TMA_STORE_READ_WAIT();')
+    p('        __syncthreads();')
+    p('        if (lane0_) {')
+    p('            unsigned int n_ = 0;')
+    p('            for (unsigned int j_ = %du + (t_ >> 5); j_ < %du; j_ += MKB_STAGE_WARPS) n_++;' % (ne, n_slots))
+    p('            MKB_MBAR_EXPECT_TX(&stage_bar[0], n_ * MKB_STAGE_TILE * (unsigned int)sizeof(Real));')
+    p('            for (unsigned int j_ = %du + (t_ >> 5); j_ < %du; j_ += MKB_STAGE_WARPS)' % (ne, n_slots))
+    p('                MKB_TMA_LOAD_3D(main_base + (j_ - %du) * MKB_STAGE_TILE, g.tmap_state,' % ne)
+    p('                                (int)(bxb * MKB_BX), (int)(byr * MKB_BY), (int)mkb_stage_plane[j_],')
+    p('                                &stage_bar[0]);')
+    p('        }')
+    p('        // the next tile\'s early data, into the other buffers')
+    p('        if (tile_ + gridDim.x < ntiles) {')
+    request_early('(tile_ + gridDim.x)', '(pb_ ^ 1u)')
+    p('        }')
+    p('        if (active) {')
+    if grid:
+        p('        Real (*const tile)[MKB_BX + 2] = tile2[pb_];')
+        p('        const Real vc = tile[ty + 1][tx + 1];')
+        p('        const unsigned int iyg = iy + (unsigned int)g.iy_offset;  // global row')
+        p('        const unsigned int nyg = (unsigned int)g.ny_global;')
+        p('        (void)nyg;')
+    for k, var in enumerate(fields):
+        pass
+    for line in L['early']:
+        p('    ' + line)
+    if diffusion:
+        p('        // openclsim.cl:249-280, 322-329')
+        if paced_list:
+            p('        const Real pace = g.paced_mask[cid] ? pace_in : (Real)0;')
+        else:
+            p('        const int pix = (int)ix, piy = (int)iyg;')
+            p('        const Real pace = (pix >= (int)g.pace_x0 && pix < (int)g.pace_x1 &&')
+            p('                           piy >= (int)g.pace_y0 && piy < (int)g.pace_y1) ? pace_in : (Real)0;')
+    else:
+        p('        const Real pace = pace_in;')
+    p('        (void)pace;')
+    for line in consts:
+        p('    ' + line)
+
+    # the diffusion current, where the equations first need it
+    dblock = []
+    d = dblock.append
+    if grid:
+        d('        // Diffusion current of this cell (formed here, where it is first used)')
+        d('        Real idiff;')
+        d('        {')
+        d('            const Real vxm = tile[ty + 1][tx], vxp = tile[ty + 1][tx + 2];')
+        d('            const Real vym = tile[ty][tx + 1], vyp = tile[ty + 2][tx + 1];')
+        if diffusion_mode == DIFF_HOMOGENEOUS:
+            d('            // openclsim.cl:401-434 (diff_step)')
+            d('            const Real gx = (Real)g.gx, gy = (Real)g.gy;')
+            d('            if (nx > 1) {')
+            d('                if (ix == 0) idiff = gx * (vc - vxp);')
+            d('                else if (ix == nx - 1) idiff = gx * (vc - vxm);')
+            d('                else idiff = gx * (2 * vc - vxm - vxp);')
+            d('            } else {')
+            d('                idiff = 0;')
+            d('            }')
+            d('            if (nyg > 1) {')
+            d('                if (iyg == 0) idiff += gy * (vc - vyp);')
+            d('                else if (iyg == nyg - 1) idiff += gy * (vc - vym);')
+            d('                else idiff += gy * (2 * vc - vym - vyp);')
+            d('            }')
+        else:
+            d('            // openclsim.cl:469-486 (diff_hetero); gx[(ny, nx-1)], gy[(ny-1, nx)]')
+            d('            const Real* const gxf = (const Real*)g.gx_field;')
+            d('            const Real* const gyf = (const Real*)g.gy_field;')
+            d('            const bool has_xm = nx > 1 && ix > 0, has_xp = nx > 1 && ix < nx - 1;')
+            d('            const bool has_ym = nyg > 1 && iyg > 0, has_yp = nyg > 1 && iyg < nyg - 1;')
+            d('            const Real gxm = has_xm ? gxf[cid - iy - 1] : (Real)0;')
+            d('            const Real gxp = has_xp ? gxf[cid - iy] : (Real)0;')
+            d('            const Real gym = has_ym ? gyf[(long long)cid - (long long)nx] : (Real)0;')
+            d('            const Real gyp = has_yp ? gyf[cid] : (Real)0;')
+            d('            idiff = 0.0;')
+            d('            if (has_xm) { idiff += gxm * (vc - vxm); }')
+            d('            if (has_xp) { idiff += gxp * (vc - vxp); }')
+            d('            if (has_ym) idiff += gym * (vc - vym);')
+            d('            if (has_yp) idiff += gyp * (vc - vyp);')
+        d('        }')
+        d('        if (store_aux) ((Real*)g.idiff)[cid] = idiff;')
+    first = None
+    if dblock:
+        import re as _re
+        for i, line in enumerate(body):
+            if _re.search(r'\bidiff\b', line):
+                first = i
+                break
+        if first is None:
+            first = len(body)
+    for i, line in enumerate(body):
+        if dblock and i == first:
+            for x in dblock:
+                p(x)
+        if line == '@PREFETCH_NEXT@':
+            continue
+        for x in line.split('\n'):
+            p('    ' + x)
+    if dblock and first == len(body):
+        for x in dblock:
+            p(x)
+    p('        }   // active')
+    p('        // The tile goes back: stores visible to the TMA unit, the block meets,')
+    p('        // the first lane of every warp issues its share of the boxes.')
+    p('        MKB_FENCE_ASYNC_SMEM();')
+    p('        __syncthreads();')
+    p('        if (lane0_) {')
+    p('            for (unsigned int j_ = t_ >> 5; j_ < %du; j_ += MKB_STAGE_WARPS)' % n_slots)
+    p('                MKB_TMA_STORE_3D(g.tmap_state, (int)(bxb * MKB_BX), (int)(byr * MKB_BY), (int)mkb_stage_plane[j_],')
+    p('                    (j_ < %du) ? early_base + (pb_ * %du + j_) * MKB_STAGE_TILE' % (ne, ne))
+    p('                               : main_base + (j_ - %du) * MKB_STAGE_TILE);' % ne)
+    p('            MKB_TMA_STORE_COMMIT();')
+    p('        }')
+    p('    }')
+    p('    if (lane0_) MKB_TMA_STORE_READ_WAIT();')
+    p('}')
+    p('')
+
+
 def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              diffusion_mode, paced_list, block, native_maths=False, fmad=True,
              max_registers=None, pow_multiply=True, fast_div=False,
@@ -1104,7 +1369,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              div_cubic=False, prefetch=None, debug_mem=None,
              fast_libm=False, select=False, exp_scale='mul', stream=False,
              overlap=False, plane_stride=None, stage=False,
-             stage_group=8, stage_store=True, prefetch_next=None):
+             stage_group=8, stage_store=True, prefetch_next=None,
+             tile_loop=False, stage_early=4):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -1292,6 +1558,12 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         and diffusion_mode != DIFF_CONNECTIONS
         and (bx * rs_) % 16 == 0 and (bx * by * rs_) % 128 == 0
         and bx <= 256 and by <= 256)
+    # Staged kernel as a loop over tiles (see the emitter below): plain grids
+    # and uncoupled cells on one GPU, steps that do not overlap
+    tile_loop = bool(tile_loop) and stage and stage_store and not (
+        slab or overlap or partitioned or junction)
+    if tile_loop:
+        stage_group = (max(int(stage_early or 4), 1),)
     if isinstance(stage_group, (tuple, list)):
         # explicit group sizes; the last group takes what is left
         stage_sizes = [max(int(x), 1) for x in stage_group]
@@ -1428,8 +1700,8 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             lines = []
             if stage_group_of(j) not in stage_waited:
                 stage_waited.add(stage_group_of(j))
-                lines.append('    MKB_MBAR_WAIT(&stage_bar[%d], 0u);' % stage_group_of(j))
-            lines.append('    const Real %s = stage_c[%d * MKB_STAGE_TILE];' % (v(var), j))
+                lines.append('    MKB_STAGE_WAIT(%d);' % stage_group_of(j))
+            lines.append('    const Real %s = MKB_STAGE_AT(%d);' % (v(var), j))
             return '\n'.join(lines)
         src = 'MKB_LD(&MKB_AT(state_c, %d))' % k
         if debug_mem:
@@ -1477,7 +1749,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         if k == i_vm:
             return '    v_out[cid] = %s;' % rhs
         if var in stage_slot and stage_store:
-            return '    stage_c[%d * MKB_STAGE_TILE] = %s;' % (stage_slot[var], rhs)
+            return '    MKB_STAGE_AT(%d) = %s;' % (stage_slot[var], rhs)
         if debug_mem == 'l1ns':
             return '    { const Real vnew = %s; if (dt < (Real)0) MKB_AT(state_c, %d) = vnew; }' % (rhs, k)
         return '    MKB_AT(state_c, %d) = %s;' % (k, rhs)
@@ -2282,7 +2554,26 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
           % (len(slot_plane_), ', '.join(str(x) for x in slot_plane_)))
         p('__constant__ unsigned char mkb_stage_group[%d] = {%s};'
           % (len(slot_plane_), ', '.join(str(stage_group_of(j)) for j in range(len(slot_plane_)))))
+        if tile_loop:
+            p('#define MKB_LOOP_BYTES %d' % (
+                128 + (len(stage_slot) + min(stage_sizes[0], len(stage_slot))) * bx * by * rs_))
+        if not tile_loop:
+            p('#define MKB_STAGE_AT(j) stage_c[(j) * MKB_STAGE_TILE]')
+            p('#define MKB_STAGE_WAIT(k) MKB_MBAR_WAIT(&stage_bar[k], 0u)')
         p('')
+    if tile_loop and stage_slot:
+        _emit_tile_loop(
+            p, locals())
+        code = '\n'.join(out)
+        options = ['--fmad=true' if fmad else '--fmad=false']
+        ks = KernelSource(code, block, n_state, i_vm, len(inter_log),
+                          len(fields), diffusion_mode, options)
+        ks.plane_stride = int(plane_stride or 0)
+        ne_ = stage_sizes[0]
+        ks.smem_bytes = 128 + (len(stage_slot) + min(ne_, len(stage_slot))) * bx * by * rs_
+        # MKB_KERNEL_STAGE | MKB_KERNEL_TILE_LOOP, thread blocks per SM
+        ks.kernel_flags = 8 | 16 | (int(min_blocks or 2) << 8)
+        return ks
     if min_blocks:
         p('extern "C" __global__ void __launch_bounds__(MKB_BX * MKB_BY, %d)'
           % int(min_blocks))

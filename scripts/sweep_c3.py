@@ -275,6 +275,20 @@ SETS = {
         ('stage 8+ la4 cheap 256x1', also(SB, block=(256, 1))),
         ('stage 8+ la4 cheap direct stores', also(SB, stage_store=False)),
     ],
+    # the staged kernel as a loop over tiles (next tile's V and first planes requested a tile ahead)
+    'r3g': [
+        ('stage 8+ la4 cheap', dict(SB)),
+        ('tile loop early 4 la4 cheap', also(SB, tile_loop=True)),
+        ('tile loop early 4 la2 cheap', also(SB, tile_loop=True, load_ahead=2)),
+        ('tile loop early 4 la8 cheap', also(SB, tile_loop=True, load_ahead=8)),
+        ('tile loop early 2 la4 cheap', also(SB, tile_loop=True, stage_early=2)),
+        ('tile loop early 3 la4 cheap', also(SB, tile_loop=True, stage_early=3)),
+        ('tile loop early 5 la4 cheap', also(SB, tile_loop=True, stage_early=5)),
+        ('tile loop early 4 la4', also(SB, tile_loop=True, select=False)),
+        ('tile loop early 4 la4 cheap 256x1', also(SB, tile_loop=True, block=(256, 1))),
+        ('tile loop early 4 la4 cheap 64x4', also(SB, tile_loop=True, block=(64, 4))),
+        ('tile loop early 4 la4 cheap, 300 steps', also(SB, tile_loop=True, _steps=300)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -294,7 +308,8 @@ for name, opts in variants:
         fast_exp='poly', split_gates=False, div_parallel=False,
         const_div=True, fmad=True, debug_mem=None, exp_scale='mul',
         plane_stride=True, div_int_check=False, stage=False, stage_group=8,
-        overlap=False, stage_store=True, prefetch_next=None), **opts))
+        overlap=False, stage_store=True, prefetch_next=None, tile_loop=False,
+        stage_early=4), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:

@@ -95,7 +95,7 @@ def run_on_host(sim, duration, log_interval=1.0, inter_log=(), contract=None,
     lib.shim_set_thread_order(1 if reverse else 0)
     lib.shim_set_persistent(1 if getattr(src, 'persistent', False) else 0)
     # streaming kernels: a persistent grid of a few blocks walks all tiles
-    lib.shim_set_stream_blocks(stream_blocks if (src.kernel_flags & 2) else 0)
+    lib.shim_set_stream_blocks(stream_blocks if (src.kernel_flags & (2 | 16)) else 0)
     nx, ny = sim._nx, sim._ny
     if getattr(src, 'persistent', False):
         assert nx <= src.block[0] and ny <= src.block[1]

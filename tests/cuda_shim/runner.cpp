@@ -65,6 +65,12 @@ void shim_barrier() {
     swapcontext(&g_cur->ctx, &g_sched);
 }
 
+// a thread that polls (an arrival barrier another thread has yet to serve)
+// lets the others run and comes back
+void shim_yield() {
+    swapcontext(&g_cur->ctx, &g_sched);
+}
+
 int shim_barrier_or(int pred) {
     g_or_acc |= (pred != 0);
     shim_barrier();
@@ -103,8 +109,13 @@ void run_block(std::vector<Fiber>& fibers, std::vector<char>& stacks, unsigned i
             g_cur = &f;
             swapcontext(&g_sched, &f.ctx);
         }
-        for (unsigned int t = 0; t < nthreads; t++) alive = alive || !fibers[t].done;
+        bool polling = false;
+        for (unsigned int t = 0; t < nthreads; t++) {
+            alive = alive || !fibers[t].done;
+            polling = polling || (!fibers[t].done && !fibers[t].waiting);
+        }
         if (!alive) break;
+        if (polling) continue;      // somebody yielded: another round before any barrier opens
         // every thread that has not exited is waiting: release the barrier
         g_or_res = g_or_acc;
         g_or_acc = 0;

@@ -812,3 +812,52 @@ def test_staged_states_variants_bit_for_bit(extra):
     got, want, wstate = both(make, opts, 3.0, 0.5, 12, 9)
     assert np.array_equal(got['V'], want['membrane.V'])
     assert np.array_equal(got['state'].ravel(), wstate)
+
+
+@pytest.mark.parametrize('nx,ny,block,early', [(24, 16, (8, 4), 4), (20, 9, (8, 2), 3), (16, 30, (16, 2), 1)])
+def test_staged_tile_loop_kernel_bit_for_bit(nx, ny, block, early):
+    # option tile_loop: a fixed number of thread blocks (three here) walks the
+    # tiles, the next tile's membrane potentials and first state planes
+    # requested while this one is computed; 4-10 tiles per block, ragged rims
+    def make(cls):
+        return workloads.c3_hetero(cls, nx=nx, ny=ny)
+    opts = dict(EXACT, block=block, stage=True, load_ahead=2, tile_loop=True,
+                stage_early=early, overlap=False)
+    a = make(myokit_b200.SimulationCUDA)
+    a.set_kernel_options(**opts)
+    src = a.kernel_source()
+    assert src.kernel_flags & 8 and src.kernel_flags & 16
+    assert 'MKB_CP_ASYNC(&tl_' in src.code
+    got, want, wstate = both(make, opts, 3.0, 0.5, nx, ny)
+    assert want['membrane.V'].max() > 0
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+    b = make(myokit_b200.SimulationCUDA)
+    b.set_kernel_options(**opts)
+    rev = cuda_shim.run_on_host(b, 3.0, log_interval=0.5, reverse=True)
+    assert np.array_equal(rev['state'], got['state'])
+
+
+def test_staged_tile_loop_uncoupled_and_homogeneous():
+    m, p, _ = myokit.load('example')
+
+    def pop(cls):
+        s = cls(m, p, ncells=100, diffusion=False, precision=DP, rl=True)
+        s.set_field('ina.gNa', np.linspace(8, 16, 100))
+        return s
+    opts = dict(EXACT, block=(16, 1), stage=True, tile_loop=True, overlap=False)
+    a = pop(myokit_b200.SimulationCUDA)
+    a.set_kernel_options(**opts)
+    assert a.kernel_source().kernel_flags & 16
+    got = cuda_shim.run_on_host(a, 2.0, log_interval=0.5)
+    log, ostate = pop(OracleSimulation).run(2.0, log=['engine.time'], log_interval=0.5)
+    assert np.array_equal(got['state'].ravel(), np.asarray(ostate))
+    # homogeneous conduction, logged intermediary
+    got, want, wstate = both(lr91_2d, dict(EXACT, block=(4, 2), stage=True, tile_loop=True,
+                                           overlap=False), 5.0, 0.5, 10, 7,
+                             inter_log=['ina.INa'])
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['inter'][:, 0], want['ina.INa'])
+    assert np.array_equal(got['state'].ravel(), wstate)

@@ -803,3 +803,32 @@ def test_staged_states_uncoupled_and_cable():
     a.run(5, log=myokit.LOG_NONE)
     b.run(5, log=myokit.LOG_NONE)
     assert np.array_equal(a.state_array(), b.state_array())
+
+
+def test_staged_tile_loop_kernel_equals_the_plain_kernel():
+    # kernelgen tile_loop=True: a fixed grid of thread blocks walks the tiles;
+    # the next tile's V (LDGSTS) and first state planes (TMA) are requested
+    # while this one is computed, arrival barriers change phase every tile.
+    # 1000 x 203 under 128 x 2 tiles: 816 tiles for 296 blocks (2-3 tiles per
+    # block), ragged in both directions. Same arithmetic, so the same bits.
+    nx, ny = 1000, 203
+
+    def make(cls, **opts):
+        s = workloads.c3_hetero(cls, nx=nx, ny=ny)
+        if opts:
+            s.set_kernel_options(**opts)
+        return s
+    a = make(myokit_b200.SimulationCUDA, tile_loop=True, overlap=False, fmad=False)
+    src = a.kernel_source()
+    assert src.kernel_flags & 16 and src.kernel_flags & 8
+    b = make(myokit_b200.SimulationCUDA, stage=False, overlap=False, fmad=False)
+    ta, fa = a.run_fields(3, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    tb, fb = b.run_fields(3, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    assert fb['membrane.V'].max() > 0
+    for k in fb:
+        assert np.array_equal(fa[k], fb[k]), k
+    assert np.array_equal(a.state_array(), b.state_array())
+    ta, fa = a.run_fields(1, ['membrane.V'], log_interval=0.5)
+    tb, fb = b.run_fields(1, ['membrane.V'], log_interval=0.5)
+    assert np.array_equal(fa['membrane.V'], fb['membrane.V'])
+    assert np.array_equal(a.state_array(), b.state_array())
