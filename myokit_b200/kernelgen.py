@@ -1279,7 +1279,10 @@ def _emit_tile_loop(p, L):
     for line in consts:
         p('    ' + line)
 
-    # the diffusion current, where the equations first need it
+    # the diffusion current, where the equations first need it; its
+    # conductances are requested `cond_ahead` statements earlier
+    cond_ahead = 40
+    dloads = []
     dblock = []
     d = dblock.append
     if grid:
@@ -1304,15 +1307,17 @@ def _emit_tile_loop(p, L):
             d('                else idiff += gy * (2 * vc - vym - vyp);')
             d('            }')
         else:
-            d('            // openclsim.cl:469-486 (diff_hetero); gx[(ny, nx-1)], gy[(ny-1, nx)]')
-            d('            const Real* const gxf = (const Real*)g.gx_field;')
-            d('            const Real* const gyf = (const Real*)g.gy_field;')
-            d('            const bool has_xm = nx > 1 && ix > 0, has_xp = nx > 1 && ix < nx - 1;')
-            d('            const bool has_ym = nyg > 1 && iyg > 0, has_yp = nyg > 1 && iyg < nyg - 1;')
-            d('            const Real gxm = has_xm ? gxf[cid - iy - 1] : (Real)0;')
-            d('            const Real gxp = has_xp ? gxf[cid - iy] : (Real)0;')
-            d('            const Real gym = has_ym ? gyf[(long long)cid - (long long)nx] : (Real)0;')
-            d('            const Real gyp = has_yp ? gyf[cid] : (Real)0;')
+            d('            // openclsim.cl:469-486 (diff_hetero)')
+            dl = dloads.append
+            dl('        // Edge conductances gx[(ny, nx-1)], gy[(ny-1, nx)], ahead of the diffusion current')
+            dl('        const Real* const gxf = (const Real*)g.gx_field;')
+            dl('        const Real* const gyf = (const Real*)g.gy_field;')
+            dl('        const bool has_xm = nx > 1 && ix > 0, has_xp = nx > 1 && ix < nx - 1;')
+            dl('        const bool has_ym = nyg > 1 && iyg > 0, has_yp = nyg > 1 && iyg < nyg - 1;')
+            dl('        const Real gxm = has_xm ? gxf[cid - iy - 1] : (Real)0;')
+            dl('        const Real gxp = has_xp ? gxf[cid - iy] : (Real)0;')
+            dl('        const Real gym = has_ym ? gyf[(long long)cid - (long long)nx] : (Real)0;')
+            dl('        const Real gyp = has_yp ? gyf[cid] : (Real)0;')
             d('            idiff = 0.0;')
             d('            if (has_xm) { idiff += gxm * (vc - vxm); }')
             d('            if (has_xp) { idiff += gxp * (vc - vxp); }')
@@ -1330,6 +1335,9 @@ def _emit_tile_loop(p, L):
         if first is None:
             first = len(body)
     for i, line in enumerate(body):
+        if dloads and i == max(first - cond_ahead, 0):
+            for x in dloads:
+                p(x)
         if dblock and i == first:
             for x in dblock:
                 p(x)
@@ -1338,7 +1346,7 @@ def _emit_tile_loop(p, L):
         for x in line.split('\n'):
             p('    ' + x)
     if dblock and first == len(body):
-        for x in dblock:
+        for x in dloads + dblock:
             p(x)
     p('        }   // active')
     p('        // The tile goes back: stores visible to the TMA unit, the block meets,')
