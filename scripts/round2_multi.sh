@@ -2,7 +2,7 @@
 # Runs on an N-GPU box (gpurun --gpus N): multi-GPU tests on distinct devices, the bench at N (and below), slab overhead.
 N=${1:-2}
 ONLY=${2:-"1 2 4 8"}   # which GPU counts to bench
-O=gpurun_out/r02
+O=gpurun_out/${OUT:-r02}
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 nvidia-smi -L | head -8

@@ -4,10 +4,12 @@ sys.path.insert(0, os.getcwd())
 import myokit_b200
 from myokit_b200 import workloads, multigpu, capi
 ny = int(sys.argv[1]) if len(sys.argv) > 1 else 512          # rows of the whole grid: two slabs of ny / 2
-variants = [('default', {}), ('la16', dict(load_ahead=16)), ('la32', dict(load_ahead=32)), ('la20', dict(load_ahead=20)),
-            ('64x4', dict(block=(64, 4))), ('64x4 la16', dict(block=(64, 4), load_ahead=16)),
-            ('pf l2', dict(prefetch='l2')), ('no overlap', dict(overlap=False)), ('not lean', dict(slab_lean=False)),
-            ('256x1', dict(block=(256, 1)))]
+variants = [('default', {}), ('no overlap', dict(overlap=False)), ('overlap', dict(overlap=True)),
+            ('no stage', dict(stage=False)), ('no stage, no overlap', dict(stage=False, overlap=False)),
+            ('no stage, overlap', dict(stage=False, overlap=True)),
+            ('direct stores', dict(stage_store=False)), ('direct stores, no overlap', dict(stage_store=False, overlap=False)),
+            ('one group la8', dict(stage_group=64, load_ahead=8)),
+            ('not lean', dict(slab_lean=False)), ('256x1', dict(block=(256, 1)))]
 ndev = capi.device_count()
 def work(comm):
     out = []
