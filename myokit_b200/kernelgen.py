@@ -1161,8 +1161,8 @@ def _emit_tile_loop(p, L):
     p('    const Real time = (Real)sp->time;')
     p('    const Real dt = (Real)sp->dt;')
     p('    const Real pace_in = (Real)sp->pace;')
-    p('    const bool store_aux = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
-    p('    (void)time; (void)pace_in; (void)store_aux; (void)v_in; (void)v_out; (void)stride; (void)state;')
+    p('    const bool store_aux_ = (sp->flags & MKB_FLAG_STORE_AUX) != 0;')
+    p('    (void)time; (void)pace_in; (void)store_aux_; (void)v_in; (void)v_out; (void)stride; (void)state;')
     p('    // Shared memory: arrival barriers (main, early[2]); the main buffer (%d' % nm)
     p('    // state planes of this tile); two early buffers (%d planes each: this' % ne)
     p('    // tile\'s and the next one\'s); two V tiles with their rims.')
@@ -1254,7 +1254,18 @@ def _emit_tile_loop(p, L):
     p('        if (tile_ + gridDim.x < ntiles) {')
     request_early('(tile_ + gridDim.x)', '(pb_ ^ 1u)')
     p('        }')
-    p('        if (active) {')
+    p('        // Every thread takes the step, also those of a rim tile that lie outside')
+    p('        // the grid (their states arrive as zeros, their results are clipped, their')
+    p('        // accesses to global memory are predicated): the body stays uniform')
+    p('        // control flow, in which ptxas keeps the constants in uniform registers —')
+    p('        // inside `if (active)` it copies them to ordinary ones, some twenty')
+    p('        // registers that the schedule of the FP64 chains then lacks.')
+    p('        {')
+    p('        const bool store_aux = store_aux_ && active;')
+    p('        (void)store_aux;')
+    kernel_p = p
+    active_lines = []
+    p = active_lines.append
     if grid:
         p('        Real (*const tile)[MKB_BX + 2] = tile2[pb_];')
         p('        const Real vc = tile[ty + 1][tx + 1];')
@@ -1268,7 +1279,7 @@ def _emit_tile_loop(p, L):
     if diffusion:
         p('        // openclsim.cl:249-280, 322-329')
         if paced_list:
-            p('        const Real pace = g.paced_mask[cid] ? pace_in : (Real)0;')
+            p('        const Real pace = (active && g.paced_mask[cid]) ? pace_in : (Real)0;')
         else:
             p('        const int pix = (int)ix, piy = (int)iyg;')
             p('        const Real pace = (pix >= (int)g.pace_x0 && pix < (int)g.pace_x1 &&')
@@ -1312,8 +1323,8 @@ def _emit_tile_loop(p, L):
             dl('        // Edge conductances gx[(ny, nx-1)], gy[(ny-1, nx)], ahead of the diffusion current')
             dl('        const Real* const gxf = (const Real*)g.gx_field;')
             dl('        const Real* const gyf = (const Real*)g.gy_field;')
-            dl('        const bool has_xm = nx > 1 && ix > 0, has_xp = nx > 1 && ix < nx - 1;')
-            dl('        const bool has_ym = nyg > 1 && iyg > 0, has_yp = nyg > 1 && iyg < nyg - 1;')
+            dl('        const bool has_xm = active && nx > 1 && ix > 0, has_xp = active && nx > 1 && ix < nx - 1;')
+            dl('        const bool has_ym = active && nyg > 1 && iyg > 0, has_yp = active && nyg > 1 && iyg < nyg - 1;')
             dl('        const Real gxm = has_xm ? gxf[cid - iy - 1] : (Real)0;')
             dl('        const Real gxp = has_xp ? gxf[cid - iy] : (Real)0;')
             dl('        const Real gym = has_ym ? gyf[(long long)cid - (long long)nx] : (Real)0;')
@@ -1344,9 +1355,18 @@ def _emit_tile_loop(p, L):
         if line == '@PREFETCH_NEXT@':
             continue
         for x in line.split('\n'):
+            if x.startswith('    v_out[cid] = '):
+                x = '    if (active) ' + x.strip()
             p('    ' + x)
     if dblock and first == len(body):
         for x in dloads + dblock:
+            p(x)
+    p = kernel_p
+    if L.get('tile_call'):
+        p('            mkb_tile_body(g, tx, ty, ix, iy, active, pb_, pe_, pm_, time, dt, pace_in, store_aux,')
+        p('                          v_out, %s, main_c, early_c);' % ('&tile2[0][0][0]' if grid else '(Real*)0'))
+    else:
+        for x in active_lines:
             p(x)
     p('        }   // active')
     p('        // The tile goes back: stores visible to the TMA unit, the block meets,')
@@ -1364,6 +1384,46 @@ def _emit_tile_loop(p, L):
     p('    if (lane0_) MKB_TMA_STORE_READ_WAIT();')
     p('}')
     p('')
+    if not L.get('tile_call'):
+        return []
+    # One cell's step as a function of its own: ptxas schedules a loop body
+    # with far fewer independent chains in flight than straight-line code
+    # (r03_tile_loop.md: 36 % of the FP64 instructions two or fewer
+    # instructions behind their producer, against 20 %).
+    F = []
+    q = F.append
+    q('static __device__ __noinline__ void mkb_tile_body(')
+    q('    const MkbGridArgs& g, const unsigned int tx, const unsigned int ty,')
+    q('    const unsigned int ix, const unsigned int iy, const bool active, const unsigned int pb_,')
+    q('    const unsigned int pe_, const unsigned int pm_, const Real time, const Real dt,')
+    q('    const Real pace_in, const bool store_aux, Real* __restrict__ v_out, Real* const tile2_,')
+    q('    Real* __restrict__ const main_c, Real* __restrict__ const early_c)')
+    q('{')
+    q('    const unsigned int nx = (unsigned int)g.nx, ny = (unsigned int)g.ny;')
+    if plane_stride:
+        q('    constexpr unsigned long long stride = %dull;' % int(plane_stride))
+    else:
+        q('    const unsigned long long stride = g.stride;')
+    q('    (void)time; (void)pace_in; (void)store_aux; (void)stride; (void)ny; (void)tile2_;')
+    q('    const unsigned int t_ = ty * MKB_BX + tx;')
+    q('    const unsigned long long cid = (unsigned long long)iy * nx + ix;')
+    q('    Real* const state = (Real*)g.state;')
+    q('    Real* const state_c = state + cid;')
+    q('    const Real* const field_c = (const Real*)g.field + cid;')
+    q('    Real* const inter_c = (Real*)g.inter + cid;')
+    q('    (void)state_c; (void)field_c; (void)inter_c;')
+    q('    MKB_STAGE_DECL(MKB_LOOP_BYTES);')
+    q('    unsigned long long* const stage_bar = (unsigned long long*)mkb_stage_mem;')
+    q('    // (the two buffers never overlap: told to the compiler, which otherwise')
+    q('    // keeps every shared-memory load behind every earlier store)')
+    q('    (void)main_c; (void)early_c; (void)stage_bar; (void)t_;')
+    if grid:
+        q('    Real (*const tile2)[MKB_BY + 2][MKB_BX + 2] = (Real (*)[MKB_BY + 2][MKB_BX + 2])tile2_;')
+    for x in active_lines:
+        q(x)
+    q('}')
+    q('')
+    return F
 
 
 def generate(model, precision, bound_variables, inter_log, fields, rl_states,
@@ -1378,7 +1438,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              fast_libm=False, select=False, exp_scale='mul', stream=False,
              overlap=False, plane_stride=None, stage=False,
              stage_group=8, stage_store=True, prefetch_next=None,
-             tile_loop=False, stage_early=4):
+             tile_loop=False, stage_early=4, tile_call=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -2570,8 +2630,14 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('#define MKB_STAGE_WAIT(k) MKB_MBAR_WAIT(&stage_bar[k], 0u)')
         p('')
     if tile_loop and stage_slot:
-        _emit_tile_loop(
-            p, locals())
+        kernel_lines = []
+        fn_lines = _emit_tile_loop(kernel_lines.append, locals())
+        for x in kernel_lines[:3]:      # (the macros of this form)
+            p(x)
+        for x in fn_lines:
+            p(x)
+        for x in kernel_lines[3:]:
+            p(x)
         code = '\n'.join(out)
         options = ['--fmad=true' if fmad else '--fmad=false']
         ks = KernelSource(code, block, n_state, i_vm, len(inter_log),

@@ -289,6 +289,20 @@ SETS = {
         ('tile loop early 4 la4 cheap 64x4', also(SB, tile_loop=True, block=(64, 4))),
         ('tile loop early 4 la4 cheap, 300 steps', also(SB, tile_loop=True, _steps=300)),
     ],
+    # loop over tiles, body in uniform control flow
+    'r3i': [
+        ('stage 8+ la4 cheap', dict(SB)),
+        ('tile loop early 4 la4 cheap', also(SB, tile_loop=True)),
+        ('tile loop early 4 la2 cheap', also(SB, tile_loop=True, load_ahead=2)),
+        ('tile loop early 4 la8 cheap', also(SB, tile_loop=True, load_ahead=8)),
+        ('tile loop early 3 la4 cheap', also(SB, tile_loop=True, stage_early=3)),
+        ('tile loop early 5 la4 cheap', also(SB, tile_loop=True, stage_early=5)),
+        ('tile loop early 4 la4', also(SB, tile_loop=True, select=False)),
+        ('tile loop early 4 la4 select', also(SB, tile_loop=True, select=True)),
+        ('tile loop early 4 la4 cheap 64x4', also(SB, tile_loop=True, block=(64, 4))),
+        ('tile loop early 4 la4 cheap call', also(SB, tile_loop=True, tile_call=True)),
+        ('tile loop early 4 la4 cheap, 300 steps', also(SB, tile_loop=True, _steps=300)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -309,7 +323,7 @@ for name, opts in variants:
         const_div=True, fmad=True, debug_mem=None, exp_scale='mul',
         plane_stride=True, div_int_check=False, stage=False, stage_group=8,
         overlap=False, stage_store=True, prefetch_next=None, tile_loop=False,
-        stage_early=4), **opts))
+        stage_early=4, tile_call=False), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:
