@@ -21,6 +21,13 @@ if 'plain' in which:
     s = workloads.c3_hetero(S, nx=72, ny=20)
     t, f = s.run_fields(0.7, ['membrane.V', 'membrane.i_diff', 'ikr.IKr'], log_interval=0.25)
     print('plain', f['membrane.V'].shape, s.last_run_info()['kernel_launches'])
+if 'loop' in which:
+    # the staged kernel as a loop over tiles: 396 tiles of 128 x 2 for 296 blocks, ragged rims
+    s = workloads.c3_hetero(S, nx=328, ny=66)
+    s.set_kernel_options(tile_loop=True, overlap=False)
+    assert s.kernel_source().kernel_flags & 16
+    t, f = s.run_fields(0.4, ['membrane.V', 'membrane.i_diff'], log_interval=0.2)
+    print('loop', f['membrane.V'].shape, s.last_run_info()['kernel_launches'])
 if 'vector' in which:
     s = workloads.stencil_only(S, 136, 37, precision=SP, hetero=True)
     s.set_kernel_options(stream=False)
