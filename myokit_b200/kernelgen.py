@@ -1438,7 +1438,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
              fast_libm=False, select=False, exp_scale='mul', stream=False,
              overlap=False, plane_stride=None, stage=False,
              stage_group=8, stage_store=True, prefetch_next=None,
-             tile_loop=False, stage_early=4, tile_call=False):
+             tile_loop=False, stage_early=4, tile_call=False, v_direct=False):
     """
     Generates the fused cell-step kernel for a prepared ``model`` (bindings
     processed and unique names created, ``openclsim.py:284-290``).
@@ -2823,7 +2823,41 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         p('    }')
     p('')
 
-    if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
+    v_direct = bool(v_direct) and stage and n_slots and diffusion_mode in (
+        DIFF_HOMOGENEOUS, DIFF_FIELD) and not stab
+    if v_direct:
+        # No V tile: a thread takes the potentials left and right of its cell
+        # from the neighbouring lanes of its warp (the first and last lane
+        # from memory) and those above and below from memory (rows another
+        # warp of the block loads at the same moment: one request to L2), so
+        # nothing is written to shared memory, read back, or waited for at a
+        # block barrier before the first equation.
+        lo_src = ('__ldcg((const Real*)g.halo_lo + (step % 3u) * nx + ix)' if slab
+                  else '((const Real*)g.halo_lo)[ix]')
+        hi_src = ('__ldcg((const Real*)g.halo_hi + (step % 3u) * nx + ix)' if slab
+                  else '((const Real*)g.halo_hi)[ix]')
+        p('    // V(t) of the four neighbours: lanes of the warp left and right, memory')
+        p('    // above and below. A neighbour outside the grid leaves the cell\'s own V,')
+        p('    // which the edge formulas below never use (as openclsim.cl).')
+        p('    Real vxm = vc, vxp = vc, vym = vc, vyp = vc;')
+        p('    {')
+        p('        const unsigned int lane_ = (ty * MKB_BX + tx) & 31u;')
+        p('        const Real left_ = MKB_SHFL_UP(vc, 1), right_ = MKB_SHFL_DOWN(vc, 1);')
+        p('        if (active) {')
+        p('            if (ix > 0) vxm = (lane_ > 0u && tx > 0u) ? left_ : MKB_LD(v_in + cid - 1);')
+        p('            if (ix < nx - 1) vxp = (lane_ < 31u && tx < MKB_BX - 1) ? right_ : MKB_LD(v_in + cid + 1);')
+        p('            if (iy > 0) vym = MKB_LD(v_in + cid - nx);')
+        p('            else if (iyg > 0 && g.halo_lo) vym = %s;' % lo_src)
+        p('            if (iy < ny - 1) vyp = MKB_LD(v_in + cid + nx);')
+        p('            else if (iyg < nyg - 1 && g.halo_hi) vyp = %s;' % hi_src)
+        p('        }')
+        p('    }')
+        stage_prologue()
+        if slab and not slab_lean:
+            p('    if (active) {')
+        else:
+            p('    if (!active) return;')
+    if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD) and not v_direct:
         p('    // V(t) tile + one-cell halo in shared memory. Out-of-grid halo')
         p('    // entries hold the cell\'s own V and are never used: the edge')
         p('    // formulas below drop those terms exactly as openclsim.cl does.')
@@ -2884,6 +2918,7 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
             p('    if (!active) return;')
         p('    const Real vxm = tile[ty + 1][tx], vxp = tile[ty + 1][tx + 2];')
         p('    const Real vym = tile[ty][tx + 1], vyp = tile[ty + 2][tx + 1];')
+    if diffusion_mode in (DIFF_HOMOGENEOUS, DIFF_FIELD):
         p('    Real idiff;')
         if diffusion_mode == DIFF_HOMOGENEOUS:
             p('    // openclsim.cl:401-434 (diff_step)')

@@ -303,6 +303,20 @@ SETS = {
         ('tile loop early 4 la4 cheap call', also(SB, tile_loop=True, tile_call=True)),
         ('tile loop early 4 la4 cheap, 300 steps', also(SB, tile_loop=True, _steps=300)),
     ],
+    # no V tile: left / right neighbours by warp shuffle, above / below from memory
+    'r3j': [
+        ('stage 8+ la4 cheap', dict(SB)),
+        ('v_direct', also(SB, v_direct=True)),
+        ('v_direct (again)', also(SB, v_direct=True)),
+        ('v_direct 256x1', also(SB, v_direct=True, block=(256, 1))),
+        ('v_direct 64x4', also(SB, v_direct=True, block=(64, 4))),
+        ('v_direct 4+', also(SB, v_direct=True, stage_group=(4,))),
+        ('v_direct one group', also(SB, v_direct=True, stage_group=64)),
+        ('v_direct la2', also(SB, v_direct=True, load_ahead=2)),
+        ('v_direct la8', also(SB, v_direct=True, load_ahead=8)),
+        ('v_direct, 300 steps', also(SB, v_direct=True, _steps=300)),
+        ('stage 8+ la4 cheap, 300 steps', also(SB, _steps=300)),
+    ],
 }
 variants = SETS[os.environ.get('SWEEP_SET', 'r2a')]
 only = os.environ.get('SWEEP_ONLY')
@@ -323,7 +337,7 @@ for name, opts in variants:
         const_div=True, fmad=True, debug_mem=None, exp_scale='mul',
         plane_stride=True, div_int_check=False, stage=False, stage_group=8,
         overlap=False, stage_store=True, prefetch_next=None, tile_loop=False,
-        stage_early=4, tile_call=False), **opts))
+        stage_early=4, tile_call=False, v_direct=False), **opts))
     src = s.kernel_source()
     t0 = time.time()
     try:

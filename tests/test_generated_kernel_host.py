@@ -861,3 +861,44 @@ def test_staged_tile_loop_uncoupled_and_homogeneous():
     assert np.array_equal(got['idiff'], want['membrane.i_diff'])
     assert np.array_equal(got['inter'][:, 0], want['ina.INa'])
     assert np.array_equal(got['state'].ravel(), wstate)
+
+
+@pytest.mark.parametrize('block,nx,ny', [((8, 4), 12, 9), ((32, 2), 40, 5), ((64, 1), 70, 3), ((8, 2), 10, 5)])
+def test_staged_kernel_neighbours_by_shuffle_bit_for_bit(block, nx, ny):
+    # option v_direct: no V tile in shared memory — left / right neighbours from
+    # the adjacent lanes of the warp, above / below from memory; blocks narrower
+    # and wider than a warp, rows that end inside a warp
+    def make(cls):
+        return workloads.c3_hetero(cls, nx=nx, ny=ny)
+    opts = dict(EXACT, block=block, stage=True, load_ahead=2, v_direct=True)
+    a = make(myokit_b200.SimulationCUDA)
+    a.set_kernel_options(**opts)
+    src = a.kernel_source()
+    assert src.kernel_flags & 8 and 'MKB_SHFL_UP(vc, 1)' in src.code
+    assert '__shared__ Real tile[' not in src.code
+    got, want, wstate = both(make, opts, 3.0, 0.5, nx, ny)
+    assert want['membrane.V'].max() > 0
+    assert np.array_equal(got['V'], want['membrane.V'])
+    assert np.array_equal(got['idiff'], want['membrane.i_diff'])
+    assert np.array_equal(got['state'].ravel(), wstate)
+    b = make(myokit_b200.SimulationCUDA)
+    b.set_kernel_options(**opts)
+    rev = cuda_shim.run_on_host(b, 3.0, log_interval=0.5, reverse=True)
+    assert np.array_equal(rev['state'], got['state'])
+
+
+def test_staged_kernel_neighbours_by_shuffle_row_slabs():
+    def make(comm):
+        kw = {} if comm is None else dict(comm=comm)
+        return workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=12, ny=11, **kw)
+    opts = dict(EXACT, block=(8, 4))
+    whole = make(None)
+    whole.set_kernel_options(**opts)
+    one = cuda_shim.run_on_host(whole, 3.0, log_interval=0.5)
+    for lean in (False, True):
+        out = cuda_shim.run_slabs_on_host(
+            make, 3, 3.0, 0.5, dict(opts, slab_lean=lean, stage=True, v_direct=True, overlap=True),
+            reverse=lean)
+        assert out['halo_error'] == 0
+        assert np.array_equal(out['V'], one['V'])
+        assert np.array_equal(out['state'], one['state'])

@@ -832,3 +832,23 @@ def test_staged_tile_loop_kernel_equals_the_plain_kernel():
     tb, fb = b.run_fields(1, ['membrane.V'], log_interval=0.5)
     assert np.array_equal(fa['membrane.V'], fb['membrane.V'])
     assert np.array_equal(a.state_array(), b.state_array())
+
+
+@pytest.mark.parametrize('overlap', [False, True], ids=['serial', 'overlap'])
+def test_staged_kernel_neighbours_by_shuffle_equal_the_plain_kernel(overlap):
+    # kernelgen v_direct=True: no V tile in shared memory (left / right from the
+    # adjacent lanes, above / below from memory); ragged 200 x 37 grid
+    def make(cls, **opts):
+        s = workloads.c3_hetero(cls, nx=200, ny=37)
+        s.set_kernel_options(**opts)
+        return s
+    a = make(myokit_b200.SimulationCUDA, stage=True, v_direct=True, overlap=overlap, fmad=False)
+    src = a.kernel_source()
+    assert src.kernel_flags & 8 and 'MKB_SHFL_UP(vc, 1)' in src.code
+    b = make(myokit_b200.SimulationCUDA, stage=False, overlap=False, fmad=False)
+    ta, fa = a.run_fields(4, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    tb, fb = b.run_fields(4, ['membrane.V', 'membrane.i_diff'], log_interval=0.5)
+    assert fb['membrane.V'].max() > 0
+    for k in fb:
+        assert np.array_equal(fa[k], fb[k]), k
+    assert np.array_equal(a.state_array(), b.state_array())
