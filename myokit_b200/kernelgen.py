@@ -1036,6 +1036,9 @@ def default_options(precision, n_state):
                 # loads 4 equations ahead and takes select='cheap')
                 stage=big,
                 stage_group=(8,),
+                # ... and without a V tile: neighbours from the adjacent lanes
+                # and from memory (0.647 -> 0.638 ms)
+                v_direct=big,
                 # small models: vector path, TMA-fed where the grid allows
                 # (stencil-only on 8192 x 4096: 92-97 % of the measured copy
                 # bandwidth in double precision against 69 % without)
@@ -1539,6 +1542,25 @@ def generate(model, precision, bound_variables, inter_log, fields, rl_states,
         kernel: plane addresses become base + constant. The kernel traps on
         any other ``MkbGridArgs::stride``; ``KernelSource.plane_stride``
         tells the runtime (``mkb_sim_config::kernel_stride``).
+    ``stage`` / ``stage_group`` / ``stage_store``
+        The thread block's tile of every state plane but V staged in shared
+        memory by TMA (see the main kernel's prologue; :func:`stage_applies`):
+        ``stage_group`` planes per arrival barrier, or explicit group sizes
+        ``(first, second, ...)`` with the last group taking the rest;
+        ``stage_store=False`` writes results with plain stores instead of TMA
+        stores (better where steps overlap).
+    ``v_direct``
+        Staged kernels: no V tile in shared memory; a thread takes the
+        potentials left and right of its cell from the adjacent lanes of its
+        warp and those above and below from memory.
+    ``tile_loop`` / ``stage_early`` / ``tile_call``
+        The staged kernel as a loop over tiles (:func:`_emit_tile_loop`),
+        ``stage_early`` state planes requested a tile ahead; ``tile_call``
+        puts the per-cell step into a function of its own. Measured slower
+        than the one-tile kernel; not a default.
+    ``prefetch_next``
+        Staged kernels: L2 hints for the tiles of the next wave of thread
+        blocks, issued at this fraction of the equations. Measured slower.
     ``div_cubic``
         ``mkb_div`` with one third-order refinement of the reciprocal and no
         residual correction: 4 FP64 instructions instead of 6, IEEE results
