@@ -679,3 +679,31 @@ def test_host_state_stays_one_cell_until_cells_differ():
     s.set_default_state([2.0] * n, 0, 0)
     assert s.default_state(0, 0) == [2.0] * n and s.default_state(1, 0) == [1.0] * n
     assert len(s.default_state()) == 5 * 4 * n
+
+
+def test_stage_applies_where_tma_can_describe_the_tile_and_two_blocks_fit():
+    from myokit_b200 import kernelgen
+    DP, SP = myokit.DOUBLE_PRECISION, myokit.SINGLE_PRECISION
+    H = kernelgen.DIFF_HOMOGENEOUS
+    assert kernelgen.stage_applies(DP, 48, (128, 2), H, 2048)
+    assert kernelgen.stage_applies(DP, 48, (128, 2), kernelgen.DIFF_NONE, 1000)
+    assert not kernelgen.stage_applies(DP, 48, (128, 2), H, 2047)          # rows not 16-byte multiples
+    assert not kernelgen.stage_applies(SP, 48, (128, 2), H, 2050)
+    assert kernelgen.stage_applies(SP, 48, (128, 2), H, 2052)
+    assert not kernelgen.stage_applies(DP, 48, (128, 2), kernelgen.DIFF_CONNECTIONS, 2048)
+    assert not kernelgen.stage_applies(DP, 48, (128, 2), H, 2048, cells_per_thread=2)
+    assert not kernelgen.stage_applies(DP, 48, (128, 2), H, 2048, persistent=True)
+    assert not kernelgen.stage_applies(DP, 48, (128, 2), H, 2048, junction='fiber')
+    assert not kernelgen.stage_applies(DP, 60, (128, 2), H, 2048)          # 120 KB: two blocks do not fit
+    assert kernelgen.stage_applies(DP, 60, (128, 1), H, 2048)
+    assert not kernelgen.stage_applies(DP, 48, (4, 2), H, 2048)            # 64-byte tile planes
+    # what SimulationCUDA derives from it
+    from myokit_b200 import workloads
+    s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=64, ny=24)
+    src = s.kernel_source()
+    assert src.kernel_flags & capi.KERNEL_STAGE and src.smem_bytes == 128 + 47 * 64 * 4 * 8
+    assert src.plane_stride == 64 * 24 and 'MKB_SHFL_UP(vc, 1)' in src.code
+    s.set_kernel_options(stage=False)
+    src = s.kernel_source()
+    assert not (src.kernel_flags & capi.KERNEL_STAGE) and src.smem_bytes == 0
+    assert 'MKB_PREFETCH_L' in src.code         # the plain kernel's own defaults are back

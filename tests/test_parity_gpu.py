@@ -852,3 +852,27 @@ def test_staged_kernel_neighbours_by_shuffle_equal_the_plain_kernel(overlap):
     for k in fb:
         assert np.array_equal(fa[k], fb[k]), k
     assert np.array_equal(a.state_array(), b.state_array())
+
+
+def test_staged_states_logged_every_step():
+    # the log gather kernels read state planes the step kernel wrote by TMA
+    # the launch before (only the kernel boundary orders them): states and
+    # intermediaries of a few cells, every step, graph replays included
+    def make(cls, **opts):
+        s = workloads.c3_hetero(cls, nx=200, ny=37)
+        s.set_kernel_options(**opts)
+        return s
+    keys = ['engine.time']
+    for x, y in ((0, 0), (199, 36), (127, 1), (128, 2), (64, 20)):
+        for name in ('membrane.V', 'ina.m', 'calcium.uCa_i', 'ikr.IKr', 'membrane.i_diff'):
+            keys.append('%d.%d.%s' % (x, y, name))
+    a = make(myokit_b200.SimulationCUDA, stage=True, fmad=False)
+    assert a.kernel_source().kernel_flags & 8
+    b = make(myokit_b200.SimulationCUDA, stage=False, fmad=False)
+    da = a.run(1.5, log=keys, log_interval=0.005)
+    db = b.run(1.5, log=keys, log_interval=0.005)
+    assert len(da['engine.time']) == 300
+    for k in keys:
+        assert np.array_equal(np.asarray(da[k]), np.asarray(db[k])), k
+    assert np.asarray(da['0.0.membrane.V']).max() > 0
+    assert np.array_equal(a.state_array(), b.state_array())
