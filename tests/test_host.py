@@ -707,3 +707,47 @@ def test_stage_applies_where_tma_can_describe_the_tile_and_two_blocks_fit():
     src = s.kernel_source()
     assert not (src.kernel_flags & capi.KERNEL_STAGE) and src.smem_bytes == 0
     assert 'MKB_PREFETCH_L' in src.code         # the plain kernel's own defaults are back
+
+
+def test_staged_kernel_forms_compile_and_use_the_tma_unit(tmp_path):
+    # cross-compiled for sm_100a here (no GPU): the SASS must hold the TMA
+    # loads / stores, the arrival-barrier waits, the warp shuffles of the
+    # neighbour exchange and, for the tile loop, the asynchronous copies
+    import subprocess
+
+    def sass(opts, comm=None, nx=2048, ny=None):
+        kw = {} if comm is None else dict(comm=comm)
+        s = workloads.c3_hetero(myokit_b200.SimulationCUDA, nx=nx, ny=ny or nx, **kw)
+        s.set_kernel_options(**opts)
+        src = s.kernel_source()
+        cubin, log = capi.jit_compile(src.code, src.options + ('--ptxas-options=-v',))
+        path = tmp_path / 'k.cubin'
+        path.write_bytes(cubin)
+        text = subprocess.check_output(['cuobjdump', '-sass', str(path)]).decode()
+        return src, log, text
+    # what bench.py runs on one GPU
+    src, log, text = sass({})
+    assert src.kernel_flags == capi.KERNEL_STAGE and src.plane_stride == 2048 * 2048
+    assert 'UTMALDG.3D' in text and 'UTMASTG.3D' in text and 'SYNCS' in text
+    assert 'SHFL.UP' in text and 'SHFL.DOWN' in text
+    assert 'Used 128 registers' in log or 'Used 127 registers' in log
+    m = re.search(r'(\d+) bytes spill stores', log)
+    assert int(m.group(1)) <= 16                        # (the plain kernel: 156)
+    assert 'CCTL' not in text                            # no software prefetch left
+    # small grids: steps overlap, results leave by plain stores
+    src, log, text = sass({}, nx=512)
+    assert src.kernel_flags == capi.KERNEL_STAGE | capi.KERNEL_OVERLAP
+    assert 'UTMALDG.3D' in text and 'UTMASTG' not in text
+    # the loop over tiles
+    src, log, text = sass(dict(tile_loop=True))
+    assert src.kernel_flags & capi.KERNEL_TILE_LOOP and (src.kernel_flags >> 8) == 2
+    assert 'LDGSTS' in text and 'UTMALDG.3D' in text and 'UTMASTG.3D' in text
+    # two resident blocks fit: dynamic + static shared memory + 1 KiB each
+    static = int(re.search(r'(\d+) bytes smem', log).group(1))
+    assert 2 * (src.smem_bytes + static + 1024) <= 233472
+    # the plain kernel, compiled for its stride
+    src, log, text = sass(dict(stage=False))
+    assert src.kernel_flags == 0 and 'UTMALDG' not in text and 'CCTL' in text
+    assert 'constexpr unsigned long long stride = 4194304ull;' in src.code
+    src, log, text = sass(dict(stage=False, plane_stride=False))
+    assert src.plane_stride == 0 and 'const unsigned long long stride = g.stride;' in src.code
